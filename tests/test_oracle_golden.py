@@ -1,0 +1,93 @@
+"""The oracle restatement (oracle/cfd_oracle.py) against golden vectors produced by the
+reference's own code (oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import cfd_oracle
+import golden_util as gu
+
+
+@pytest.mark.parametrize('name', gu.step_cases())
+@pytest.mark.parametrize('prec', ['f32', 'f64'])
+def test_step_matches_reference(name, prec):
+  rec = gu.load(name)
+  dtype = np.float32 if prec == 'f32' else np.float64
+  # f32: same arithmetic as the reference up to reassociation -> a few ulp; f64: 1e-12 class,
+  # except that `diagonals` are complex64 in both (fast_diagonalization.py:214) -> ~1e-7.
+  tol = 2e-6 if prec == 'f32' else 1e-6
+  d = rec['ndim']
+  v = tuple(rec[f'v0_{i}'].astype(dtype) for i in range(d))
+  forcing = gu.oracle_forcing(rec, dtype)
+  a, b = gu.TABLEAUS[rec['stepper']]
+  diag = cfd_oracle.pinv_diagonals(rec['shape'], rec['h'], np.float32)
+  done = 0
+  for n in rec['nsteps']:
+    for _ in range(n - done):
+      if rec['stepper'] == 'forward_euler':
+        out = cfd_oracle.step(v, rec['dt'], rec['h'], rec['density'], rec['viscosity'], forcing,
+                              diag=diag, return_q=True, return_ustar=True)
+        if done == 0:
+          vnew, q, ustar = out
+          for i in range(d):
+            assert gu.rel_l2(ustar[i], rec[f'{prec}_ustar_{i}']) < tol
+          assert gu.rel_l2(q, rec[f'{prec}_q']) < 10 * tol
+        v = out[0]
+      else:
+        v = cfd_oracle.rk_step(v, rec['dt'], rec['h'], a, b, rec['density'], rec['viscosity'],
+                               forcing, diag=diag)
+      done += 1
+    for i in range(d):
+      assert v[i].dtype == dtype
+      err = gu.rel_l2(v[i], rec[f'{prec}_v{n}_{i}'])
+      assert err < tol * max(1, n), (name, n, i, err)
+
+
+@pytest.mark.parametrize('name', ['k2d_64x32', 'k2d_32x64_rho', 'tg2d_32', 's3d_16x8x32_kolm'])
+def test_constant_forcing_field_bit_exact(name):
+  """Forcing and grid-indexing logic reproduced bit-exactly (forcings.py:63-104, 35-60)."""
+  rec = gu.load(name)
+  f = [t for t in gu.oracle_forcing(rec).terms if t[0] == 'const']
+  assert len(f) == 1
+  for i, a in enumerate(f[0][1]):
+    ref = rec[f'f32_constforce_{i}']
+    assert a.dtype == np.float32 and ref.dtype == np.float32
+    np.testing.assert_array_equal(a, ref)
+
+
+@pytest.mark.parametrize('name', ['proj2d_64x32', 'proj3d_16x8x32', 'proj2d_step1_30x20'])
+def test_projection_matches_reference(name):
+  rec = gu.load(name)
+  d = rec['ndim']
+  for prec, dtype in (('f32', np.float32), ('f64', np.float64)):
+    v = tuple(rec[f'v0_{i}'].astype(dtype) for i in range(d))
+    vp, q = cfd_oracle.projection(v, rec['h'])
+    assert gu.rel_l2(q, rec[f'{prec}_q']) < 2e-6
+    for i in range(d):
+      assert gu.rel_l2(vp[i], rec[f'{prec}_proj_{i}']) < 2e-6
+    div = cfd_oracle.divergence(vp, rec['h'])
+    assert np.abs(div).max() < 1e-4 * max(1.0, np.abs(np.asarray(v)).max() / min(rec['h']))
+
+
+def test_shift_kat():
+  """boundaries_test.py:170-209."""
+  a = np.array([11, 12, 13, 14])
+  np.testing.assert_array_equal(cfd_oracle.shift(a, +1, 0), [12, 13, 14, 11])
+  np.testing.assert_array_equal(cfd_oracle.shift(a, -1, 0), [14, 11, 12, 13])
+  np.testing.assert_array_equal(cfd_oracle.shift(a, +2, 0), [13, 14, 11, 12])
+
+
+def test_cell_faces_kat():
+  """grids.py:567-572."""
+  assert cfd_oracle.cell_faces(2) == ((1.0, 0.5), (0.5, 1.0))
+  assert cfd_oracle.cell_faces(3) == ((1.0, 0.5, 0.5), (0.5, 1.0, 0.5), (0.5, 0.5, 1.0))
+
+
+def test_pinv_poisson_kat():
+  """fast_diagonalization_test.py:58-67: A x == b - mean(b)."""
+  rs = np.random.RandomState(0)
+  shape, h = (16, 12), (0.5, 0.25)
+  b = rs.standard_normal(shape)
+  diag = cfd_oracle.pinv_diagonals(shape, h, np.float64)
+  x = np.fft.irfftn(diag * np.fft.rfftn(b), s=shape, axes=(0, 1))
+  ax = cfd_oracle.laplacian(x, h)
+  np.testing.assert_allclose(ax, b - b.mean(), atol=1e-5)
