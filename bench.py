@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the staggered-grid FVM time step on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload K8192|D2048|E1024|K256]
+  python bench.py --impl reference ...     # the CPU implementation (oracle port) timed beside it
+
+A "step" is one forward-Euler projection step (explicit terms + pressure projection) of the whole
+grid.  `value` has the state resident in HBM; `e2e` goes through the public host-array API with
+H2D/D2H copies of the full state inside every timed step.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TWO_PI = 2 * np.pi
+WORKLOADS = {
+    # name: shape, batch, viscosity, vmax, forcing, description
+    'K8192': dict(shape=(8192, 8192), batch=1, nu=1e-4, vmax=7.0, kolmogorov=True, kpeak=4,
+                  desc='2D Kolmogorov flow 8192x8192 (scale 1, k 4, linear -0.1, nu 1e-4), float32'),
+    'D2048': dict(shape=(2048, 2048), batch=1, nu=1e-3, vmax=2.0, kolmogorov=False, kpeak=3,
+                  desc='2D decaying turbulence 2048x2048 periodic (nu 1e-3, vmax 2), float32'),
+    'K256': dict(shape=(256, 256), batch=1, nu=1e-3, vmax=7.0, kolmogorov=True, kpeak=4,
+                 desc='demo 2D Kolmogorov flow 256x256, float32'),
+    'E1024': dict(shape=(256, 256), batch=1024, nu=1e-3, vmax=7.0, kolmogorov=True, kpeak=4,
+                  desc='ensemble of 1024 Kolmogorov 256x256 trajectories, float32'),
+}
+# algorithmic HBM bytes per cell of each kernel (its inputs read once + outputs written once)
+KERNEL_BYTES = {'explicit_2d': 20.0, 'rfft_rows': 8.0, 'xlines': 8.0, 'irfft_rows_correct': 20.0}
+STEP_BYTES_PER_CELL = 40.0  # 2-D, working set > L2
+
+
+def synth_ic(shape, batch, seed, vmax, kpeak):
+  """Filtered-noise velocity field in the spirit of initial_conditions.filtered_velocity_field
+  (log-normal spectrum peaked at kpeak), built with float32 real FFTs on all cores; it is made
+  divergence free by the device projection afterwards (see run_gpu)."""
+  import scipy.fft
+  nx, ny = shape
+  rs = np.random.RandomState(seed)
+  kx = TWO_PI * np.fft.fftfreq(nx, TWO_PI / nx)
+  ky = TWO_PI * np.fft.rfftfreq(ny, TWO_PI / ny)
+  k = np.sqrt(kx[:, None] ** 2 + ky[None, :] ** 2).astype(np.float32)
+  with np.errstate(divide='ignore', invalid='ignore'):
+    logk = np.log(k)
+    filt = np.exp(-(np.log(kpeak) + 0.25 - logk) ** 2 / 0.5 - logk) / k
+  filt[0, 0] = 0.0
+  filt = filt.astype(np.float32)
+  out = []
+  for _ in range(2):
+    comp = np.empty((batch,) + tuple(shape), np.float32)
+    for b in range(batch):
+      noise = rs.standard_normal(shape).astype(np.float32)
+      spec = scipy.fft.rfft2(noise, workers=-1)
+      spec *= filt
+      comp[b] = scipy.fft.irfft2(spec, s=shape, workers=-1)
+    comp *= np.float32(vmax / max(np.abs(comp).max(), 1e-30))
+    out.append(comp if batch > 1 else comp[0])
+  return out
+
+
+class ClockSampler(threading.Thread):
+  """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index=0):
+    super().__init__(daemon=True)
+    self.index, self.rows, self.proc = index, [], None
+
+  def run(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+           '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      for line in self.proc.stdout:
+        self.rows.append([x.strip() for x in line.split(',')])
+    except Exception:
+      pass
+
+  def stop(self):
+    if self.proc is not None:
+      self.proc.terminate()
+    sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+    mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = sorted({n for r in self.rows if len(r) >= 7 for n, f in zip(names, r[3:7]) if f == 'Active'})
+    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'reasons': reasons, 'samples': len(sm)}
+
+
+def peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def cpu_reference(wl, steps, warmup, sample_rows=None):
+  """The oracle's OpenMP/pocketfft implementation of the same step on the host cores."""
+  sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+  import cfd_oracle
+  import cpu_baseline
+  nx, ny = wl['shape']
+  if sample_rows is not None and sample_rows < nx:
+    nx = sample_rows
+  shape = (nx, ny)
+  dom = ((0.0, TWO_PI * nx / wl['shape'][0]), (0.0, TWO_PI))
+  h = cfd_oracle.grid_step(shape, dom)
+  dt = 0.5 * min(h) / wl['vmax']
+  u, v = synth_ic(shape, 1, 0, wl['vmax'], wl['kpeak'])
+  const = lin = None
+  if wl['kolmogorov']:
+    const = cfd_oracle.kolmogorov_field(shape, dom, 1.0, 4)
+    lin = -0.1
+  cores = os.cpu_count()
+  cs = cpu_baseline.CpuStep(shape, h, dt, 1.0, wl['nu'], const, lin, workers=cores)
+  u2, v2 = np.empty_like(u), np.empty_like(v)
+  for _ in range(warmup):
+    cs.step(u, v, u2, v2)
+    u, u2, v, v2 = u2, u, v2, v
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    cs.step(u, v, u2, v2)
+    u, u2, v, v2 = u2, u, v2, v
+  dt_s = time.perf_counter() - t0
+  assert np.isfinite(u).all()
+  value = nx * ny * steps / dt_s / 1e9
+  return dict(value=value, unit='Gcell*step/s', cores=cores, kind='port',
+              sample=f'{steps} steps of a {nx}x{ny} slab of the workload (same physics, OpenMP C '
+                     f'stencils + scipy.fft pocketfft on {cores} threads; JAX is not installed so '
+                     'the reference jitted CPU path cannot run)'), dt_s / steps * 1e3
+
+
+def run_reference(args, wl, name):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  rows = min(wl['shape'][0], 2048)
+  cb, ms = cpu_reference(wl, args.steps, args.warmup, sample_rows=rows)
+  line = {
+      'impl': 'reference', 'metric': 'cell-updates/sec', 'value': cb['value'], 'unit': 'Gcell*step/s',
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+      'data': 'synthetic', 'config': {'workload': name, 'description': wl['desc']},
+      'cpu_baseline': cb,
+      'e2e': {'value': cb['value'], 'unit': 'Gcell*step/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def run_gpu(args, wl, name):
+  import jax_cfd_b200 as cfd
+  from jax_cfd_b200 import _lib
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  dist = None
+  if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  lib = _lib.lib()
+  _lib.check(lib.cfd_set_device(local_rank))
+  _lib.require_device()
+
+  shape, batch = wl['shape'], wl['batch']
+  grid = cfd.grids.Grid(shape, domain=((0.0, TWO_PI), (0.0, TWO_PI)))
+  dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
+  forcing = None
+  if wl['kolmogorov']:
+    forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
+                                        cfd.forcings.linear_forcing(grid, -0.1))
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, wl['nu'], dt, grid, forcing=forcing)
+  bc = cfd.boundaries.periodic_boundary_conditions(2)
+  host = synth_ic(shape, batch, 1000 + rank, wl['vmax'], wl['kpeak'])
+  full = ((batch,) if batch > 1 else ()) + tuple(shape)
+  cells = int(np.prod(full))
+
+  def wrap(datas):
+    return tuple(cfd.grids.GridVariable(cfd.grids.GridArray(d, o, grid), bc)
+                 for d, o in zip(datas, grid.cell_faces))
+
+  # device-resident state: project the synthetic field once so it is divergence free
+  v = cfd.pressure.projection(wrap([_lib.DeviceArray.from_numpy(a) for a in host]))
+  plan = cfd.get_plan(grid, batch, local_rank)
+  params = step.params()
+  import ctypes
+  stream = _lib.Stream()
+  a = [u.data for u in v]
+  b = [_lib.DeviceArray(full) for _ in a]
+  pa, pb = _lib.ptr_array(a), _lib.ptr_array(b)
+  in_b = ctypes.c_int(0)
+
+  def advance(n, src_a=True):
+    x, y = (pa, pb) if src_a else (pb, pa)
+    _lib.check(lib.cfd_repeated(plan.handle, stream.handle, x, y, n, ctypes.byref(params),
+                                ctypes.byref(in_b)))
+    return src_a != bool(in_b.value)  # True if the result is in a
+
+  def barrier():
+    stream.sync()
+    _lib.check(lib.cfd_device_sync())
+    if dist is not None:
+      dist.barrier()
+
+  in_a = advance(args.warmup, True)
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+    time.sleep(0.25)
+  e0, e1 = _lib.Event(), _lib.Event()
+  launches0 = lib.cfd_launch_count()
+  barrier()
+  e0.record(stream.handle)
+  in_a = advance(args.steps, in_a)
+  e1.record(stream.handle)
+  barrier()
+  ms_total = e0.elapsed_ms(e1)
+  launches = lib.cfd_launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  if dist is not None:
+    import torch
+    t = torch.tensor([ms_total], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+  ms_step = ms_total / args.steps
+  value = cells * world * args.steps / (ms_total * 1e-3) / 1e9
+
+  # sanity: the state is finite and divergence free after the timed steps
+  diag = cfd.diagnostics(wrap(a if in_a else b))
+  assert np.isfinite(diag['kinetic_energy']) and diag['max_abs_div'] < 1.0, diag
+
+  line = None
+  if rank == 0:
+    peak, peak_src = peaks()
+    # per-kernel CUDA-event times of one step (live, same stream)
+    names = (ctypes.c_char_p * 8)()
+    ms = (ctypes.c_float * 8)()
+    nk = ctypes.c_int(0)
+    src, dst = (pa, pb) if in_a else (pb, pa)
+    _lib.check(lib.cfd_step_profile(plan.handle, stream.handle, src, dst, ctypes.byref(params), 5, 8,
+                                    ms, names, ctypes.byref(nk)))
+    kern = {names[i].decode(): float(ms[i]) for i in range(nk.value)}
+    dom = max(kern, key=kern.get)
+    dom_bytes = KERNEL_BYTES[dom] * cells
+    achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': dom_bytes, 'kernel_ms': kern[dom],
+                'share_of_step': kern[dom] / sum(kern.values())}
+    step_gbs = STEP_BYTES_PER_CELL * cells / (ms_step * 1e-3) / 1e9
+    roofline_step = {'bound': 'hbm', 'bytes_per_cell_model': STEP_BYTES_PER_CELL,
+                     'achieved': step_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': step_gbs / peak,
+                     'kernel_ms': kern,
+                     'kernel_gbs': {k: KERNEL_BYTES[k] * cells / (t * 1e-3) / 1e9 for k, t in kern.items()}}
+
+    # e2e: public host-array API, pinned host buffers, H2D + D2H of the whole state every step
+    hin = [_lib.PinnedArray(full) for _ in range(2)]
+    hout = [_lib.PinnedArray(full) for _ in range(2)]
+    for p, src_arr in zip(hin, host):
+      p.array[...] = src_arr
+    nb = cells * 4
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+      _lib.check(lib.cfd_step_host(plan.handle, _lib.ptr_array([p.ptr for p in hin]),
+                                   _lib.ptr_array([p.ptr for p in hout]), None, 1,
+                                   ctypes.byref(params)))
+    e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+      e2e_step()
+      hin, hout = hout, hin
+    e2e_s = time.perf_counter() - t0
+    e2e = {'value': cells * e2e_steps / e2e_s / 1e9, 'unit': 'Gcell*step/s',
+           'h2d_bytes_per_step': 2 * nb, 'd2h_bytes_per_step': 2 * nb, 'steps': e2e_steps,
+           'ms_per_step': e2e_s / e2e_steps * 1e3,
+           'api': 'cfd_step_host (C ABI, pinned numpy in/out) == step_fn on host arrays'}
+    cb = None
+    if not args.no_cpu_baseline:
+      cb, _ = cpu_reference(wl, 3, 1, sample_rows=min(shape[0], 2048))
+    line = {
+        'metric': 'cell-updates/sec', 'value': value, 'unit': 'Gcell*step/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': name, 'description': wl['desc'], 'grid': list(shape), 'batch': batch,
+                   'cells_per_gpu': cells, 'l2_policy': 'working set (7 fields x %.0f MB) %s L2 (126 MB)' % (
+                       cells * 4 / 1e6, 'larger than' if cells * 4 * 7 > 126e6 else 'fits in'),
+                   'parallelism': 'single GPU' if world == 1 else f'{world} independent domain replicas'},
+        'roofline': roofline, 'roofline_step': roofline_step, 'cpu_baseline': cb, 'e2e': e2e,
+        'gpu_launches': int(launches), 'clocks': clocks,
+        'diagnostics_after': diag,
+    }
+    print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
+  return line
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=50)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--workload', default='K8192', choices=sorted(WORKLOADS))
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3)
+  wl = WORKLOADS[args.workload]
+  if args.impl == 'reference':
+    run_reference(args, wl, args.workload)
+  else:
+    run_gpu(args, wl, args.workload)
+
+
+if __name__ == '__main__':
+  main()

@@ -1,0 +1,81 @@
+// Shared declarations for the CUDA core (no framework types).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cfd_b200.h"
+
+namespace cfd {
+
+// Scalars of one step, rounded to float32 exactly where x64-disabled JAX rounds them
+// (SURVEY.md Appendix A): (dt/h_j) and viscosity/density are formed in double then rounded once
+// (interpolation.py:210, equations.py:107); the Laplacian scales are formed in float32
+// (finite_differences.py:129).
+struct StepConsts {
+  float dt;                 // time_stepping.py:101
+  float dth[CFD_MAX_DIM];   // (dt / h_j)
+  float inv_h[CFD_MAX_DIM]; // 1 / h_j   (divisions by h_j become multiplications: <= 1 ulp)
+  float lap_s[CFD_MAX_DIM]; // square(1 / float32(h_j))
+  float lap_sum;            // float32 sum of lap_s
+  float nu;                 // viscosity / density
+  float rho;                // density (forcing / rho, equations.py:109)
+  int has_nu;
+  // forcing
+  int n_terms;
+  int term_kind[CFD_MAX_FORCING_TERMS];
+  float linear_coef;
+  float smag_coef;          // (cs * cutoff)^2, cutoff = prod(h)^(1/d)   subgrid_models.py:91-93
+  const float* sep_prof[CFD_MAX_DIM][CFD_MAX_DIM];
+  float sep_scale[CFD_MAX_DIM];
+  int has_sep[CFD_MAX_DIM];
+  const float* field[CFD_MAX_DIM];
+};
+
+__device__ __forceinline__ int wrap_idx(int i, int n) {  // i in [-n, 2n)
+  i = i < 0 ? i + n : i;
+  return i >= n ? i - n : i;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming (evict-first) variants for data touched once per sweep
+__device__ __forceinline__ float4 ldcs4(const float* p) {
+  return __ldcs(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void stcs4(float* p, float4 v) {
+  __stcs(reinterpret_cast<float4*>(p), v);
+}
+
+// One TVD-limited face flux  F = c_face * U :
+//   upwind (interpolation.py:147-151), Lax-Wendroff (interpolation.py:210-217), van Leer limiter
+//   on r+ / r- (interpolation.py:224-231, 287-297), flux = c * u (advection.py:73).
+// Only the branch selected by U > 0 is evaluated; phi = 2r/(1+r) with r = num/den is computed
+// as 2 num / (den + num) (one MUFU.RCP-based division instead of two).
+__device__ __forceinline__ float face_flux(float cL, float c0, float cR, float cRR, float U,
+                                           float dth) {
+  const float d = cR - c0;
+  const bool pos = U > 0.f;
+  const float num = pos ? (c0 - cL) : (cRR - cR);
+  const float den = (d != 0.f) ? d : 1.f;  // safe_div default numerator 1
+  // r > 0  <=>  num and den have the same sign and num != 0
+  const bool rpos = ((__float_as_int(num) ^ __float_as_int(den)) >= 0) && (num != 0.f);
+  const float phi = rpos ? __fdividef(2.f * num, den + num) : 0.f;
+  const float C = dth * U;
+  const float half = 0.5f * (1.f - fabsf(C)) * d * phi;
+  const float face = pos ? (c0 + half) : (cR - half);
+  return face * U;
+}
+
+#define CFD_CUDA_OK(expr)                                                        \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) return cfd::set_error(#expr, _e, __FILE__, __LINE__); \
+  } while (0)
+
+int set_error(const char* what, cudaError_t e, const char* file, int line);
+int set_error_msg(const char* msg);
+void count_launch(int n = 1);
+
+}  // namespace cfd

@@ -1,0 +1,245 @@
+// Shared-memory line FFTs for the pressure solve (replaces jnp.fft.rfftn / irfftn at
+// /root/reference/jax_cfd/base/fast_diagonalization.py:223).
+//
+// A line of M = 2^LM complex points is owned by G = M / E threads (E = points per thread, 16
+// unless M < 16).  Between radix passes the points live in REGISTERS; shared memory is used only
+// to exchange them (register-staged in-place Stockham: every thread reads its E inputs, the group
+// synchronises, every thread writes its E outputs to the auto-sort positions).  Thread t always
+// reads logical positions {t + G*e}, so reads are conflict-free; writes are made conflict-free by
+// padding one float2 per 16 (PAD()).
+//
+// Twiddles come from a per-M table built in double precision on the host (plan.cu), laid out
+// per pass as tw[(r-1) * Ns + k] = exp(-2 pi i r k / (Ns R)) so that a warp reads consecutive k.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace cfd {
+
+__host__ __device__ constexpr int PAD(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int padded_len(int m) { return m + (m >> 4); }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+// DIR = -1: forward (multiply by -i);  DIR = +1: inverse (multiply by +i)
+template <int DIR>
+__device__ __forceinline__ float2 mul_dir_i(float2 a) {
+  return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+template <int DIR>
+__device__ __forceinline__ float2 twmul(float2 a, float2 w) {  // w is the FORWARD twiddle
+  return DIR < 0 ? cmul(a, w) : cmulc(a, w);
+}
+
+// ---- in-register DFTs, natural-order in, natural-order out --------------------------------
+template <int DIR>
+__device__ __forceinline__ void dft2(float2& a0, float2& a1) {
+  float2 t = a0;
+  a0 = cadd(t, a1);
+  a1 = csub(t, a1);
+}
+
+template <int DIR>
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
+  float2 t2 = cadd(a1, a3), t3 = mul_dir_i<DIR>(csub(a1, a3));
+  a0 = cadd(t0, t2);
+  a1 = cadd(t1, t3);
+  a2 = csub(t0, t2);
+  a3 = csub(t1, t3);
+}
+
+template <int DIR>
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+  constexpr float H = 0.70710678118654752440f;
+  dft4<DIR>(a[0], a[2], a[4], a[6]);  // E[k] in a[0],a[2],a[4],a[6]
+  dft4<DIR>(a[1], a[3], a[5], a[7]);  // O[k] in a[1],a[3],a[5],a[7]
+  float2 o1, o2, o3;
+  if (DIR < 0) {
+    o1 = make_float2((a[3].x + a[3].y) * H, (a[3].y - a[3].x) * H);
+    o3 = make_float2((a[7].y - a[7].x) * H, (-a[7].x - a[7].y) * H);
+  } else {
+    o1 = make_float2((a[3].x - a[3].y) * H, (a[3].x + a[3].y) * H);
+    o3 = make_float2((-a[7].x - a[7].y) * H, (a[7].x - a[7].y) * H);
+  }
+  o2 = mul_dir_i<DIR>(a[5]);
+  float2 e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1];
+  a[0] = cadd(e0, o0);
+  a[4] = csub(e0, o0);
+  a[1] = cadd(e1, o1);
+  a[5] = csub(e1, o1);
+  a[2] = cadd(e2, o2);
+  a[6] = csub(e2, o2);
+  a[3] = cadd(e3, o3);
+  a[7] = csub(e3, o3);
+}
+
+template <int DIR>
+__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+  float2 e[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    e[i] = a[2 * i];
+    o[i] = a[2 * i + 1];
+  }
+  dft8<DIR>(e);
+  dft8<DIR>(o);
+  // forward twiddles exp(-2 pi i k / 16), k = 1..7
+  constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;
+  constexpr float H = 0.70710678118654752440f;
+  const float2 w1 = make_float2(C1, -S1), w2 = make_float2(H, -H), w3 = make_float2(S1, -C1);
+  const float2 w5 = make_float2(-S1, -C1), w6 = make_float2(-H, -H), w7 = make_float2(-C1, -S1);
+  o[1] = twmul<DIR>(o[1], w1);
+  o[2] = twmul<DIR>(o[2], w2);
+  o[3] = twmul<DIR>(o[3], w3);
+  o[4] = mul_dir_i<DIR>(o[4]);
+  o[5] = twmul<DIR>(o[5], w5);
+  o[6] = twmul<DIR>(o[6], w6);
+  o[7] = twmul<DIR>(o[7], w7);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a[k] = cadd(e[k], o[k]);
+    a[k + 8] = csub(e[k], o[k]);
+  }
+}
+
+template <int R, int DIR>
+struct Dft;
+template <int DIR>
+struct Dft<2, DIR> {
+  static __device__ __forceinline__ void run(float2 (&a)[2]) { dft2<DIR>(a[0], a[1]); }
+};
+template <int DIR>
+struct Dft<4, DIR> {
+  static __device__ __forceinline__ void run(float2 (&a)[4]) { dft4<DIR>(a[0], a[1], a[2], a[3]); }
+};
+template <int DIR>
+struct Dft<8, DIR> {
+  static __device__ __forceinline__ void run(float2 (&a)[8]) { dft8<DIR>(a); }
+};
+template <int DIR>
+struct Dft<16, DIR> {
+  static __device__ __forceinline__ void run(float2 (&a)[16]) { dft16<DIR>(a); }
+};
+
+// ---- radix plan -------------------------------------------------------------------------------
+// M = 2^LM points, E = min(16, M) points per thread.  Passes use radix 16 while possible and one
+// final smaller radix.  Forward and inverse share the pass order and the twiddle table (the
+// inverse conjugates).  Every transform starts from registers v[e] = x[t + G*e] and ends with
+// v[slot] = X[t + G*slot], so a forward transform can be scaled in registers and fed straight
+// into an inverse transform without an exchange.
+template <int LM>
+struct FftPlan {
+  static constexpr int M = 1 << LM;
+  static constexpr int E = M < 16 ? M : 16;
+  static constexpr int G = M / E;  // threads per line
+  static constexpr int LE = LM < 4 ? LM : 4;
+  static constexpr int NP = (LM + LE - 1) / LE;  // passes
+  // log2 radix of forward pass p
+  __host__ __device__ static constexpr int lr_fwd(int p) {
+    return (p < LM / LE) ? LE : (LM - (LM / LE) * LE);
+  }
+  __host__ __device__ static constexpr int lns_fwd(int p) {  // log2 Ns before pass p
+    int s = 0;
+    for (int q = 0; q < p; ++q) s += lr_fwd(q);
+    return s;
+  }
+  // twiddle table: pass p owns a block of (R - 1) * Ns entries at offset tw_off_fwd(p).
+  __host__ __device__ static constexpr int tw_off_fwd(int p) {
+    int o = 0;
+    for (int q = 0; q < p; ++q) o += ((1 << lr_fwd(q)) - 1) << lns_fwd(q);
+    return o;
+  }
+  __host__ __device__ static constexpr int tw_len() { return tw_off_fwd(NP); }
+};
+
+// One radix pass on the E register-resident points of thread t.
+//   v[e] holds x[t + G*e] on entry; on exit v[q + r*NB] holds output r of butterfly j = t + G*q.
+template <int LM, int LR, int LNS, int DIR>
+__device__ __forceinline__ void fft_pass_compute(float2 (&v)[FftPlan<LM>::E], int t,
+                                                 const float2* __restrict__ tw) {
+  using P = FftPlan<LM>;
+  constexpr int R = 1 << LR, NB = P::E / R, NS = 1 << LNS;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    float2 a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = v[q + r * NB];
+    if (LNS > 0) {
+      const int k = (t + P::G * q) & (NS - 1);
+#pragma unroll
+      for (int r = 1; r < R; ++r) a[r] = twmul<DIR>(a[r], __ldg(&tw[(r - 1) * NS + k]));
+    }
+    Dft<R, DIR>::run(a);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[q + r * NB] = a[r];
+  }
+}
+
+// Scatter the outputs of a pass to their Stockham positions in the (padded) line buffer.
+template <int LM, int LR, int LNS>
+__device__ __forceinline__ void fft_pass_store(const float2 (&v)[FftPlan<LM>::E], int t, float2* s) {
+  using P = FftPlan<LM>;
+  constexpr int R = 1 << LR, NB = P::E / R, NS = 1 << LNS;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = t + P::G * q;
+    const int k = j & (NS - 1);
+    const int base = ((j - k) << LR) + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[PAD(base + r * NS)] = v[q + r * NB];
+  }
+}
+
+template <int LM>
+__device__ __forceinline__ void fft_load_regs(float2 (&v)[FftPlan<LM>::E], int t, const float2* s) {
+  using P = FftPlan<LM>;
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) v[e] = s[PAD(t + P::G * e)];
+}
+
+// Logical index (frequency for a finished forward transform / sample for a finished inverse) held
+// in v[slot] after the LAST pass: the last pass has Ns = M / R so output r of butterfly j sits at
+// j + r * Ns = t + G*q + r*(M/R) = t + G*(q + r*NB): slot q + r*NB  <->  index t + G*slot.
+template <int LM>
+__device__ __forceinline__ int fft_final_index(int t, int slot) {
+  return t + FftPlan<LM>::G * slot;
+}
+
+// Full transforms.  `SYNC` is a functor synchronising the G threads that own the line (all
+// threads of the CTA call these functions in lock-step, so __syncthreads is always valid).
+// Forward: data taken from registers v (x[t + G e]); result left in registers, natural index
+// t + G*slot.   Exchanges through `s`.
+template <int LM, int DIR, int P0 = 0>
+struct FftRun {
+  using P = FftPlan<LM>;
+  template <int PASS>
+  static __device__ __forceinline__ void passes(float2 (&v)[P::E], int t, float2* s,
+                                                const float2* __restrict__ tw) {
+    if constexpr (PASS < P::NP) {
+      constexpr int LR = P::lr_fwd(PASS);
+      constexpr int LNS = P::lns_fwd(PASS);
+      constexpr int OFF = P::tw_off_fwd(PASS);
+      fft_pass_compute<LM, LR, LNS, DIR>(v, t, tw + OFF);
+      if constexpr (PASS + 1 < P::NP) {
+        __syncthreads();  // all reads of the previous layout are done
+        fft_pass_store<LM, LR, LNS>(v, t, s);
+        __syncthreads();
+        fft_load_regs<LM>(v, t, s);
+        passes<PASS + 1>(v, t, s, tw);
+      }
+    }
+  }
+  static __device__ __forceinline__ void run(float2 (&v)[P::E], int t, float2* s,
+                                             const float2* __restrict__ tw) {
+    passes<0>(v, t, s, tw);
+  }
+};
+
+}  // namespace cfd

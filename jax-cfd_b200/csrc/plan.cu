@@ -1,0 +1,539 @@
+// Plan management + the extern "C" ABI declared in include/cfd_b200.h.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_smem.cuh"
+
+namespace cfd {
+
+// ---- kernels implemented in the other translation units ------------------------------------
+int launch_explicit_2d(cudaStream_t, const float* u, const float* v, float* us, float* vs,
+                       float* rhs, int batch, int Nx, int Ny, const StepConsts& c, int dvdt_mode);
+int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
+                     const float2* tw, const float2* rtw);
+int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
+                  const double* lamx, const double* lamy, double cutoff, float norm);
+int launch_irfft_correct(cudaStream_t, int lm_row, const float2* T, const float* us,
+                         const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
+                         const float2* tw, const float2* rtw, float inv_hx, float inv_hy);
+int launch_divergence_2d(cudaStream_t, const float* u, const float* v, float* rhs, int batch,
+                         int Nx, int Ny, float inv_hx, float inv_hy);
+int launch_axpy(cudaStream_t, const float* x, int nterms, const float* const* y, const float* coef,
+                float* out, size_t n);
+int launch_diag_2d(cudaStream_t, const float* u, const float* v, int batch, int Nx, int Ny,
+                   float inv_hx, float inv_hy, double* out4);
+
+// ---- errors / counters ------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(const char* what, cudaError_t e, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  g_err = buf;
+  return 1;
+}
+int set_error_msg(const char* msg) {
+  g_err = msg;
+  return 1;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int ilog2(int64_t n) {
+  int l = 0;
+  while ((int64_t(1) << l) < n) ++l;
+  return l;
+}
+static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// Twiddle table for a 2^lm-point transform, same pass structure as FftPlan<LM>.
+static std::vector<float2> build_twiddles(int lm) {
+  const int le = lm < 4 ? lm : 4;
+  const int np = (lm + le - 1) / le;
+  std::vector<float2> tw;
+  int lns = 0;
+  for (int p = 0; p < np; ++p) {
+    const int lr = (p < lm / le) ? le : (lm - (lm / le) * le);
+    const int R = 1 << lr, Ns = 1 << lns;
+    for (int r = 1; r < R; ++r)
+      for (int k = 0; k < Ns; ++k) {
+        const double ang = -2.0 * M_PI * (double)r * (double)k / ((double)Ns * (double)R);
+        tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+      }
+    lns += lr;
+  }
+  return tw;
+}
+
+}  // namespace cfd
+
+using namespace cfd;
+
+struct cfd_plan {
+  int ndim = 0;
+  int64_t shape[CFD_MAX_DIM] = {1, 1, 1};
+  double step[CFD_MAX_DIM] = {1, 1, 1};
+  int batch = 1;
+  int device = 0;
+  size_t cells = 0;  // per batch member
+  // FFT tables
+  int lm_row = 0, lm_x = 0;
+  float2* tw_row = nullptr;
+  float2* tw_x = nullptr;
+  float2* rtw = nullptr;
+  double* lam[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  double cutoff = 0;
+  float norm = 0;
+  // workspace
+  float* us[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* rhs = nullptr;
+  float2* T = nullptr;
+  size_t workspace_bytes = 0;
+  // host-call staging
+  float* dev_a[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* dev_b[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* dev_q = nullptr;
+  cudaStream_t host_stream = nullptr;
+  double* diag_dev = nullptr;
+  // per-kernel timing
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<const char*> prof_names;
+};
+
+namespace {
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+  CFD_CUDA_OK(cudaMalloc((void**)dst, src.size() * sizeof(T)));
+  CFD_CUDA_OK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void prof_mark(cfd_plan* p, cudaStream_t st, const char* name) {
+  if (!p->profiling) return;
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  cudaEventRecord(ev, st);
+  p->prof_events.push_back(ev);
+  p->prof_names.push_back(name);
+}
+
+int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
+  memset(c, 0, sizeof *c);
+  const int d = p->ndim;
+  c->dt = (float)prm->dt;
+  float lap_sum = 0.f;
+  for (int j = 0; j < d; ++j) {
+    c->dth[j] = (float)(prm->dt / p->step[j]);
+    c->inv_h[j] = (float)(1.0 / p->step[j]);
+    const float hf = (float)p->step[j];
+    const float inv = 1.0f / hf;
+    c->lap_s[j] = inv * inv;
+  }
+  // np.sum over a float32 array of <= 3 entries: sequential float32 adds
+  for (int j = 0; j < d; ++j) lap_sum = (j == 0) ? c->lap_s[0] : lap_sum + c->lap_s[j];
+  c->lap_sum = lap_sum;
+  c->has_nu = prm->has_viscosity ? 1 : 0;
+  c->nu = (float)(prm->viscosity / prm->density);
+  c->rho = (float)prm->density;
+  if (prm->n_terms < 0 || prm->n_terms > CFD_MAX_FORCING_TERMS)
+    return set_error_msg("cfd_params.n_terms out of range");
+  c->n_terms = prm->n_terms;
+  for (int t = 0; t < prm->n_terms; ++t) {
+    const int k = prm->term_kind[t];
+    if (k < CFD_FORCE_SEPARABLE || k > CFD_FORCE_SMAGORINSKY)
+      return set_error_msg("cfd_params.term_kind: unknown forcing kind");
+    if (k == CFD_FORCE_SMAGORINSKY && d == 2)
+      return set_error_msg("Smagorinsky closure is implemented for 3-D grids only in this build");
+    c->term_kind[t] = k;
+  }
+  c->linear_coef = (float)prm->linear_coef;
+  double prod = 1.0;
+  for (int j = 0; j < d; ++j) prod *= p->step[j];
+  const double cutoff = pow(prod, 1.0 / d);
+  c->smag_coef = (float)((prm->smagorinsky_cs * cutoff) * (prm->smagorinsky_cs * cutoff));
+  for (int a = 0; a < CFD_MAX_DIM; ++a) {
+    for (int j = 0; j < CFD_MAX_DIM; ++j) c->sep_prof[a][j] = prm->sep_prof[a][j];
+    c->sep_scale[a] = prm->sep_scale[a];
+    c->has_sep[a] = prm->has_sep[a];
+    c->field[a] = prm->field[a];
+  }
+  return 0;
+}
+
+int check_plan(const cfd_plan* p) {
+  if (p == nullptr) return set_error_msg("null plan");
+  CFD_CUDA_OK(cudaSetDevice(p->device));
+  return 0;
+}
+
+int poisson_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, float* uo,
+               float* vo, float* qo) {
+  const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
+  if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw)) return e;
+  prof_mark(p, st, "rfft_rows");
+  if (int e = launch_xlines(st, p->lm_x, p->T, p->batch, Ny / 2, p->tw_x, p->lam[0], p->lam[1],
+                            p->cutoff, p->norm))
+    return e;
+  prof_mark(p, st, "xlines");
+  if (int e = launch_irfft_correct(st, p->lm_row, p->T, us, vs, uo, vo, qo, p->batch, Nx,
+                                   p->tw_row, p->rtw, (float)(1.0 / p->step[0]),
+                                   (float)(1.0 / p->step[1])))
+    return e;
+  prof_mark(p, st, "irfft_rows_correct");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cfd_last_error(void) { return g_err.c_str(); }
+const char* cfd_version(void) { return "cfd_b200 0.1 (sm_100a)"; }
+int cfd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+uint64_t cfd_launch_count(void) { return g_launches.load(); }
+
+int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double* step, int batch,
+                    int device) {
+  if (out == nullptr || shape == nullptr || step == nullptr) return set_error_msg("null argument");
+  *out = nullptr;
+  if (ndim != 2) return set_error_msg("cfd_plan_create: only ndim == 2 is implemented in this build");
+  if (batch < 1) return set_error_msg("batch must be >= 1");
+  for (int j = 0; j < ndim; ++j) {
+    if (!is_pow2(shape[j]) || shape[j] < 16)
+      return set_error_msg("every grid axis must be a power of two >= 16");
+    if (!(step[j] > 0)) return set_error_msg("grid step must be positive");
+  }
+  if (shape[ndim - 1] < 32) return set_error_msg("last grid axis must be >= 32");
+  if (shape[0] > (1 << 14)) return set_error_msg("axis 0 longer than 16384 is not supported yet");
+  if (shape[ndim - 1] > (1 << 14))
+    return set_error_msg("last axis longer than 16384 is not supported yet");
+  if (cfd_device_count() <= device) return set_error_msg("no such CUDA device (no CPU fallback)");
+  CFD_CUDA_OK(cudaSetDevice(device));
+  cfd_plan* p = new cfd_plan();
+  p->ndim = ndim;
+  p->batch = batch;
+  p->device = device;
+  p->cells = 1;
+  for (int j = 0; j < ndim; ++j) {
+    p->shape[j] = shape[j];
+    p->step[j] = step[j];
+    p->cells *= (size_t)shape[j];
+  }
+  const int Nx = (int)shape[0], Ny = (int)shape[ndim - 1];
+  p->lm_row = ilog2(Ny / 2);
+  p->lm_x = ilog2(Nx);
+  int err = 0;
+  err |= upload(&p->tw_row, build_twiddles(p->lm_row));
+  err |= upload(&p->tw_x, build_twiddles(p->lm_x));
+  {
+    const int M = Ny / 2;
+    std::vector<float2> rtw(M / 2 + 1);
+    for (int k = 0; k <= M / 2; ++k) {  // -i * exp(-2 pi i k / N)
+      const double ang = -2.0 * M_PI * (double)k / (double)Ny - 0.5 * M_PI;
+      rtw[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    err |= upload(&p->rtw, rtw);
+  }
+  for (int j = 0; j < ndim; ++j) {
+    // eigenvalues of the periodic second-difference operator (array_utils.py:168-173 column
+    // [-2, 1, 0, ..., 0, 1] / h^2 transformed by np.fft.fft, fast_diagonalization.py:211-212)
+    const int n = (int)shape[j];
+    const int len = (j == ndim - 1) ? n / 2 + 1 : n;
+    std::vector<double> lam(len);
+    for (int k = 0; k < len; ++k)
+      lam[k] = (2.0 * cos(2.0 * M_PI * (double)k / (double)n) - 2.0) / (step[j] * step[j]);
+    lam[0] = 0.0;
+    err |= upload(&p->lam[j], lam);
+  }
+  p->cutoff = 10.0 * 1.1920928955078125e-07;  // 10 * finfo(float32).eps, fast_diagonalization.py:257-258
+  p->norm = (float)(1.0 / (2.0 * (double)p->cells));
+  const size_t fbytes = (size_t)batch * p->cells * sizeof(float);
+  for (int a = 0; a < ndim && !err; ++a) {
+    if (cudaMalloc((void**)&p->us[a], fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  }
+  if (!err && cudaMalloc((void**)&p->rhs, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  if (!err && cudaMalloc((void**)&p->T, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  if (!err && cudaMalloc((void**)&p->diag_dev, 8 * sizeof(double)) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  p->workspace_bytes = (size_t)(ndim + 2) * fbytes;
+  if (err) {
+    cudaGetLastError();
+    cfd_plan_destroy(p);
+    return 1;
+  }
+  *out = p;
+  return 0;
+}
+
+void cfd_plan_destroy(cfd_plan* p) {
+  if (p == nullptr) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->tw_row);
+  cudaFree(p->tw_x);
+  cudaFree(p->rtw);
+  for (int j = 0; j < CFD_MAX_DIM; ++j) {
+    cudaFree(p->lam[j]);
+    cudaFree(p->us[j]);
+    cudaFree(p->dev_a[j]);
+    cudaFree(p->dev_b[j]);
+  }
+  cudaFree(p->rhs);
+  cudaFree(p->T);
+  cudaFree(p->dev_q);
+  cudaFree(p->diag_dev);
+  if (p->host_stream) cudaStreamDestroy(p->host_stream);
+  for (auto ev : p->prof_events) cudaEventDestroy(ev);
+  delete p;
+}
+
+size_t cfd_plan_workspace_bytes(const cfd_plan* p) { return p ? p->workspace_bytes : 0; }
+
+int cfd_step(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
+             float* q_out, const cfd_params* params) {
+  if (int e = check_plan(p)) return e;
+  if (!v_in || !v_out || !params) return set_error_msg("null argument");
+  for (int a = 0; a < p->ndim; ++a) {
+    if (!v_in[a] || !v_out[a]) return set_error_msg("null velocity component pointer");
+    if (v_in[a] == v_out[a]) return set_error_msg("cfd_step: v_out must not alias v_in");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  StepConsts c;
+  if (int e = make_consts(p, params, &c)) return e;
+  const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
+  prof_mark(p, st, "begin");
+  if (int e = launch_explicit_2d(st, v_in[0], v_in[1], p->us[0], p->us[1], p->rhs, p->batch, Nx, Ny, c, 0))
+    return e;
+  prof_mark(p, st, "explicit_2d");
+  return poisson_2d(p, st, p->us[0], p->us[1], v_out[0], v_out[1], q_out);
+}
+
+int cfd_repeated(cfd_plan* p, cfd_stream stream, float* const* v_a, float* const* v_b, int nsteps,
+                 const cfd_params* params, int* result_in_b) {
+  if (nsteps < 0) return set_error_msg("nsteps must be >= 0");
+  for (int n = 0; n < nsteps; ++n) {
+    float* const* src = (n & 1) ? v_b : v_a;
+    float* const* dst = (n & 1) ? v_a : v_b;
+    if (int e = cfd_step(p, stream, src, dst, nullptr, params)) return e;
+  }
+  if (result_in_b) *result_in_b = nsteps & 1;
+  return 0;
+}
+
+int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
+                       float* const* dvdt_out, const cfd_params* params) {
+  if (int e = check_plan(p)) return e;
+  if (!v_in || !dvdt_out || !params) return set_error_msg("null argument");
+  StepConsts c;
+  if (int e = make_consts(p, params, &c)) return e;
+  for (int a = 0; a < p->ndim; ++a)
+    if (v_in[a] == dvdt_out[a]) return set_error_msg("cfd_explicit_terms: output must not alias input");
+  return launch_explicit_2d((cudaStream_t)stream, v_in[0], v_in[1], dvdt_out[0], dvdt_out[1],
+                            nullptr, p->batch, (int)p->shape[0], (int)p->shape[1], c, 1);
+}
+
+int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
+                float* q_out) {
+  if (int e = check_plan(p)) return e;
+  if (!v_in || !v_out) return set_error_msg("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
+  if (int e = launch_divergence_2d(st, v_in[0], v_in[1], p->rhs, p->batch, Nx, Ny,
+                                   (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1])))
+    return e;
+  return poisson_2d(p, st, v_in[0], v_in[1], v_out[0], v_out[1], q_out);
+}
+
+int cfd_axpy(cfd_plan* p, cfd_stream stream, const float* const* x, int nterms,
+             const float* const* const* y, const double* coef, float* const* out) {
+  if (int e = check_plan(p)) return e;
+  if (nterms < 0 || nterms > 4) return set_error_msg("cfd_axpy: 0 <= nterms <= 4");
+  const size_t n = (size_t)p->batch * p->cells;
+  for (int a = 0; a < p->ndim; ++a) {
+    const float* ys[4] = {nullptr, nullptr, nullptr, nullptr};
+    float cf[4] = {0, 0, 0, 0};
+    for (int k = 0; k < nterms; ++k) {
+      ys[k] = y[k][a];
+      cf[k] = (float)coef[k];
+    }
+    if (int e = launch_axpy((cudaStream_t)stream, x[a], nterms, ys, cf, out[a], n)) return e;
+  }
+  return 0;
+}
+
+int cfd_diagnostics(cfd_plan* p, cfd_stream stream, const float* const* v, cfd_diag* out) {
+  if (int e = check_plan(p)) return e;
+  if (!v || !out) return set_error_msg("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = launch_diag_2d(st, v[0], v[1], p->batch, (int)p->shape[0], (int)p->shape[1],
+                             (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1]), p->diag_dev))
+    return e;
+  double h[4];
+  CFD_CUDA_OK(cudaMemcpyAsync(h, p->diag_dev, sizeof h, cudaMemcpyDeviceToHost, st));
+  CFD_CUDA_OK(cudaStreamSynchronize(st));
+  const double n = (double)p->batch * (double)p->cells;
+  out->kinetic_energy = h[0] / n;
+  out->enstrophy = h[1] / n;
+  out->max_abs_div = h[2];
+  out->max_speed_sq = h[3];
+  return 0;
+}
+
+int cfd_step_host(cfd_plan* p, const float* const* v_in_host, float* const* v_out_host,
+                  float* q_out_host, int nsteps, const cfd_params* params) {
+  if (int e = check_plan(p)) return e;
+  if (!v_in_host || !v_out_host || !params) return set_error_msg("null argument");
+  if (nsteps < 1) return set_error_msg("nsteps must be >= 1");
+  const size_t bytes = (size_t)p->batch * p->cells * sizeof(float);
+  if (!p->host_stream) CFD_CUDA_OK(cudaStreamCreateWithFlags(&p->host_stream, cudaStreamNonBlocking));
+  for (int a = 0; a < p->ndim; ++a) {
+    if (!p->dev_a[a]) CFD_CUDA_OK(cudaMalloc((void**)&p->dev_a[a], bytes));
+    if (!p->dev_b[a]) CFD_CUDA_OK(cudaMalloc((void**)&p->dev_b[a], bytes));
+  }
+  if (q_out_host && !p->dev_q) CFD_CUDA_OK(cudaMalloc((void**)&p->dev_q, bytes));
+  cudaStream_t st = p->host_stream;
+  for (int a = 0; a < p->ndim; ++a)
+    CFD_CUDA_OK(cudaMemcpyAsync(p->dev_a[a], v_in_host[a], bytes, cudaMemcpyHostToDevice, st));
+  float** cur = p->dev_a;
+  float** nxt = p->dev_b;
+  for (int n = 0; n < nsteps; ++n) {
+    float* q = (q_out_host && n == nsteps - 1) ? p->dev_q : nullptr;
+    if (int e = cfd_step(p, st, cur, nxt, q, params)) return e;
+    float** tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  for (int a = 0; a < p->ndim; ++a)
+    CFD_CUDA_OK(cudaMemcpyAsync(v_out_host[a], cur[a], bytes, cudaMemcpyDeviceToHost, st));
+  if (q_out_host) CFD_CUDA_OK(cudaMemcpyAsync(q_out_host, p->dev_q, bytes, cudaMemcpyDeviceToHost, st));
+  CFD_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int cfd_step_profile(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
+                     const cfd_params* params, int reps, int max_kernels, float* ms,
+                     const char** names, int* n_kernels) {
+  if (int e = check_plan(p)) return e;
+  if (reps < 1) reps = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<double> acc;
+  std::vector<const char*> nm;
+  for (int r = 0; r < reps; ++r) {
+    for (auto ev : p->prof_events) cudaEventDestroy(ev);
+    p->prof_events.clear();
+    p->prof_names.clear();
+    p->profiling = true;
+    int e = cfd_step(p, stream, v_in, v_out, nullptr, params);
+    p->profiling = false;
+    if (e) return e;
+    CFD_CUDA_OK(cudaStreamSynchronize(st));
+    const size_t n = p->prof_events.size();
+    if (acc.empty()) {
+      acc.assign(n > 0 ? n - 1 : 0, 0.0);
+      nm.assign(p->prof_names.begin() + (n > 0 ? 1 : 0), p->prof_names.end());
+    }
+    for (size_t i = 1; i < n; ++i) {
+      float t = 0.f;
+      CFD_CUDA_OK(cudaEventElapsedTime(&t, p->prof_events[i - 1], p->prof_events[i]));
+      acc[i - 1] += t;
+    }
+  }
+  const int n = (int)acc.size();
+  if (n_kernels) *n_kernels = n;
+  for (int i = 0; i < n && i < max_kernels; ++i) {
+    ms[i] = (float)(acc[i] / reps);
+    names[i] = nm[i];
+  }
+  return 0;
+}
+
+// ---- device helpers ---------------------------------------------------------------------------
+int cfd_malloc(void** dptr, size_t bytes) {
+  CFD_CUDA_OK(cudaMalloc(dptr, bytes));
+  return 0;
+}
+int cfd_free(void* dptr) {
+  CFD_CUDA_OK(cudaFree(dptr));
+  return 0;
+}
+int cfd_malloc_host(void** hptr, size_t bytes) {
+  CFD_CUDA_OK(cudaMallocHost(hptr, bytes));
+  return 0;
+}
+int cfd_free_host(void* hptr) {
+  CFD_CUDA_OK(cudaFreeHost(hptr));
+  return 0;
+}
+int cfd_memcpy_h2d(void* dst, const void* src, size_t bytes, cfd_stream s) {
+  CFD_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s));
+  return 0;
+}
+int cfd_memcpy_d2h(void* dst, const void* src, size_t bytes, cfd_stream s) {
+  CFD_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  return 0;
+}
+int cfd_memcpy_d2d(void* dst, const void* src, size_t bytes, cfd_stream s) {
+  CFD_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+  return 0;
+}
+int cfd_memset(void* dst, int value, size_t bytes, cfd_stream s) {
+  CFD_CUDA_OK(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)s));
+  return 0;
+}
+int cfd_stream_create(cfd_stream* out) {
+  cudaStream_t s;
+  CFD_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *out = (cfd_stream)s;
+  return 0;
+}
+int cfd_stream_destroy(cfd_stream s) {
+  CFD_CUDA_OK(cudaStreamDestroy((cudaStream_t)s));
+  return 0;
+}
+int cfd_stream_sync(cfd_stream s) {
+  CFD_CUDA_OK(cudaStreamSynchronize((cudaStream_t)s));
+  return 0;
+}
+int cfd_device_sync(void) {
+  CFD_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+int cfd_set_device(int device) {
+  CFD_CUDA_OK(cudaSetDevice(device));
+  return 0;
+}
+int cfd_event_create(void** ev) {
+  cudaEvent_t e;
+  CFD_CUDA_OK(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return 0;
+}
+int cfd_event_destroy(void* ev) {
+  CFD_CUDA_OK(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+int cfd_event_record(void* ev, cfd_stream s) {
+  CFD_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)s));
+  return 0;
+}
+int cfd_event_elapsed_ms(void* start, void* stop, float* ms) {
+  CFD_CUDA_OK(cudaEventSynchronize((cudaEvent_t)stop));
+  CFD_CUDA_OK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+
+}  // extern "C"

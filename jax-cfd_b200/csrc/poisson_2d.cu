@@ -1,0 +1,399 @@
+// Sweeps "R", "X", "C" (2-D): the fast-diagonalisation pressure projection
+//   q = irfftn( D * rfftn(rhs) ),  v' = u* - grad q
+// replacing fast_diagonalization.py:199-225,257-262 (`_circulant_rfft_transform`, pseudoinverse),
+// pressure.py:115-157 (`solve_fast_diag`) and pressure.py:181-198 (`projection`).
+//
+//   R  rfft_rows:   real FFT of every row (axis 1, contiguous) of rhs; the half spectrum is
+//                   written TRANSPOSED, T[ky][x], packed to exactly Ny/2 complex columns
+//                   (Re/Im of column 0 hold the two real coefficients ky = 0 and ky = Ny/2).
+//   X  xlines:      for every ky: contiguous complex FFT along x, multiply by the pseudo-inverse
+//                   eigenvalue table D(kx, ky) (built in f64 from the analytic circulant
+//                   eigenvalues), inverse FFT along x, in place.  One read + one write of T.
+//   C  irfft_rows_correct: gather T[ky][x] for R+1 rows, inverse real FFT -> q rows in shared
+//                   memory, then v' = u* - forward_difference(q) (pressure.py:194-196) written
+//                   straight to the output state.
+//
+// Scaling: R stores 2*X, C's pre-processing produces 2*Z, the inverse passes are unnormalised, so
+// the table D carries 1 / (2 * Nx * Ny) (a power of two: exact).
+#include "common.cuh"
+#include "fft_smem.cuh"
+
+#include <type_traits>
+
+namespace cfd {
+
+namespace {
+
+__host__ __device__ constexpr int row_stride(int M, int rows) {
+  // padded line length rounded up to 16 float2, plus a skew so that the transposed access
+  // (lane -> row fastest) is bank-conflict free.
+  return ((padded_len(M) + 15) & ~15) + (rows >= 16 ? 1 : 16 / rows);
+}
+
+// ------------------------------------------------------------------------------------------
+// R: rows of `rhs` (N = 2M reals each)  ->  T[b][ky][x]   (ky = 0..M-1, packed)
+template <int LM, int ROWS>
+__global__ void __launch_bounds__(ROWS * FftPlan<LM>::G)
+rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
+                 const float2* __restrict__ tw, const float2* __restrict__ rtw) {
+  using P = FftPlan<LM>;
+  constexpr int M = P::M, G = P::G, E = P::E;
+  constexpr int RS = row_stride(M, ROWS);
+  extern __shared__ float2 smem[];
+  const int tid = threadIdx.x;
+  const int row = tid / G, t = tid % G;
+  const int x0 = blockIdx.x * ROWS;
+  const size_t b = blockIdx.y;
+  float2* s = smem + row * RS;
+
+  float2 v[E];
+  {
+    const float2* src = reinterpret_cast<const float2*>(rhs + (b * Nx + x0 + row) * (size_t)(2 * M));
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = __ldg(src + t + G * e);
+  }
+  FftRun<LM, -1>::run(v, t, s, tw);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
+  __syncthreads();
+  // split the half-size complex transform into the real-input spectrum (in place, pairs k, M-k)
+  for (int k = t; k <= M / 2; k += G) {
+    if (k == 0) {
+      const float2 z = s[0];
+      s[0] = make_float2(2.f * (z.x + z.y), 2.f * (z.x - z.y));
+    } else if (k == M / 2) {
+      const float2 z = s[PAD(k)];
+      s[PAD(k)] = make_float2(2.f * z.x, -2.f * z.y);
+    } else {
+      const float2 zk = s[PAD(k)], zm = s[PAD(M - k)];
+      const float2 A = make_float2(zk.x + zm.x, zk.y - zm.y);  // Zk + conj(Zm)
+      const float2 B = make_float2(zk.x - zm.x, zk.y + zm.y);  // Zk - conj(Zm)
+      const float2 WB = cmul(__ldg(rtw + k), B);               // (-i w^k) B
+      s[PAD(k)] = make_float2(A.x + WB.x, A.y + WB.y);
+      s[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
+    }
+  }
+  __syncthreads();
+  // transposed store: for each ky the ROWS values of this CTA are contiguous in T
+  float2* Tb = T + b * (size_t)M * Nx + x0;
+  constexpr int NT = ROWS * G;
+#pragma unroll 4
+  for (int idx = tid; idx < ROWS * M; idx += NT) {
+    const int r = idx % ROWS, ky = idx / ROWS;
+    Tb[(size_t)ky * Nx + r] = smem[r * RS + PAD(ky)];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// X: lines T[line][0..Nx)  (line = b * My + ky), forward FFT * D * inverse FFT, in place.
+template <int LM, int LINES>
+__global__ void __launch_bounds__(LINES * FftPlan<LM>::G)
+xlines_kernel(float2* __restrict__ T, int My, const float2* __restrict__ tw,
+              const double* __restrict__ lamx, const double* __restrict__ lamy, double cutoff,
+              float norm) {
+  using P = FftPlan<LM>;
+  constexpr int M = P::M, G = P::G, E = P::E;
+  constexpr int RS = row_stride(M, 16);
+  extern __shared__ float2 smem[];
+  const int tid = threadIdx.x;
+  const int ln = tid / G, t = tid % G;
+  const size_t line0 = (size_t)blockIdx.x * LINES;
+  const size_t line = line0 + ln;
+  const int ky = (int)(line % My);
+  float2* s = smem + ln * RS;
+  float2* Tl = T + line * M;
+
+  float2 v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) v[e] = Tl[t + G * e];
+  FftRun<LM, -1>::run(v, t, s, tw);
+
+  const bool cta_has_packed = (line0 % My) == 0;  // only the first line of a CTA can be ky = 0
+  if (!cta_has_packed || ky != 0) {
+    const double ly = __ldg(lamy + ky);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const double lam = __ldg(lamx + t + G * e) + ly;
+      const float d = (fabs(lam) > cutoff) ? norm * __frcp_rn((float)lam) : 0.f;
+      v[e].x *= d;
+      v[e].y *= d;
+    }
+  }
+  if (cta_has_packed) {
+    // Line ky = 0 carries two real sequences (ky = 0 in Re, ky = Ny/2 in Im).  Their spectra are
+    // A = (C[k] + conj C[N-k]) / 2 and B = (C[k] - conj C[N-k]) / 2i; scale them with D(kx, 0) and
+    // D(kx, Ny/2) and recombine:  C'[k] = D0/2 (C[k] + conj C[N-k]) + DM/2 (C[k] - conj C[N-k]).
+    __syncthreads();
+    if (ky == 0) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
+    }
+    __syncthreads();
+    if (ky == 0) {
+      const double ly0 = __ldg(lamy + 0), lyM = __ldg(lamy + My);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int kx = t + G * e;
+        const float2 cp = s[PAD((M - kx) & (M - 1))];
+        const double lx = __ldg(lamx + kx);
+        const double l0 = lx + ly0, lM = lx + lyM;
+        const float d0 = (fabs(l0) > cutoff) ? 0.5f * norm * __frcp_rn((float)l0) : 0.f;
+        const float dM = (fabs(lM) > cutoff) ? 0.5f * norm * __frcp_rn((float)lM) : 0.f;
+        const float2 c = v[e];
+        const float2 sum = make_float2(c.x + cp.x, c.y - cp.y);
+        const float2 dif = make_float2(c.x - cp.x, c.y + cp.y);
+        v[e] = make_float2(d0 * sum.x + dM * dif.x, d0 * sum.y + dM * dif.y);
+      }
+    }
+  }
+  FftRun<LM, +1>::run(v, t, s, tw);
+#pragma unroll
+  for (int e = 0; e < E; ++e) Tl[t + G * e] = v[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// C: gather RP = R + 1 rows of T, inverse real FFT -> q in smem, v' = u* - grad q.
+template <int LM, int RP>
+__global__ void __launch_bounds__(RP * FftPlan<LM>::G)
+irfft_rows_correct_kernel(const float2* __restrict__ T, const float* __restrict__ us,
+                          const float* __restrict__ vs, float* __restrict__ uo,
+                          float* __restrict__ vo, float* __restrict__ qo, int Nx,
+                          const float2* __restrict__ tw, const float2* __restrict__ rtw,
+                          float inv_hx, float inv_hy) {
+  using P = FftPlan<LM>;
+  constexpr int M = P::M, G = P::G, E = P::E;
+  constexpr int R = RP - 1;
+  constexpr int RS = row_stride(M, RP);  // skewed: the gather below walks rows fastest
+  constexpr int NT = RP * G;
+  constexpr int N = 2 * M;
+  extern __shared__ float2 smem[];
+  const int tid = threadIdx.x;
+  const int row = tid / G, t = tid % G;
+  const int x0 = blockIdx.x * R;
+  const size_t b = blockIdx.y;
+  float2* s = smem + row * RS;
+
+  // gather: rows x0 .. x0+R (the last one is the periodic neighbour needed by d/dx)
+  {
+    const float2* Tb = T + b * (size_t)M * Nx;
+    for (int idx = tid; idx < RP * M; idx += NT) {
+      const int r = idx % RP, ky = idx / RP;
+      int x = x0 + r;
+      x = x >= Nx ? x - Nx : x;
+      smem[r * RS + PAD(ky)] = __ldg(Tb + (size_t)ky * Nx + x);
+    }
+  }
+  __syncthreads();
+  // rebuild the half-size complex spectrum Z'' = 2Z from the packed real-input spectrum
+  for (int k = t; k <= M / 2; k += G) {
+    if (k == 0) {
+      const float2 x = s[0];
+      s[0] = make_float2(x.x + x.y, x.x - x.y);
+    } else if (k == M / 2) {
+      const float2 x = s[PAD(k)];
+      s[PAD(k)] = make_float2(2.f * x.x, -2.f * x.y);
+    } else {
+      const float2 xk = s[PAD(k)], xm = s[PAD(M - k)];
+      const float2 A = make_float2(xk.x + xm.x, xk.y - xm.y);
+      const float2 B = make_float2(xk.x - xm.x, xk.y + xm.y);
+      const float2 WB = cmulc(B, __ldg(rtw + k));  // conj(-i w^k) B
+      s[PAD(k)] = make_float2(A.x + WB.x, A.y + WB.y);
+      s[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
+    }
+  }
+  __syncthreads();
+  float2 v[E];
+  fft_load_regs<LM>(v, t, s);
+  FftRun<LM, +1>::run(v, t, s, tw);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];  // (q[2m], q[2m+1]) at PAD(m)
+  __syncthreads();
+
+  // correction (pressure.py:194-196): 4 columns per thread, rows 0..R-1
+  const float* sf = reinterpret_cast<const float*>(smem);
+  constexpr int QPR = N / 4;  // float4 groups per row
+  for (int idx = tid; idx < R * QPR; idx += NT) {
+    const int r = idx / QPR, g = idx % QPR;
+    const int x = x0 + r;
+    if (x >= Nx) break;
+    const int j = 4 * g, m = 2 * g;
+    const float* q0 = sf + 2 * (size_t)(r * RS);
+    const float* q1 = sf + 2 * (size_t)((r + 1) * RS);
+    const float2 a0 = *reinterpret_cast<const float2*>(q0 + 2 * PAD(m));
+    const float2 a1 = *reinterpret_cast<const float2*>(q0 + 2 * PAD(m + 1));
+    const float a2 = q0[2 * PAD((m + 2) & (M - 1))];
+    const float2 b0 = *reinterpret_cast<const float2*>(q1 + 2 * PAD(m));
+    const float2 b1 = *reinterpret_cast<const float2*>(q1 + 2 * PAD(m + 1));
+    const size_t off = (b * Nx + x) * (size_t)N + j;
+    const float4 u4 = ldg4(us + off), v4 = ldg4(vs + off);
+    float4 ou, ov;
+    ou.x = u4.x - (b0.x - a0.x) * inv_hx;
+    ou.y = u4.y - (b0.y - a0.y) * inv_hx;
+    ou.z = u4.z - (b1.x - a1.x) * inv_hx;
+    ou.w = u4.w - (b1.y - a1.y) * inv_hx;
+    ov.x = v4.x - (a0.y - a0.x) * inv_hy;
+    ov.y = v4.y - (a1.x - a0.y) * inv_hy;
+    ov.z = v4.z - (a1.y - a1.x) * inv_hy;
+    ov.w = v4.w - (a2 - a1.y) * inv_hy;
+    stg4(uo + off, ou);
+    stg4(vo + off, ov);
+    if (qo != nullptr) stg4(qo + off, make_float4(a0.x, a0.y, a1.x, a1.y));
+  }
+}
+
+// rhs = divergence(v)   (finite_differences.py:136-143) -- used by cfd_project only
+__global__ void divergence2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                    float* __restrict__ rhs, int Nx, int Ny, float inv_hx,
+                                    float inv_hy) {
+  const size_t b = blockIdx.z;
+  const int x = blockIdx.y;
+  const int j = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (j >= Ny) return;
+  const int xm = x == 0 ? Nx - 1 : x - 1;
+  const size_t off = (b * Nx + x) * (size_t)Ny + j, offm = (b * Nx + xm) * (size_t)Ny + j;
+  const float4 u0 = ldg4(u + off), um = ldg4(u + offm), v0 = ldg4(v + off);
+  const float vl = __ldg(v + (b * Nx + x) * (size_t)Ny + (j == 0 ? Ny - 1 : j - 1));
+  float4 d;
+  d.x = (u0.x - um.x) * inv_hx + (v0.x - vl) * inv_hy;
+  d.y = (u0.y - um.y) * inv_hx + (v0.y - v0.x) * inv_hy;
+  d.z = (u0.z - um.z) * inv_hx + (v0.z - v0.y) * inv_hy;
+  d.w = (u0.w - um.w) * inv_hx + (v0.w - v0.z) * inv_hy;
+  stg4(rhs + off, d);
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem)", e, __FILE__, __LINE__);
+  }
+  return 0;
+}
+
+// rows per CTA for the row kernels: as many as fit ~100 KB / 1024 threads, at most 32
+constexpr int rows_for(int LM) {
+  const int M = 1 << LM, G = (M < 16 ? 1 : M / 16);
+  int rows = 32;
+  while (rows > 1 && (rows * G > 1024 || rows * (long)row_stride(M, 16) * 8 > 140 * 1024)) rows /= 2;
+  return rows;
+}
+constexpr int lines_for(int LM) {
+  const int M = 1 << LM, G = (M < 16 ? 1 : M / 16);
+  int lines = 16;
+  while (lines > 1 && (lines * G > 256)) lines /= 2;
+  return lines;
+}
+
+template <int LM>
+int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, int Nx,
+                       const float2* tw, const float2* rtw) {
+  constexpr int ROWS_MAX = rows_for(LM);
+  using P = FftPlan<LM>;
+  // ROWS must divide Nx
+  auto go = [&](auto rows_c) -> int {
+    constexpr int ROWS = decltype(rows_c)::value;
+    constexpr size_t smem = (size_t)ROWS * row_stride(P::M, ROWS) * sizeof(float2);
+    auto k = rfft_rows_kernel<LM, ROWS>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  if (Nx >= ROWS_MAX) return go(std::integral_constant<int, ROWS_MAX>{});
+  if constexpr (ROWS_MAX > 16) {
+    if (Nx >= 16) return go(std::integral_constant<int, 16>{});
+  }
+  return set_error_msg("grid axis 0 too small for the row FFT kernel (need >= 16)");
+}
+
+template <int LM>
+int launch_xlines_t(cudaStream_t st, float2* T, int batch, int My, const float2* tw,
+                    const double* lamx, const double* lamy, double cutoff, float norm) {
+  constexpr int LINES = lines_for(LM);
+  using P = FftPlan<LM>;
+  constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
+  auto k = xlines_kernel<LM, LINES>;
+  if (int e = set_smem(k, smem)) return e;
+  const size_t nlines = (size_t)batch * My;
+  if (nlines % LINES) return set_error_msg("internal: line count not divisible");
+  k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, My, tw, lamx, lamy, cutoff, norm);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int LM>
+int launch_irfft_correct_t(cudaStream_t st, const float2* T, const float* us, const float* vs,
+                           float* uo, float* vo, float* qo, int batch, int Nx, const float2* tw,
+                           const float2* rtw, float inv_hx, float inv_hy) {
+  using P = FftPlan<LM>;
+  constexpr int ROWS_MAX = rows_for(LM);
+  constexpr int RP = ROWS_MAX < 2 ? 2 : ROWS_MAX;  // R = RP - 1 output rows per CTA
+  if constexpr (RP * P::G > 1024) {
+    return set_error_msg("last grid axis too long for the inverse row kernel (max 16384)");
+  } else {
+    constexpr size_t smem = (size_t)RP * row_stride(P::M, RP) * sizeof(float2);
+    auto k = irfft_rows_correct_kernel<LM, RP>;
+    if (int e = set_smem(k, smem)) return e;
+    constexpr int R = RP - 1;
+    k<<<dim3((Nx + R - 1) / R, batch), RP * P::G, smem, st>>>(T, us, vs, uo, vo, qo, Nx, tw, rtw,
+                                                            inv_hx, inv_hy);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+}
+
+}  // namespace
+
+#define CFD_DISPATCH_LM(lm, LO, HI, CALL)                       \
+  switch (lm) {                                                 \
+    case 4: { constexpr int LM_ = 4; CALL; } break;             \
+    case 5: { constexpr int LM_ = 5; CALL; } break;             \
+    case 6: { constexpr int LM_ = 6; CALL; } break;             \
+    case 7: { constexpr int LM_ = 7; CALL; } break;             \
+    case 8: { constexpr int LM_ = 8; CALL; } break;             \
+    case 9: { constexpr int LM_ = 9; CALL; } break;             \
+    case 10: { constexpr int LM_ = 10; CALL; } break;           \
+    case 11: { constexpr int LM_ = 11; CALL; } break;           \
+    case 12: { constexpr int LM_ = 12; CALL; } break;           \
+    case 13: { constexpr int LM_ = 13; CALL; } break;           \
+    case 14: { constexpr int LM_ = 14; CALL; } break;           \
+    default: return set_error_msg("unsupported FFT length (need 2^4 .. 2^14 complex points)"); \
+  }
+
+// lm_row = log2(Ny / 2)
+int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, int batch, int Nx,
+                     const float2* tw, const float2* rtw) {
+  CFD_DISPATCH_LM(lm_row, 4, 14, return launch_rfft_rows_t<LM_>(st, rhs, T, batch, Nx, tw, rtw));
+  return 0;
+}
+// lm_x = log2(Nx)
+int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const float2* tw,
+                  const double* lamx, const double* lamy, double cutoff, float norm) {
+  CFD_DISPATCH_LM(lm_x, 4, 14,
+                  return launch_xlines_t<LM_>(st, T, batch, My, tw, lamx, lamy, cutoff, norm));
+  return 0;
+}
+int launch_irfft_correct(cudaStream_t st, int lm_row, const float2* T, const float* us,
+                         const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
+                         const float2* tw, const float2* rtw, float inv_hx, float inv_hy) {
+  CFD_DISPATCH_LM(lm_row, 4, 14,
+                  return launch_irfft_correct_t<LM_>(st, T, us, vs, uo, vo, qo, batch, Nx, tw, rtw,
+                                                     inv_hx, inv_hy));
+  return 0;
+}
+int launch_divergence_2d(cudaStream_t st, const float* u, const float* v, float* rhs, int batch,
+                         int Nx, int Ny, float inv_hx, float inv_hy) {
+  const int threads = 128;
+  dim3 grid((Ny / 4 + threads - 1) / threads, Nx, batch);
+  divergence2d_kernel<<<grid, threads, 0, st>>>(u, v, rhs, Nx, Ny, inv_hx, inv_hy);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cfd

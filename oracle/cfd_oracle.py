@@ -85,11 +85,11 @@ def kolmogorov_field(shape, domain, scale=1.0, k=2, swap_xy=False, dtype=np.floa
   if swap_xy:
     x = grid_axes(shape, domain, faces[1], dtype)[0]
     prof = (dtype(scale) * np.sin((dtype(k) * x).astype(dtype)).astype(dtype)).astype(dtype)
-    out[1] = np.broadcast_to(prof.reshape((-1,) + (1,) * (ndim - 1)), shape).astype(dtype)
+    out[1] = np.ascontiguousarray(np.broadcast_to(prof.reshape((-1,) + (1,) * (ndim - 1)), shape), dtype)
   else:
     y = grid_axes(shape, domain, faces[0], dtype)[1]
     prof = (dtype(scale) * np.sin((dtype(k) * y).astype(dtype)).astype(dtype)).astype(dtype)
-    out[0] = np.broadcast_to(prof.reshape((1, -1) + (1,) * (ndim - 2)), shape).astype(dtype)
+    out[0] = np.ascontiguousarray(np.broadcast_to(prof.reshape((1, -1) + (1,) * (ndim - 2)), shape), dtype)
   return tuple(out)
 
 
@@ -108,8 +108,8 @@ def taylor_green_field(shape, scale=1.0, k=2, dtype=np.float32):
   v = (v.astype(dtype) * dtype(scale)).astype(dtype)
   if len(shape) == 2:
     return (u, v)
-  u3 = np.broadcast_to(u[..., None], shape).astype(dtype)
-  v3 = np.broadcast_to(v[..., None], shape).astype(dtype)
+  u3 = np.ascontiguousarray(np.broadcast_to(u[..., None], shape), dtype)
+  v3 = np.ascontiguousarray(np.broadcast_to(v[..., None], shape), dtype)
   return (u3, v3, np.zeros(shape, dtype))
 
 

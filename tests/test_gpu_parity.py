@@ -1,0 +1,243 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden
+vectors.  Bar: per-step relative L2 <= 1e-5 on every velocity component
+and on q.  All tests here need a GPU."""
+import numpy as np
+import pytest
+
+import cfd_oracle
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # the north star's per-step relative L2 bar (float32)
+
+
+@pytest.fixture(scope='module')
+def cfd():
+  import jax_cfd_b200 as m
+  m._lib.require_device()
+  return m
+
+
+def make_forcing(cfd, grid, rec):
+  fs = []
+  for kind, arg in (rec['forcing_spec'] or []):
+    if kind == 'kolmogorov':
+      fs.append(cfd.forcings.kolmogorov_forcing(grid, **arg))
+    elif kind == 'taylor_green':
+      fs.append(cfd.forcings.taylor_green_forcing(grid, **arg))
+    elif kind == 'linear':
+      fs.append(cfd.forcings.linear_forcing(grid, arg))
+  if not fs:
+    return None
+  return cfd.forcings.sum_forcings(*fs) if len(fs) > 1 else fs[0]
+
+
+def wrap(cfd, grid, arrays, device=True):
+  bc = cfd.boundaries.periodic_boundary_conditions(grid.ndim)
+  conv = (lambda a: cfd.DeviceArray.from_numpy(np.ascontiguousarray(a, np.float32))) if device else (
+      lambda a: np.ascontiguousarray(a, np.float32))
+  return tuple(cfd.grids.GridVariable(cfd.grids.GridArray(conv(a), o, grid), bc)
+               for a, o in zip(arrays, grid.cell_faces))
+
+
+def to_np(v):
+  return [np.asarray(u.data) for u in v]
+
+
+def build_step(cfd, rec, grid, stepper=None):
+  kw = dict(density=rec['density'], viscosity=rec['viscosity'], dt=rec['dt'], grid=grid,
+            forcing=make_forcing(cfd, grid, rec))
+  if stepper is not None:
+    kw['time_stepper'] = getattr(cfd.time_stepping, stepper)
+  if rec['smag_cs'] >= 0:
+    dt = kw.pop('dt')
+    return cfd.subgrid_models.explicit_smagorinsky_navier_stokes(dt=dt, cs=rec['smag_cs'], **kw)
+  return cfd.equations.semi_implicit_navier_stokes(**kw)
+
+
+GOLDEN_2D = ['k2d_64x32', 'd2d_128', 'k2d_32x64_rho', 'tg2d_32']
+
+
+@pytest.mark.parametrize('name', GOLDEN_2D)
+def test_step_matches_reference_golden(cfd, name):
+  rec = gu.load(name)
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  step = build_step(cfd, rec, grid)
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(2)])
+  # first step, with q
+  v1, q = step.advance(v, 1, return_q=True)
+  for i, a in enumerate(to_np(v1)):
+    assert gu.rel_l2(a, rec[f'f32_v1_{i}']) < TOL
+    assert gu.rel_l2(a, rec[f'f64_v1_{i}']) < TOL
+  assert gu.rel_l2(np.asarray(q), rec['f32_q']) < TOL
+  # all recorded step counts through repeated()
+  for n in rec['nsteps']:
+    vn = cfd.funcutils.repeated(step, n)(v)
+    for i, a in enumerate(to_np(vn)):
+      err = gu.rel_l2(a, rec[f'f32_v{n}_{i}'])
+      assert err < TOL * max(1, n / 2), (name, n, i, err)
+
+
+@pytest.mark.parametrize('name', ['rk4_2d_32', 'rk2_2d_32'])
+def test_rk_steppers_match_reference_golden(cfd, name):
+  rec = gu.load(name)
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  step = build_step(cfd, rec, grid, stepper=rec['stepper'])
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(2)])
+  done = 0
+  for n in rec['nsteps']:
+    for _ in range(n - done):
+      v = step(v)
+    done = n
+    for i, a in enumerate(to_np(v)):
+      assert gu.rel_l2(a, rec[f'f32_v{n}_{i}']) < TOL * n
+
+
+def test_projection_matches_reference_golden(cfd):
+  rec = gu.load('proj2d_64x32')
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(2)])
+  vp = cfd.pressure.projection(v)
+  q = cfd.pressure.solve_fast_diag(v)
+  assert q.offset == grid.cell_center
+  assert gu.rel_l2(np.asarray(q.data), rec['f32_q']) < TOL
+  for i, a in enumerate(to_np(vp)):
+    assert gu.rel_l2(a, rec[f'f32_proj_{i}']) < TOL
+    assert vp[i].offset == grid.cell_faces[i]
+  # pressure_test.py:59-110: div(projection(v)) ~ 0
+  div = cfd_oracle.divergence(to_np(vp), rec['h'])
+  assert np.abs(div).max() < 1e-3  # white-noise input of magnitude ~3/h
+
+
+@pytest.mark.parametrize('shape,nsteps', [((256, 256), 10), ((512, 1024), 3), ((1024, 64), 3),
+                                         ((16, 32), 5), ((2048, 2048), 1)])
+def test_step_matches_oracle(cfd, shape, nsteps):
+  dom = ((0.0, 2 * np.pi), (0.0, 2 * np.pi))
+  grid = cfd.grids.Grid(shape, domain=dom)
+  v0 = cfd_oracle.filtered_velocity_field(42, shape, dom, 3.0, 4)
+  dt = 0.5 * min(grid.step) / 3.0
+  nu = 1e-3 if max(shape) <= 512 else 1e-4
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, nu, dt, grid, forcing=forcing)
+  of = cfd_oracle.Forcing((('const', cfd_oracle.kolmogorov_field(shape, dom, 1.0, 4)),
+                           ('linear', -0.1)))
+  got, q = step.advance(wrap(cfd, grid, v0), nsteps, return_q=True)
+  want = v0
+  for n in range(nsteps):
+    want, wq = cfd_oracle.step(want, dt, grid.step, 1.0, nu, of, return_q=True)
+  for a, b in zip(to_np(got), want):
+    assert gu.rel_l2(a, b) < TOL
+  assert gu.rel_l2(np.asarray(q), wq) < TOL
+  # divergence-free residual (equations_test.py:99: max|div| stays small)
+  assert np.abs(cfd_oracle.divergence(to_np(got), grid.step)).max() < 2e-3
+
+
+def test_host_and_device_paths_agree_bitwise(cfd):
+  rec = gu.load('k2d_64x32')
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  step = build_step(cfd, rec, grid)
+  arrays = [rec[f'v0_{i}'] for i in range(2)]
+  dev = to_np(cfd.funcutils.repeated(step, 4)(wrap(cfd, grid, arrays, device=True)))
+  host_v = cfd.funcutils.repeated(step, 4)(wrap(cfd, grid, arrays, device=False))
+  for a, u in zip(dev, host_v):
+    assert isinstance(u.data, np.ndarray)
+    np.testing.assert_array_equal(a, u.data)
+  loop = wrap(cfd, grid, arrays, device=True)
+  for _ in range(4):
+    loop = step(loop)
+  for a, b in zip(dev, to_np(loop)):
+    np.testing.assert_array_equal(a, b)
+
+
+def test_batched_members_equal_single_runs(cfd):
+  shape = (64, 128)
+  dom = ((0.0, 2 * np.pi), (0.0, 2 * np.pi))
+  grid = cfd.grids.Grid(shape, domain=dom)
+  members = [cfd_oracle.filtered_velocity_field(s, shape, dom, 2.0, 3) for s in range(3)]
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, grid, forcing=forcing)
+  batched = [np.stack([m[c] for m in members]) for c in range(2)]
+  out_b = to_np(cfd.funcutils.repeated(step, 3)(wrap(cfd, grid, batched)))
+  for s, m in enumerate(members):
+    out_s = to_np(cfd.funcutils.repeated(step, 3)(wrap(cfd, grid, m)))
+    for c in range(2):
+      np.testing.assert_array_equal(out_b[c][s], out_s[c])
+
+
+def test_explicit_terms_match_oracle(cfd):
+  rec = gu.load('k2d_64x32')
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  f = cfd.equations.navier_stokes_explicit_terms(rec['density'], rec['viscosity'], rec['dt'], grid,
+                                                 forcing=make_forcing(cfd, grid, rec))
+  arrays = [rec[f'v0_{i}'] for i in range(2)]
+  got = to_np(f(wrap(cfd, grid, arrays)))
+  want = cfd_oracle.explicit_terms(tuple(arrays), rec['dt'], rec['h'],
+                                   rec['viscosity'] / rec['density'], gu.oracle_forcing(rec),
+                                   rec['density'])
+  for a, b in zip(got, want):
+    assert gu.rel_l2(a, b) < TOL
+
+
+def test_diagnostics_match_oracle(cfd):
+  rec = gu.load('d2d_128')
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  arrays = [rec[f'f32_v20_{i}'] for i in range(2)]
+  got = cfd.diagnostics(wrap(cfd, grid, arrays))
+  want = cfd_oracle.diagnostics(arrays, rec['h'])
+  assert abs(got['kinetic_energy'] - want['kinetic_energy']) < 1e-6 * want['kinetic_energy']
+  assert abs(got['enstrophy'] - want['enstrophy']) < 1e-5 * want['enstrophy']
+  assert abs(got['max_speed_sq'] - want['max_speed_sq']) < 1e-6 * want['max_speed_sq']
+  assert abs(got['max_abs_div'] - want['max_div']) < 1e-4
+
+
+def test_full_size_properties_2048(cfd):
+  """BASELINE config #2 size: size-independent properties (no oracle needed)."""
+  shape = (2048, 2048)
+  dom = ((0.0, 2 * np.pi), (0.0, 2 * np.pi))
+  grid = cfd.grids.Grid(shape, domain=dom)
+  rs = np.random.RandomState(0)
+  k = np.arange(shape[0]) * (2 * np.pi / shape[0])
+  u = (np.sin(3 * k)[:, None] * np.cos(5 * k)[None, :] + 0.1 * rs.standard_normal(shape)).astype(np.float32)
+  v = (np.cos(2 * k)[:, None] * np.sin(7 * k)[None, :] + 0.1 * rs.standard_normal(shape)).astype(np.float32)
+  vv = wrap(cfd, grid, [u, v])
+  p1 = cfd.pressure.projection(vv)
+  a1 = to_np(p1)
+  # (1) divergence-free, (2) idempotent, (3) mean (momentum) preserved, (4) linear
+  assert np.abs(cfd_oracle.divergence(a1, grid.step)).max() < 5e-2 * np.abs(cfd_oracle.divergence([u, v], grid.step)).max() * 1e-3
+  a2 = to_np(cfd.pressure.projection(p1))
+  for x, y in zip(a1, a2):
+    assert gu.rel_l2(y, x) < 1e-5
+  for x, y in zip([u, v], a1):
+    assert abs(float(x.mean(dtype=np.float64)) - float(y.mean(dtype=np.float64))) < 1e-6
+  a3 = to_np(cfd.pressure.projection(wrap(cfd, grid, [2 * u, 2 * v])))
+  for x, y in zip(a1, a3):
+    assert gu.rel_l2(y, 2 * x) < 1e-6
+  # full step: stays divergence free, momentum conserved without forcing (equations_test.py:84-163)
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-4, 0.2 * grid.step[0], grid)
+  s = to_np(cfd.funcutils.repeated(step, 5)(p1))
+  assert np.abs(cfd_oracle.divergence(s, grid.step)).max() < 1e-2
+  for x, y in zip(a1, s):
+    assert abs(float(x.mean(dtype=np.float64)) - float(y.mean(dtype=np.float64))) < 1e-5
+
+
+def test_unsupported_options_raise(cfd):
+  grid = cfd.grids.Grid((64, 64), domain=((0, 1), (0, 1)))
+  with pytest.raises(NotImplementedError):
+    cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, grid, convect=lambda v: v)
+  with pytest.raises(NotImplementedError):
+    cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, grid, forcing=lambda v: v)
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, grid)
+  bc = cfd.boundaries.periodic_boundary_conditions(2)
+  bad = tuple(cfd.grids.GridVariable(cfd.grids.GridArray(np.zeros((64, 64), np.float32), (0.5, 0.5), grid), bc)
+              for _ in range(2))
+  with pytest.raises(cfd.grids.InconsistentOffsetError):
+    step(bad)
+  g3 = cfd.grids.Grid((48, 64), domain=((0, 1), (0, 1)))
+  s3 = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, g3)
+  v3 = tuple(cfd.grids.GridVariable(cfd.grids.GridArray(np.zeros((48, 64), np.float32), o, g3), bc)
+             for o in g3.cell_faces)
+  with pytest.raises(cfd.CfdError):
+    s3(v3)  # non power-of-two axis
