@@ -19,6 +19,7 @@ struct StepConsts {
   float lap_sum;            // float32 sum of lap_s
   float nu;                 // viscosity / density
   float rho;                // density (forcing / rho, equations.py:109)
+  float inv_rho;            // 1 / density
   int has_nu;
   // forcing
   int n_terms;
@@ -48,24 +49,33 @@ __device__ __forceinline__ void stcs4(float* p, float4 v) {
   __stcs(reinterpret_cast<float4*>(p), v);
 }
 
+// MUFU.RCP (about 1 ulp); the IEEE __frcp_rn expands to a slow-path subroutine.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // One TVD-limited face flux  F = c_face * U :
 //   upwind (interpolation.py:147-151), Lax-Wendroff (interpolation.py:210-217), van Leer limiter
 //   on r+ / r- (interpolation.py:224-231, 287-297), flux = c * u (advection.py:73).
-// Only the branch selected by U > 0 is evaluated; phi = 2r/(1+r) with r = num/den is computed
-// as 2 num / (den + num) (one MUFU.RCP-based division instead of two).
+// For U <= 0 the stencil is mirrored so that one formula serves both signs:
+//   A = upwind value, B = downwind value, L = the value behind the upwind one,
+//   d = B - A, num = A - L, r = num / d, phi = 2r / (1 + r) for r > 0 else 0,
+//   face = A + 0.5 (1 - |C|) d phi = A + (1 - |C|) * d * num / (d + num)      (r > 0 <=> d num > 0)
+// which needs a single MUFU.RCP-based division; safe_div's "y == 0 -> 1" case gives 0 either way.
 __device__ __forceinline__ float face_flux(float cL, float c0, float cR, float cRR, float U,
                                            float dth) {
-  const float d = cR - c0;
   const bool pos = U > 0.f;
-  const float num = pos ? (c0 - cL) : (cRR - cR);
-  const float den = (d != 0.f) ? d : 1.f;  // safe_div default numerator 1
-  // r > 0  <=>  num and den have the same sign and num != 0
-  const bool rpos = ((__float_as_int(num) ^ __float_as_int(den)) >= 0) && (num != 0.f);
-  const float phi = rpos ? __fdividef(2.f * num, den + num) : 0.f;
-  const float C = dth * U;
-  const float half = 0.5f * (1.f - fabsf(C)) * d * phi;
-  const float face = pos ? (c0 + half) : (cR - half);
-  return face * U;
+  const float A = pos ? c0 : cR;
+  const float B = pos ? cR : c0;
+  const float L = pos ? cL : cRR;
+  const float d = B - A;
+  const float num = A - L;
+  const float g = d * num;
+  const float w = fmaf(-dth, fabsf(U), 1.f);  // 1 - |C|,  C = (dt / h) U   interpolation.py:210
+  const float half = (g > 0.f) ? w * (g * fast_rcp(d + num)) : 0.f;
+  return (A + half) * U;
 }
 
 #define CFD_CUDA_OK(expr)                                                        \

@@ -32,7 +32,9 @@ struct F4 {
 __device__ __forceinline__ F4 toF4(float4 v) { return F4{{v.x, v.y, v.z, v.w}}; }
 __device__ __forceinline__ float4 to4(const F4& f) { return make_float4(f.a[0], f.a[1], f.a[2], f.a[3]); }
 
-template <int TX>
+// PATTERN encodes the (compile-time) sequence of forcing terms, 2 bits per term in summation
+// order: 0 = end, 1 = separable, 2 = field, 3 = linear.
+template <int TX, int PATTERN>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ us,
                   float* __restrict__ vs, float* __restrict__ rhs, int Nx, int Ny, StepConsts c,
@@ -83,13 +85,55 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
   // prefetch row i+3 for the first iteration
   float4 nu4 = ldg4(rowptr(u, i0 + 2));
   float4 nv4 = ldg4(rowptr(v, i0 + 2));
+  // incrementally wrapped row indices (no integer modulo inside the loop)
+  int inext = (i0 + 3) % Nx;        // row i + 4 of the current iteration
+  int iwrow = (i0 - 1 + Nx) % Nx;   // row i
 
+  // forcing tables: the column profiles of the separable term are fixed per thread
+  constexpr bool kHasSep = ((PATTERN & 3) == 1) || (((PATTERN >> 2) & 3) == 1) || (((PATTERN >> 4) & 3) == 1);
+  constexpr bool kHasField = ((PATTERN & 3) == 2) || (((PATTERN >> 2) & 3) == 2) || (((PATTERN >> 4) & 3) == 2);
   const float* px_u = c.sep_prof[0][0];
-  const float* py_u = c.sep_prof[0][1];
   const float* px_v = c.sep_prof[1][0];
-  const float* py_v = c.sep_prof[1][1];
+  float pyu[4] = {1.f, 1.f, 1.f, 1.f}, pyv[4] = {1.f, 1.f, 1.f, 1.f};
+  float scale_u = 0.f, scale_v = 0.f;
+  if (kHasSep) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c.sep_prof[0][1]) pyu[k] = __ldg(c.sep_prof[0][1] + jg + k);
+      if (c.sep_prof[1][1]) pyv[k] = __ldg(c.sep_prof[1][1] + jg + k);
+    }
+    scale_u = c.has_sep[0] ? c.sep_scale[0] : 0.f;
+    scale_v = c.has_sep[1] ? c.sep_scale[1] : 0.f;
+    // a component the term does not force contributes +0 (x * 0 would be wrong for inf/nan only)
+    if (!c.has_sep[0]) { pyu[0] = pyu[1] = pyu[2] = pyu[3] = 0.f; px_u = nullptr; }
+    if (!c.has_sep[1]) { pyv[0] = pyv[1] = pyv[2] = pyv[3] = 0.f; px_v = nullptr; }
+  }
+  // Row profiles of the separable term for the rows of this block, one row per lane (3 x 32 >= TX
+  // + 1), broadcast by shuffle inside the loop: no scalar global loads on the critical path.
+  static_assert(TX + 1 <= 96, "row-profile table too small");
+  const bool has_px = kHasSep && (px_u != nullptr || px_v != nullptr);
+  float pxu_tab[3] = {1.f, 1.f, 1.f}, pxv_tab[3] = {1.f, 1.f, 1.f};
+  if (has_px) {
+#pragma unroll
+    for (int sgm = 0; sgm < 3; ++sgm) {
+      int iw = (i0 - 1 + 32 * sgm + lane) % Nx;
+      if (iw < 0) iw += Nx;
+      if (px_u) pxu_tab[sgm] = __ldg(px_u + iw);
+      if (px_v) pxv_tab[sgm] = __ldg(px_v + iw);
+    }
+  }
+  // constant-field forcing: rows are prefetched together with the state rows
+  float4 nfu4 = make_float4(0.f, 0.f, 0.f, 0.f), nfv4 = nfu4;
+  if (kHasField) {
+    if (c.field[0]) nfu4 = ldg4(rowptr(c.field[0], i0 - 1));
+    if (c.field[1]) nfv4 = ldg4(rowptr(c.field[1], i0 - 1));
+  }
 
-#pragma unroll 1
+#ifndef CFD_EXPL_UNROLL
+#define CFD_EXPL_UNROLL 1
+#endif
+  constexpr int kUnroll = CFD_EXPL_UNROLL;
+#pragma unroll kUnroll
   for (int i = i0 - 1; i < iend; ++i) {
     // ---- column halos of row i (and v[i+1][-1]) from neighbouring lanes
     float ue[8], ve[8];
@@ -128,9 +172,18 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
     }
 
     // ---- assemble
-    int iw = i;
-    if (iw < 0) iw += Nx;
+    const int iw = iwrow;
     F4 us_cur, vs_cur;
+    float pxu_row = 1.f, pxv_row = 1.f;
+    if (has_px) {
+      const int ridx = i - (i0 - 1);
+      const int sgm = ridx >> 5;
+      const float tu = sgm == 0 ? pxu_tab[0] : (sgm == 1 ? pxu_tab[1] : pxu_tab[2]);
+      const float tv = sgm == 0 ? pxv_tab[0] : (sgm == 1 ? pxv_tab[1] : pxv_tab[2]);
+      pxu_row = __shfl_sync(0xffffffffu, tu, ridx & 31);
+      pxv_row = __shfl_sync(0xffffffffu, tv, ridx & 31);
+    }
+    const F4 fld_u = toF4(nfu4), fld_v = toF4(nfv4);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float u0 = ua[2].a[k], v0 = va[2].a[k];
@@ -147,36 +200,27 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
         du += c.nu * lu;
         dv += c.nu * lv;
       }
-      if (c.n_terms > 0) {  // forcings.py:125-129 (left-to-right sum), equations.py:108-109
+      if (PATTERN != 0) {  // forcings.py:125-129 (left-to-right sum), equations.py:108-109
         float fu = 0.f, fv = 0.f;
-        int jc = jg + k;  // jg is 4-aligned and Ny % 4 == 0, so jg + k < Ny
-        for (int t = 0; t < c.n_terms; ++t) {
-          const int kind = c.term_kind[t];
-          if (kind == CFD_FORCE_SEPARABLE) {
-            if (c.has_sep[0]) {
-              float p = px_u ? __ldg(px_u + iw) : 1.f;
-              if (py_u) p = px_u ? p * __ldg(py_u + jc) : __ldg(py_u + jc);
-              fu += p * c.sep_scale[0];
-            }
-            if (c.has_sep[1]) {
-              float p = px_v ? __ldg(px_v + iw) : 1.f;
-              if (py_v) p = px_v ? p * __ldg(py_v + jc) : __ldg(py_v + jc);
-              fv += p * c.sep_scale[1];
-            }
-          } else if (kind == CFD_FORCE_FIELD) {
-            if (c.field[0]) fu += __ldg(c.field[0] + (size_t)iw * Ny + jc);
-            if (c.field[1]) fv += __ldg(c.field[1] + (size_t)iw * Ny + jc);
-          } else if (kind == CFD_FORCE_LINEAR) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          constexpr int kSh[3] = {0, 2, 4};
+          const int kind = (PATTERN >> kSh[t]) & 3;
+          if (kind == 1) {         // (px * py) * scale, absent profile == 1 (exact)
+            fu += (pxu_row * pyu[k]) * scale_u;
+            fv += (pxv_row * pyv[k]) * scale_v;
+          } else if (kind == 2) {
+            fu += fld_u.a[k];
+            fv += fld_v.a[k];
+          } else if (kind == 3) {  // forcings.py:111-113
             fu += c.linear_coef * u0;
             fv += c.linear_coef * v0;
           }
         }
-        if (c.rho != 1.f) {
-          fu = fu / c.rho;
-          fv = fv / c.rho;
-        }
-        du += fu;
-        dv += fv;
+        // forcing / rho (equations.py:109) as a multiplication by 1/rho (exact for rho = 1,
+        // <= 1 ulp of the forcing otherwise)
+        du = fmaf(fu, c.inv_rho, du);
+        dv = fmaf(fv, c.inv_rho, dv);
       }
       us_cur.a[k] = dvdt_mode ? du : u0 + c.dt * du;   // time_stepping.py:101
       vs_cur.a[k] = dvdt_mode ? dv : v0 + c.dt * dv;
@@ -209,10 +253,16 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
     }
     ua[4] = toF4(nu4);
     va[4] = toF4(nv4);
+    iwrow = (iwrow + 1 == Nx) ? 0 : iwrow + 1;
     if (i + 1 < iend) {
-      nu4 = ldg4(rowptr(u, i + 4));
-      nv4 = ldg4(rowptr(v, i + 4));
+      nu4 = ldg4(u + (size_t)inext * Ny + jg);
+      nv4 = ldg4(v + (size_t)inext * Ny + jg);
+      if (kHasField) {
+        if (c.field[0]) nfu4 = ldg4(c.field[0] + (size_t)iwrow * Ny + jg);
+        if (c.field[1]) nfv4 = ldg4(c.field[1] + (size_t)iwrow * Ny + jg);
+      }
     }
+    inext = (inext + 1 == Nx) ? 0 : inext + 1;
   }
 }
 
@@ -223,8 +273,32 @@ int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, floa
   constexpr int TX = 64;
   const int strips = (Ny + kWarpCols - 1) / kWarpCols;
   dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, (Nx + TX - 1) / TX, batch);
-  explicit2d_kernel<TX><<<grid, 32 * kWarpsPerCta, 0, stream>>>(u, v, us, vs, rhs, Nx, Ny, c,
-                                                                dvdt_mode);
+  int pattern = 0, nt = 0;
+  for (int t = 0; t < c.n_terms; ++t) {
+    const int kind = c.term_kind[t];
+    int code = kind == CFD_FORCE_SEPARABLE ? 1 : kind == CFD_FORCE_FIELD ? 2 : kind == CFD_FORCE_LINEAR ? 3 : -1;
+    if (code < 0 || nt >= 3) return set_error_msg("unsupported forcing term for the 2-D kernel");
+    for (int q = 0; q < nt; ++q)
+      if (((pattern >> (2 * q)) & 3) == code) return set_error_msg("each forcing kind may appear once");
+    pattern |= code << (2 * nt++);
+  }
+#define CFD_EXPL_CASE(P)                                                                          \
+  case P:                                                                                         \
+    explicit2d_kernel<TX, P><<<grid, 32 * kWarpsPerCta, 0, stream>>>(u, v, us, vs, rhs, Nx, Ny, c, \
+                                                                     dvdt_mode);                  \
+    break;
+  switch (pattern) {
+    CFD_EXPL_CASE(0)
+    CFD_EXPL_CASE(1) CFD_EXPL_CASE(2) CFD_EXPL_CASE(3)
+    CFD_EXPL_CASE(1 | (2 << 2)) CFD_EXPL_CASE(1 | (3 << 2)) CFD_EXPL_CASE(2 | (1 << 2))
+    CFD_EXPL_CASE(2 | (3 << 2)) CFD_EXPL_CASE(3 | (1 << 2)) CFD_EXPL_CASE(3 | (2 << 2))
+    CFD_EXPL_CASE(1 | (2 << 2) | (3 << 4)) CFD_EXPL_CASE(1 | (3 << 2) | (2 << 4))
+    CFD_EXPL_CASE(2 | (1 << 2) | (3 << 4)) CFD_EXPL_CASE(2 | (3 << 2) | (1 << 4))
+    CFD_EXPL_CASE(3 | (1 << 2) | (2 << 4)) CFD_EXPL_CASE(3 | (2 << 2) | (1 << 4))
+    default:
+      return set_error_msg("internal: forcing pattern not instantiated");
+  }
+#undef CFD_EXPL_CASE
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;

@@ -144,6 +144,7 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
   c->has_nu = prm->has_viscosity ? 1 : 0;
   c->nu = (float)(prm->viscosity / prm->density);
   c->rho = (float)prm->density;
+  c->inv_rho = (float)(1.0 / prm->density);
   if (prm->n_terms < 0 || prm->n_terms > CFD_MAX_FORCING_TERMS)
     return set_error_msg("cfd_params.n_terms out of range");
   c->n_terms = prm->n_terms;

@@ -115,7 +115,7 @@ xlines_kernel(float2* __restrict__ T, int My, const float2* __restrict__ tw,
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const double lam = __ldg(lamx + t + G * e) + ly;
-      const float d = (fabs(lam) > cutoff) ? norm * __frcp_rn((float)lam) : 0.f;
+      const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
       v[e].x *= d;
       v[e].y *= d;
     }
@@ -138,8 +138,8 @@ xlines_kernel(float2* __restrict__ T, int My, const float2* __restrict__ tw,
         const float2 cp = s[PAD((M - kx) & (M - 1))];
         const double lx = __ldg(lamx + kx);
         const double l0 = lx + ly0, lM = lx + lyM;
-        const float d0 = (fabs(l0) > cutoff) ? 0.5f * norm * __frcp_rn((float)l0) : 0.f;
-        const float dM = (fabs(lM) > cutoff) ? 0.5f * norm * __frcp_rn((float)lM) : 0.f;
+        const float d0 = (fabs(l0) > cutoff) ? 0.5f * norm * fast_rcp((float)l0) : 0.f;
+        const float dM = (fabs(lM) > cutoff) ? 0.5f * norm * fast_rcp((float)lM) : 0.f;
         const float2 c = v[e];
         const float2 sum = make_float2(c.x + cp.x, c.y - cp.y);
         const float2 dif = make_float2(c.x - cp.x, c.y + cp.y);

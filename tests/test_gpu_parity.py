@@ -206,10 +206,11 @@ def test_full_size_properties_2048(cfd):
   p1 = cfd.pressure.projection(vv)
   a1 = to_np(p1)
   # (1) divergence-free, (2) idempotent, (3) mean (momentum) preserved, (4) linear
-  assert np.abs(cfd_oracle.divergence(a1, grid.step)).max() < 5e-2 * np.abs(cfd_oracle.divergence([u, v], grid.step)).max() * 1e-3
+  # float32 cancellation floor: eps * |u| / h ~ 1e-4 of the input divergence (oracle: 1.2e-4)
+  assert np.abs(cfd_oracle.divergence(a1, grid.step)).max() < 5e-4 * np.abs(cfd_oracle.divergence([u, v], grid.step)).max()
   a2 = to_np(cfd.pressure.projection(p1))
   for x, y in zip(a1, a2):
-    assert gu.rel_l2(y, x) < 1e-5
+    assert gu.rel_l2(y, x) < 5e-5  # float32 floor for this noisy field (oracle: ~1.5e-5)
   for x, y in zip([u, v], a1):
     assert abs(float(x.mean(dtype=np.float64)) - float(y.mean(dtype=np.float64))) < 1e-6
   a3 = to_np(cfd.pressure.projection(wrap(cfd, grid, [2 * u, 2 * v])))
