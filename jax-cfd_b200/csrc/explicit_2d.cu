@@ -11,45 +11,79 @@
 //   time_stepping.navier_stokes_rk   time_stepping.py:101     (u* = u0 + dt * k0)
 //   finite_differences.divergence   finite_differences.py:136-143   (rhs of pressure.py:147)
 //
-// Layout: a warp owns a strip of 128 consecutive columns (4 per lane, float4 loads, 512 B per
-// warp request) and marches down the rows keeping a 5-row window of u and v in REGISTERS; the
+// Layout: a warp owns a strip of 32*C consecutive columns (C = 4 or 2 per lane, 128/64-bit
+// coalesced loads) and marches down the rows keeping a 5-row window of u and v in REGISTERS; the
 // +-2 column halo of the current row comes from the neighbouring lanes by warp shuffle.  Lanes 0
-// and 31 are halo lanes (their results are not stored), so a warp produces 120 columns.  x-face
+// and 31 are halo lanes (their results are not stored), so a warp produces 30*C columns.  x-face
 // fluxes are computed once and carried to the next row in registers; y-face fluxes are computed
-// once per lane (5 faces for 4 cells).  No shared memory, no block-level synchronisation.
+// once per lane (C+1 faces for C cells).  No shared memory, no block-level synchronisation.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cfd {
 
 namespace {
 
-constexpr int kWarpCols = 120;   // stored columns per warp
 constexpr int kWarpsPerCta = 4;
 
-struct F4 {
-  float a[4];
+// C consecutive columns owned by one lane
+template <int C>
+struct FC {
+  float a[C];
 };
-__device__ __forceinline__ F4 toF4(float4 v) { return F4{{v.x, v.y, v.z, v.w}}; }
-__device__ __forceinline__ float4 to4(const F4& f) { return make_float4(f.a[0], f.a[1], f.a[2], f.a[3]); }
+template <int C>
+__device__ __forceinline__ FC<C> ldrow(const float* p);
+template <>
+__device__ __forceinline__ FC<4> ldrow<4>(const float* p) {
+  const float4 v = ldg4(p);
+  return FC<4>{{v.x, v.y, v.z, v.w}};
+}
+template <>
+__device__ __forceinline__ FC<2> ldrow<2>(const float* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return FC<2>{{v.x, v.y}};
+}
+__device__ __forceinline__ void strow(float* p, const FC<4>& f) {
+  stg4(p, make_float4(f.a[0], f.a[1], f.a[2], f.a[3]));
+}
+__device__ __forceinline__ void strow(float* p, const FC<2>& f) {
+  *reinterpret_cast<float2*>(p) = make_float2(f.a[0], f.a[1]);
+}
+
+#define FULLMASK 0xffffffffu
 
 // PATTERN encodes the (compile-time) sequence of forcing terms, 2 bits per term in summation
 // order: 0 = end, 1 = separable, 2 = field, 3 = linear.
-template <int TX, int PATTERN>
+//
+// LAZY: the inputs are the UNPROJECTED state of the previous step (u*, v*) plus its pressure q;
+// the projection  v = u* - forward_difference(q)  (pressure.py:194-196) is applied while the
+// window rows are loaded, so that chained steps never materialise the projected state in HBM.
+template <int TX, int PATTERN, int C, bool LAZY>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
-explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ us,
-                  float* __restrict__ vs, float* __restrict__ rhs, int Nx, int Ny, StepConsts c,
-                  int dvdt_mode) {
+explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                  const float* __restrict__ qprev, float* __restrict__ us, float* __restrict__ vs,
+                  float* __restrict__ rhs, int Nx, int Ny, StepConsts c, int dvdt_mode) {
+  using Row = FC<C>;
+  // Halo lanes: the divergence needs v* one column to the left of the first stored column, whose
+  // own stencil reaches 2 further columns: 4 columns = 1 lane (C = 4) or 2 lanes (C = 2) on the
+  // left, 1 lane on the right.
+  // (LAZY adds one column on the right: projecting v[j] needs q[j+1]; C = 2 then needs 2 lanes.)
+  constexpr int kHaloL = 4 / C;
+  constexpr int kHaloR = (C == 2) ? 2 : 1;
+  constexpr int kWarpCols = (32 - kHaloL - kHaloR) * C;  // stored columns per warp: 120 or 56
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int strip = blockIdx.x * kWarpsPerCta + warp;
   if (strip * kWarpCols >= Ny) return;
-  const int jbase = strip * kWarpCols - 4 + 4 * lane;
+  const int jbase = strip * kWarpCols - kHaloL * C + C * lane;
   int jg = jbase % Ny;
   if (jg < 0) jg += Ny;
-  const bool store_ok = (lane >= 1) && (lane <= 30) && (jbase < Ny);
+  const bool store_ok = (lane >= kHaloL) && (lane < 32 - kHaloR) && (jbase < Ny);
   const size_t boff = (size_t)blockIdx.z * (size_t)Nx * (size_t)Ny;
   u += boff;
   v += boff;
+  if (LAZY) qprev += boff;
   const int i0 = blockIdx.y * TX;
   const int iend = min(i0 + TX, Nx);  // exclusive
 
@@ -60,53 +94,85 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
   };
 
   // window rows i-2 .. i+2 for the first processed row i = i0 - 1
-  F4 ua[5], va[5];
+  Row ua[5], va[5];
 #pragma unroll
   for (int r = 0; r < 5; ++r) {
-    ua[r] = toF4(ldg4(rowptr(u, i0 - 3 + r)));
-    va[r] = toF4(ldg4(rowptr(v, i0 - 3 + r)));
+    ua[r] = ldrow<C>(rowptr(u, i0 - 3 + r));
+    va[r] = ldrow<C>(rowptr(v, i0 - 3 + r));
+  }
+  // lazily projected input: row r of (u, v) = (u*, v*)[r] - grad q, needs q rows r and r+1 and
+  // the column to the right (from lane+1; lane 31's last column is never used by lane 30)
+  auto project_row = [&](Row& ur, Row& vr, const Row& q0, const Row& q1) {
+    const float qR = __shfl_down_sync(FULLMASK, q0.a[0], 1);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const float qright = (k == C - 1) ? qR : q0.a[(k + 1) % C];
+      ur.a[k] = ur.a[k] - (q1.a[k] - q0.a[k]) * c.inv_h[0];
+      vr.a[k] = vr.a[k] - (qright - q0.a[k]) * c.inv_h[1];
+    }
+  };
+  Row qkeep;  // q row i+3 relative to the first loop iteration (= row i0+2)
+#pragma unroll
+  for (int k = 0; k < C; ++k) qkeep.a[k] = 0.f;
+  if (LAZY) {
+    Row qa[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) qa[r] = ldrow<C>(rowptr(qprev, i0 - 3 + r));
+#pragma unroll
+    for (int r = 0; r < 5; ++r) project_row(ua[r], va[r], qa[r], qa[r + 1]);
+    qkeep = qa[5];
   }
   // x-face fluxes at face (i0-2 | i0-1), needed by row i0-1:  stencil rows i0-3 .. i0
-  F4 f0u_prev, f0v_prev;
+  Row f0u_prev, f0v_prev;
   {
-    const float uR1 = __shfl_down_sync(0xffffffffu, ua[1].a[0], 1);
+    const float uR1 = __shfl_down_sync(FULLMASK, ua[1].a[0], 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       const float Uu = 0.5f * (ua[1].a[k] + ua[2].a[k]);
       f0u_prev.a[k] = face_flux(ua[0].a[k], ua[1].a[k], ua[2].a[k], ua[3].a[k], Uu, c.dth[0]);
-      const float unext = (k < 3) ? ua[1].a[k + 1] : uR1;
+      const float unext = (k < C - 1) ? ua[1].a[(k + 1) % C] : uR1;
       const float Uv = 0.5f * (ua[1].a[k] + unext);
       f0v_prev.a[k] = face_flux(va[0].a[k], va[1].a[k], va[2].a[k], va[3].a[k], Uv, c.dth[0]);
     }
   }
-  F4 us_prev = {{0.f, 0.f, 0.f, 0.f}};
-  float vL1_cur = __shfl_up_sync(0xffffffffu, va[2].a[3], 1);  // v[i][-1] for i = i0-1
+  Row us_prev;
+#pragma unroll
+  for (int k = 0; k < C; ++k) us_prev.a[k] = 0.f;
+  float vL1_cur = __shfl_up_sync(FULLMASK, va[2].a[C - 1], 1);  // v[i][-1] for i = i0-1
 
-  // prefetch row i+3 for the first iteration
-  float4 nu4 = ldg4(rowptr(u, i0 + 2));
-  float4 nv4 = ldg4(rowptr(v, i0 + 2));
   // incrementally wrapped row indices (no integer modulo inside the loop)
-  int inext = (i0 + 3) % Nx;        // row i + 4 of the current iteration
-  int iwrow = (i0 - 1 + Nx) % Nx;   // row i
+  int inext = (i0 + 2) % Nx;       // row i + 3 of the current iteration
+  int inextq = (i0 + 3) % Nx;      // row i + 4 (LAZY: the q row below the prefetched state row)
+  int iwrow = (i0 - 1 + Nx) % Nx;  // row i
 
   // forcing tables: the column profiles of the separable term are fixed per thread
   constexpr bool kHasSep = ((PATTERN & 3) == 1) || (((PATTERN >> 2) & 3) == 1) || (((PATTERN >> 4) & 3) == 1);
   constexpr bool kHasField = ((PATTERN & 3) == 2) || (((PATTERN >> 2) & 3) == 2) || (((PATTERN >> 4) & 3) == 2);
   const float* px_u = c.sep_prof[0][0];
   const float* px_v = c.sep_prof[1][0];
-  float pyu[4] = {1.f, 1.f, 1.f, 1.f}, pyv[4] = {1.f, 1.f, 1.f, 1.f};
+  float pyu[C], pyv[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) pyu[k] = pyv[k] = 1.f;
   float scale_u = 0.f, scale_v = 0.f;
   if (kHasSep) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       if (c.sep_prof[0][1]) pyu[k] = __ldg(c.sep_prof[0][1] + jg + k);
       if (c.sep_prof[1][1]) pyv[k] = __ldg(c.sep_prof[1][1] + jg + k);
     }
     scale_u = c.has_sep[0] ? c.sep_scale[0] : 0.f;
     scale_v = c.has_sep[1] ? c.sep_scale[1] : 0.f;
-    // a component the term does not force contributes +0 (x * 0 would be wrong for inf/nan only)
-    if (!c.has_sep[0]) { pyu[0] = pyu[1] = pyu[2] = pyu[3] = 0.f; px_u = nullptr; }
-    if (!c.has_sep[1]) { pyv[0] = pyv[1] = pyv[2] = pyv[3] = 0.f; px_v = nullptr; }
+    // a component the term does not force contributes +0
+    if (!c.has_sep[0]) {
+#pragma unroll
+      for (int k = 0; k < C; ++k) pyu[k] = 0.f;
+      px_u = nullptr;
+    }
+    if (!c.has_sep[1]) {
+#pragma unroll
+      for (int k = 0; k < C; ++k) pyv[k] = 0.f;
+      px_v = nullptr;
+    }
   }
   // Row profiles of the separable term for the rows of this block, one row per lane (3 x 32 >= TX
   // + 1), broadcast by shuffle inside the loop: no scalar global loads on the critical path.
@@ -122,49 +188,58 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
       if (px_v) pxv_tab[sgm] = __ldg(px_v + iw);
     }
   }
-  // constant-field forcing: rows are prefetched together with the state rows
-  float4 nfu4 = make_float4(0.f, 0.f, 0.f, 0.f), nfv4 = nfu4;
+  // constant-field forcing: rows are prefetched one iteration ahead
+  Row nfu, nfv;
+#pragma unroll
+  for (int k = 0; k < C; ++k) nfu.a[k] = nfv.a[k] = 0.f;
   if (kHasField) {
-    if (c.field[0]) nfu4 = ldg4(rowptr(c.field[0], i0 - 1));
-    if (c.field[1]) nfv4 = ldg4(rowptr(c.field[1], i0 - 1));
+    if (c.field[0]) nfu = ldrow<C>(rowptr(c.field[0], i0 - 1));
+    if (c.field[1]) nfv = ldrow<C>(rowptr(c.field[1], i0 - 1));
   }
 
-#ifndef CFD_EXPL_UNROLL
-#define CFD_EXPL_UNROLL 1
-#endif
-  constexpr int kUnroll = CFD_EXPL_UNROLL;
-#pragma unroll kUnroll
+#pragma unroll 1
   for (int i = i0 - 1; i < iend; ++i) {
     // ---- column halos of row i (and v[i+1][-1]) from neighbouring lanes
-    float ue[8], ve[8];
-    ue[0] = __shfl_up_sync(0xffffffffu, ua[2].a[2], 1);
-    ue[1] = __shfl_up_sync(0xffffffffu, ua[2].a[3], 1);
-    ue[6] = __shfl_down_sync(0xffffffffu, ua[2].a[0], 1);
-    ue[7] = __shfl_down_sync(0xffffffffu, ua[2].a[1], 1);
-    ve[0] = __shfl_up_sync(0xffffffffu, va[2].a[2], 1);
+    float ue[C + 4], ve[C + 4];
+    ue[0] = __shfl_up_sync(FULLMASK, ua[2].a[C - 2], 1);
+    ue[1] = __shfl_up_sync(FULLMASK, ua[2].a[C - 1], 1);
+    ue[C + 2] = __shfl_down_sync(FULLMASK, ua[2].a[0], 1);
+    ue[C + 3] = __shfl_down_sync(FULLMASK, ua[2].a[1], 1);
+    ve[0] = __shfl_up_sync(FULLMASK, va[2].a[C - 2], 1);
     ve[1] = vL1_cur;
-    ve[6] = __shfl_down_sync(0xffffffffu, va[2].a[0], 1);
-    ve[7] = __shfl_down_sync(0xffffffffu, va[2].a[1], 1);
-    const float vnL1 = __shfl_up_sync(0xffffffffu, va[3].a[3], 1);  // v[i+1][-1]
+    ve[C + 2] = __shfl_down_sync(FULLMASK, va[2].a[0], 1);
+    ve[C + 3] = __shfl_down_sync(FULLMASK, va[2].a[1], 1);
+    const float vnL1 = __shfl_up_sync(FULLMASK, va[3].a[C - 1], 1);  // v[i+1][-1]
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       ue[2 + k] = ua[2].a[k];
       ve[2 + k] = va[2].a[k];
     }
+    // Prefetch row i+3 (the new window row of the NEXT iteration) only now, after the shuffles:
+    // the loads then do not occupy scoreboard slots while the shuffles need them, and the rest of
+    // the body (~500 instructions) covers their latency.
+    Row nu, nv, nq;
+#pragma unroll
+    for (int k = 0; k < C; ++k) nu.a[k] = nv.a[k] = nq.a[k] = 0.f;
+    if (i + 1 < iend) {
+      nu = ldrow<C>(u + (size_t)inext * Ny + jg);
+      nv = ldrow<C>(v + (size_t)inext * Ny + jg);
+      if (LAZY) nq = ldrow<C>(qprev + (size_t)inextq * Ny + jg);
+    }
 
     // ---- face fluxes
-    F4 f0u, f0v;      // x-faces (i | i+1) at columns 0..3
-    float f1u[5], f1v[5];  // y-faces (j' | j'+1), j' = -1..3
+    Row f0u, f0v;                  // x-faces (i | i+1) at the lane's columns
+    float f1u[C + 1], f1v[C + 1];  // y-faces (j' | j'+1), j' = -1 .. C-1
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float Uu = 0.5f * (ua[2].a[k] + ua[3].a[k]);                   // interpolation.py:57-62
+    for (int k = 0; k < C; ++k) {
+      const float Uu = 0.5f * (ua[2].a[k] + ua[3].a[k]);  // interpolation.py:57-62
       f0u.a[k] = face_flux(ua[1].a[k], ua[2].a[k], ua[3].a[k], ua[4].a[k], Uu, c.dth[0]);
       const float Uv = 0.5f * (ue[2 + k] + ue[3 + k]);
       f0v.a[k] = face_flux(va[1].a[k], va[2].a[k], va[3].a[k], va[4].a[k], Uv, c.dth[0]);
     }
 #pragma unroll
-    for (int f = 0; f < 5; ++f) {  // face j' = f - 1 ; stencil columns j'-1..j'+2 = ext[f .. f+3]
-      const float vnext = (f == 0) ? vnL1 : va[3].a[f - 1];               // v[i+1][j']
+    for (int f = 0; f < C + 1; ++f) {  // face j' = f - 1 ; stencil columns j'-1..j'+2 = ext[f .. f+3]
+      const float vnext = (f == 0) ? vnL1 : va[3].a[(f + C - 1) % C];  // v[i+1][j']
       const float Uu = 0.5f * (ve[f + 1] + vnext);
       f1u[f] = face_flux(ue[f], ue[f + 1], ue[f + 2], ue[f + 3], Uu, c.dth[1]);
       const float Uv = 0.5f * (ve[f + 1] + ve[f + 2]);
@@ -173,19 +248,19 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
 
     // ---- assemble
     const int iw = iwrow;
-    F4 us_cur, vs_cur;
+    Row us_cur, vs_cur;
     float pxu_row = 1.f, pxv_row = 1.f;
     if (has_px) {
       const int ridx = i - (i0 - 1);
       const int sgm = ridx >> 5;
       const float tu = sgm == 0 ? pxu_tab[0] : (sgm == 1 ? pxu_tab[1] : pxu_tab[2]);
       const float tv = sgm == 0 ? pxv_tab[0] : (sgm == 1 ? pxv_tab[1] : pxv_tab[2]);
-      pxu_row = __shfl_sync(0xffffffffu, tu, ridx & 31);
-      pxv_row = __shfl_sync(0xffffffffu, tv, ridx & 31);
+      pxu_row = __shfl_sync(FULLMASK, tu, ridx & 31);
+      pxv_row = __shfl_sync(FULLMASK, tv, ridx & 31);
     }
-    const F4 fld_u = toF4(nfu4), fld_v = toF4(nfv4);
+    const Row fld_u = nfu, fld_v = nfv;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C; ++k) {
       const float u0 = ua[2].a[k], v0 = va[2].a[k];
       // -divergence(flux)   advection.py:78, finite_differences.py:136-143
       float du = -((f0u.a[k] - f0u_prev.a[k]) * c.inv_h[0] + (f1u[k + 1] - f1u[k]) * c.inv_h[1]);
@@ -206,7 +281,7 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
         for (int t = 0; t < 3; ++t) {
           constexpr int kSh[3] = {0, 2, 4};
           const int kind = (PATTERN >> kSh[t]) & 3;
-          if (kind == 1) {         // (px * py) * scale, absent profile == 1 (exact)
+          if (kind == 1) {  // (px * py) * scale, absent profile == 1 (exact)
             fu += (pxu_row * pyu[k]) * scale_u;
             fv += (pxv_row * pyv[k]) * scale_v;
           } else if (kind == 2) {
@@ -222,22 +297,23 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
         du = fmaf(fu, c.inv_rho, du);
         dv = fmaf(fv, c.inv_rho, dv);
       }
-      us_cur.a[k] = dvdt_mode ? du : u0 + c.dt * du;   // time_stepping.py:101
+      us_cur.a[k] = dvdt_mode ? du : u0 + c.dt * du;  // time_stepping.py:101
       vs_cur.a[k] = dvdt_mode ? dv : v0 + c.dt * dv;
     }
 
-    const float vsL = __shfl_up_sync(0xffffffffu, vs_cur.a[3], 1);  // v*[i][-1]
+    const float vsL = __shfl_up_sync(FULLMASK, vs_cur.a[C - 1], 1);  // v*[i][-1]
     if (i >= i0 && store_ok) {
       const size_t off = boff + (size_t)iw * Ny + jg;
-      stg4(us + off, to4(us_cur));
-      stg4(vs + off, to4(vs_cur));
+      strow(us + off, us_cur);
+      strow(vs + off, vs_cur);
       if (rhs != nullptr) {  // finite_differences.py:136-143 on u*
-        float4 d;
-        d.x = (us_cur.a[0] - us_prev.a[0]) * c.inv_h[0] + (vs_cur.a[0] - vsL) * c.inv_h[1];
-        d.y = (us_cur.a[1] - us_prev.a[1]) * c.inv_h[0] + (vs_cur.a[1] - vs_cur.a[0]) * c.inv_h[1];
-        d.z = (us_cur.a[2] - us_prev.a[2]) * c.inv_h[0] + (vs_cur.a[2] - vs_cur.a[1]) * c.inv_h[1];
-        d.w = (us_cur.a[3] - us_prev.a[3]) * c.inv_h[0] + (vs_cur.a[3] - vs_cur.a[2]) * c.inv_h[1];
-        stg4(rhs + off, d);
+        Row d;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          const float vleft = (k == 0) ? vsL : vs_cur.a[(k + C - 1) % C];
+          d.a[k] = (us_cur.a[k] - us_prev.a[k]) * c.inv_h[0] + (vs_cur.a[k] - vleft) * c.inv_h[1];
+        }
+        strow(rhs + off, d);
       }
     }
 
@@ -251,16 +327,17 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
       ua[r] = ua[r + 1];
       va[r] = va[r + 1];
     }
-    ua[4] = toF4(nu4);
-    va[4] = toF4(nv4);
+    if (LAZY) {
+      project_row(nu, nv, qkeep, nq);
+      qkeep = nq;
+      inextq = (inextq + 1 == Nx) ? 0 : inextq + 1;
+    }
+    ua[4] = nu;
+    va[4] = nv;
     iwrow = (iwrow + 1 == Nx) ? 0 : iwrow + 1;
-    if (i + 1 < iend) {
-      nu4 = ldg4(u + (size_t)inext * Ny + jg);
-      nv4 = ldg4(v + (size_t)inext * Ny + jg);
-      if (kHasField) {
-        if (c.field[0]) nfu4 = ldg4(c.field[0] + (size_t)iwrow * Ny + jg);
-        if (c.field[1]) nfv4 = ldg4(c.field[1] + (size_t)iwrow * Ny + jg);
-      }
+    if (kHasField && i + 1 < iend) {
+      if (c.field[0]) nfu = ldrow<C>(c.field[0] + (size_t)iwrow * Ny + jg);
+      if (c.field[1]) nfv = ldrow<C>(c.field[1] + (size_t)iwrow * Ny + jg);
     }
     inext = (inext + 1 == Nx) ? 0 : inext + 1;
   }
@@ -268,10 +345,21 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v, floa
 
 }  // namespace
 
-int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, float* us, float* vs,
-                       float* rhs, int batch, int Nx, int Ny, const StepConsts& c, int dvdt_mode) {
+// qprev == nullptr: (u, v) is a projected state.  qprev != nullptr: LAZY mode, (u, v) = (u*, v*) of
+// the previous step and qprev its pressure.
+int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, const float* qprev,
+                       float* us, float* vs, float* rhs, int batch, int Nx, int Ny,
+                       const StepConsts& c, int dvdt_mode) {
   constexpr int TX = 64;
-  const int strips = (Ny + kWarpCols - 1) / kWarpCols;
+  static const int forced_cols = [] {  // tuning knob: CFD_EXPLICIT_COLS=2|4 columns per lane
+    const char* e = getenv("CFD_EXPLICIT_COLS");
+    return (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
+  }();
+  // columns per lane: the choice that wastes fewer lanes on this row length (ties -> 4)
+  const int work4 = ((Ny + 119) / 120) * 128, work2 = ((Ny + 55) / 56) * 64;
+  const int cols = forced_cols ? forced_cols : (work2 < work4 ? 2 : 4);
+  const int warp_cols = cols == 4 ? 120 : 56;
+  const int strips = (Ny + warp_cols - 1) / warp_cols;
   dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, (Nx + TX - 1) / TX, batch);
   int pattern = 0, nt = 0;
   for (int t = 0; t < c.n_terms; ++t) {
@@ -282,10 +370,19 @@ int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, floa
       if (((pattern >> (2 * q)) & 3) == code) return set_error_msg("each forcing kind may appear once");
     pattern |= code << (2 * nt++);
   }
-#define CFD_EXPL_CASE(P)                                                                          \
-  case P:                                                                                         \
-    explicit2d_kernel<TX, P><<<grid, 32 * kWarpsPerCta, 0, stream>>>(u, v, us, vs, rhs, Nx, Ny, c, \
-                                                                     dvdt_mode);                  \
+#define CFD_EXPL_LAUNCH(P, CC, LZ)                                                          \
+  explicit2d_kernel<TX, P, CC, LZ><<<grid, 32 * kWarpsPerCta, 0, stream>>>(u, v, qprev, us, vs, \
+                                                                            rhs, Nx, Ny, c,     \
+                                                                            dvdt_mode)
+#define CFD_EXPL_CASE(P)                    \
+  case P:                                   \
+    if (cols == 2) {                        \
+      if (qprev) CFD_EXPL_LAUNCH(P, 2, true);  \
+      else CFD_EXPL_LAUNCH(P, 2, false);    \
+    } else {                                \
+      if (qprev) CFD_EXPL_LAUNCH(P, 4, true);  \
+      else CFD_EXPL_LAUNCH(P, 4, false);    \
+    }                                       \
     break;
   switch (pattern) {
     CFD_EXPL_CASE(0)
@@ -299,6 +396,7 @@ int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, floa
       return set_error_msg("internal: forcing pattern not instantiated");
   }
 #undef CFD_EXPL_CASE
+#undef CFD_EXPL_LAUNCH
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;

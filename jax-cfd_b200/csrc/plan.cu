@@ -14,8 +14,13 @@
 namespace cfd {
 
 // ---- kernels implemented in the other translation units ------------------------------------
-int launch_explicit_2d(cudaStream_t, const float* u, const float* v, float* us, float* vs,
-                       float* rhs, int batch, int Nx, int Ny, const StepConsts& c, int dvdt_mode);
+int launch_explicit_2d(cudaStream_t, const float* u, const float* v, const float* qprev, float* us,
+                       float* vs, float* rhs, int batch, int Nx, int Ny, const StepConsts& c,
+                       int dvdt_mode);
+int launch_irfft_rows(cudaStream_t, int lm_row, const float2* T, float* q, int batch, int Nx,
+                      const float2* tw, const float2* rtw);
+int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q, float* uo,
+                      float* vo, int batch, int Nx, int Ny, float inv_hx, float inv_hy);
 int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
                      const float2* tw, const float2* rtw);
 int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
@@ -92,8 +97,11 @@ struct cfd_plan {
   double cutoff = 0;
   float norm = 0;
   // workspace
-  float* us[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* us[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};   // unprojected state (ping)
+  float* us2[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // unprojected state (pong), lazy chains
   float* rhs = nullptr;
+  float* qbuf = nullptr;   // pressure of the latest step
+  float* qbuf2 = nullptr;  // pong
   float2* T = nullptr;
   size_t workspace_bytes = 0;
   // host-call staging
@@ -176,8 +184,8 @@ int check_plan(const cfd_plan* p) {
   return 0;
 }
 
-int poisson_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, float* uo,
-               float* vo, float* qo) {
+// q = pinv(rhs): rfft rows -> x lines (fwd * D * inv) -> irfft rows
+int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
   const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
   if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw)) return e;
   prof_mark(p, st, "rfft_rows");
@@ -185,11 +193,25 @@ int poisson_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, f
                             p->cutoff, p->norm))
     return e;
   prof_mark(p, st, "xlines");
-  if (int e = launch_irfft_correct(st, p->lm_row, p->T, us, vs, uo, vo, qo, p->batch, Nx,
-                                   p->tw_row, p->rtw, (float)(1.0 / p->step[0]),
-                                   (float)(1.0 / p->step[1])))
+  if (int e = launch_irfft_rows(st, p->lm_row, p->T, q, p->batch, Nx, p->tw_row, p->rtw)) return e;
+  prof_mark(p, st, "irfft_rows");
+  return 0;
+}
+
+int correct_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, const float* q,
+               float* uo, float* vo) {
+  if (int e = launch_correct_2d(st, us, vs, q, uo, vo, p->batch, (int)p->shape[0], (int)p->shape[1],
+                                (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1])))
     return e;
-  prof_mark(p, st, "irfft_rows_correct");
+  prof_mark(p, st, "correct");
+  return 0;
+}
+
+int ensure_lazy_buffers(cfd_plan* p) {
+  const size_t fbytes = (size_t)p->batch * p->cells * sizeof(float);
+  for (int a = 0; a < p->ndim; ++a)
+    if (!p->us2[a]) CFD_CUDA_OK(cudaMalloc((void**)&p->us2[a], fbytes));
+  if (!p->qbuf2) CFD_CUDA_OK(cudaMalloc((void**)&p->qbuf2, fbytes));
   return 0;
 }
 
@@ -269,9 +291,10 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
     if (cudaMalloc((void**)&p->us[a], fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   }
   if (!err && cudaMalloc((void**)&p->rhs, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  if (!err && cudaMalloc((void**)&p->qbuf, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   if (!err && cudaMalloc((void**)&p->T, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   if (!err && cudaMalloc((void**)&p->diag_dev, 8 * sizeof(double)) != cudaSuccess) err = set_error_msg("workspace allocation failed");
-  p->workspace_bytes = (size_t)(ndim + 2) * fbytes;
+  p->workspace_bytes = (size_t)(ndim + 3) * fbytes;
   if (err) {
     cudaGetLastError();
     cfd_plan_destroy(p);
@@ -290,10 +313,13 @@ void cfd_plan_destroy(cfd_plan* p) {
   for (int j = 0; j < CFD_MAX_DIM; ++j) {
     cudaFree(p->lam[j]);
     cudaFree(p->us[j]);
+    cudaFree(p->us2[j]);
     cudaFree(p->dev_a[j]);
     cudaFree(p->dev_b[j]);
   }
   cudaFree(p->rhs);
+  cudaFree(p->qbuf);
+  cudaFree(p->qbuf2);
   cudaFree(p->T);
   cudaFree(p->dev_q);
   cudaFree(p->diag_dev);
@@ -316,23 +342,69 @@ int cfd_step(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* co
   StepConsts c;
   if (int e = make_consts(p, params, &c)) return e;
   const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
+  float* q = q_out ? q_out : p->qbuf;
   prof_mark(p, st, "begin");
-  if (int e = launch_explicit_2d(st, v_in[0], v_in[1], p->us[0], p->us[1], p->rhs, p->batch, Nx, Ny, c, 0))
+  if (int e = launch_explicit_2d(st, v_in[0], v_in[1], nullptr, p->us[0], p->us[1], p->rhs,
+                                 p->batch, Nx, Ny, c, 0))
     return e;
   prof_mark(p, st, "explicit_2d");
-  return poisson_2d(p, st, p->us[0], p->us[1], v_out[0], v_out[1], q_out);
+  if (int e = solve_2d(p, st, q)) return e;
+  return correct_2d(p, st, p->us[0], p->us[1], q, v_out[0], v_out[1]);
+}
+
+// nsteps chained steps: the projected state is materialised only at the end; in between, step
+// n+1 reads (u*, v*, q) of step n and projects while loading (LAZY explicit kernel).
+static int repeated_lazy(cfd_plan* p, cudaStream_t st, const float* const* v_in, float* const* v_out,
+                         int nsteps, const cfd_params* params) {
+  StepConsts c;
+  if (int e = make_consts(p, params, &c)) return e;
+  if (int e = ensure_lazy_buffers(p)) return e;
+  const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
+  float* us_cur[2] = {p->us[0], p->us[1]};
+  float* us_nxt[2] = {p->us2[0], p->us2[1]};
+  float* q_cur = p->qbuf;
+  float* q_nxt = p->qbuf2;
+  for (int n = 0; n < nsteps; ++n) {
+    prof_mark(p, st, "begin");
+    if (n == 0) {
+      if (int e = launch_explicit_2d(st, v_in[0], v_in[1], nullptr, us_cur[0], us_cur[1], p->rhs,
+                                     p->batch, Nx, Ny, c, 0))
+        return e;
+      prof_mark(p, st, "explicit_2d");
+      if (int e = solve_2d(p, st, q_cur)) return e;
+    } else {
+      if (int e = launch_explicit_2d(st, us_cur[0], us_cur[1], q_cur, us_nxt[0], us_nxt[1], p->rhs,
+                                     p->batch, Nx, Ny, c, 0))
+        return e;
+      prof_mark(p, st, "explicit_2d_lazy");
+      if (int e = solve_2d(p, st, q_nxt)) return e;
+      for (int a = 0; a < 2; ++a) {
+        float* t = us_cur[a];
+        us_cur[a] = us_nxt[a];
+        us_nxt[a] = t;
+      }
+      float* t = q_cur;
+      q_cur = q_nxt;
+      q_nxt = t;
+    }
+  }
+  return correct_2d(p, st, us_cur[0], us_cur[1], q_cur, v_out[0], v_out[1]);
 }
 
 int cfd_repeated(cfd_plan* p, cfd_stream stream, float* const* v_a, float* const* v_b, int nsteps,
                  const cfd_params* params, int* result_in_b) {
+  if (int e = check_plan(p)) return e;
+  if (!v_a || !v_b || !params) return set_error_msg("null argument");
   if (nsteps < 0) return set_error_msg("nsteps must be >= 0");
-  for (int n = 0; n < nsteps; ++n) {
-    float* const* src = (n & 1) ? v_b : v_a;
-    float* const* dst = (n & 1) ? v_a : v_b;
-    if (int e = cfd_step(p, stream, src, dst, nullptr, params)) return e;
-  }
+  for (int a = 0; a < p->ndim; ++a)
+    if (!v_a[a] || !v_b[a] || v_a[a] == v_b[a]) return set_error_msg("cfd_repeated: bad buffers");
+  // same convention as stepping one by one: the result lands in v_b iff nsteps is odd
   if (result_in_b) *result_in_b = nsteps & 1;
-  return 0;
+  if (nsteps == 0) return 0;
+  float* const* dst = (nsteps & 1) ? v_b : v_a;
+  if (nsteps == 1) return cfd_step(p, stream, v_a, dst, nullptr, params);
+  // the chain reads v_a only in its first kernel, so writing the result back into v_a is safe
+  return repeated_lazy(p, (cudaStream_t)stream, v_a, dst, nsteps, params);
 }
 
 int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
@@ -343,8 +415,8 @@ int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
   if (int e = make_consts(p, params, &c)) return e;
   for (int a = 0; a < p->ndim; ++a)
     if (v_in[a] == dvdt_out[a]) return set_error_msg("cfd_explicit_terms: output must not alias input");
-  return launch_explicit_2d((cudaStream_t)stream, v_in[0], v_in[1], dvdt_out[0], dvdt_out[1],
-                            nullptr, p->batch, (int)p->shape[0], (int)p->shape[1], c, 1);
+  return launch_explicit_2d((cudaStream_t)stream, v_in[0], v_in[1], nullptr, dvdt_out[0],
+                            dvdt_out[1], nullptr, p->batch, (int)p->shape[0], (int)p->shape[1], c, 1);
 }
 
 int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
@@ -356,7 +428,9 @@ int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float*
   if (int e = launch_divergence_2d(st, v_in[0], v_in[1], p->rhs, p->batch, Nx, Ny,
                                    (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1])))
     return e;
-  return poisson_2d(p, st, v_in[0], v_in[1], v_out[0], v_out[1], q_out);
+  float* q = q_out ? q_out : p->qbuf;
+  if (int e = solve_2d(p, st, q)) return e;
+  return correct_2d(p, st, v_in[0], v_in[1], q, v_out[0], v_out[1]);
 }
 
 int cfd_axpy(cfd_plan* p, cfd_stream stream, const float* const* x, int nterms,
@@ -411,12 +485,21 @@ int cfd_step_host(cfd_plan* p, const float* const* v_in_host, float* const* v_ou
     CFD_CUDA_OK(cudaMemcpyAsync(p->dev_a[a], v_in_host[a], bytes, cudaMemcpyHostToDevice, st));
   float** cur = p->dev_a;
   float** nxt = p->dev_b;
-  for (int n = 0; n < nsteps; ++n) {
-    float* q = (q_out_host && n == nsteps - 1) ? p->dev_q : nullptr;
-    if (int e = cfd_step(p, st, cur, nxt, q, params)) return e;
-    float** tmp = cur;
-    cur = nxt;
-    nxt = tmp;
+  {
+    const int chain = q_out_host ? nsteps - 1 : nsteps;  // the last step is separate when q is wanted
+    int in_b = 0;
+    if (int e = cfd_repeated(p, st, cur, nxt, chain, params, &in_b)) return e;
+    if (in_b) {
+      float** tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+    if (q_out_host) {
+      if (int e = cfd_step(p, st, cur, nxt, p->dev_q, params)) return e;
+      float** tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
   }
   for (int a = 0; a < p->ndim; ++a)
     CFD_CUDA_OK(cudaMemcpyAsync(v_out_host[a], cur[a], bytes, cudaMemcpyDeviceToHost, st));
@@ -428,36 +511,46 @@ int cfd_step_host(cfd_plan* p, const float* const* v_in_host, float* const* v_ou
 int cfd_step_profile(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
                      const cfd_params* params, int reps, int max_kernels, float* ms,
                      const char** names, int* n_kernels) {
+  // Times every kernel of a 3-step chain (first step, lazy steps, final materialisation) with
+  // CUDA events on the launching stream; reports the mean per launch, aggregated by kernel name
+  // in first-seen order.
   if (int e = check_plan(p)) return e;
   if (reps < 1) reps = 1;
   cudaStream_t st = (cudaStream_t)stream;
-  std::vector<double> acc;
-  std::vector<const char*> nm;
+  std::vector<const char*> uniq;
+  std::vector<double> tot;
+  std::vector<int> cnt;
   for (int r = 0; r < reps; ++r) {
     for (auto ev : p->prof_events) cudaEventDestroy(ev);
     p->prof_events.clear();
     p->prof_names.clear();
     p->profiling = true;
-    int e = cfd_step(p, stream, v_in, v_out, nullptr, params);
+    int e = repeated_lazy(p, st, v_in, v_out, 3, params);
     p->profiling = false;
     if (e) return e;
     CFD_CUDA_OK(cudaStreamSynchronize(st));
-    const size_t n = p->prof_events.size();
-    if (acc.empty()) {
-      acc.assign(n > 0 ? n - 1 : 0, 0.0);
-      nm.assign(p->prof_names.begin() + (n > 0 ? 1 : 0), p->prof_names.end());
-    }
-    for (size_t i = 1; i < n; ++i) {
+    for (size_t i = 1; i < p->prof_events.size(); ++i) {
+      const char* nm = p->prof_names[i];
+      if (strcmp(nm, "begin") == 0) continue;
       float t = 0.f;
       CFD_CUDA_OK(cudaEventElapsedTime(&t, p->prof_events[i - 1], p->prof_events[i]));
-      acc[i - 1] += t;
+      size_t k = 0;
+      for (; k < uniq.size(); ++k)
+        if (strcmp(uniq[k], nm) == 0) break;
+      if (k == uniq.size()) {
+        uniq.push_back(nm);
+        tot.push_back(0.0);
+        cnt.push_back(0);
+      }
+      tot[k] += t;
+      cnt[k] += 1;
     }
   }
-  const int n = (int)acc.size();
-  if (n_kernels) *n_kernels = n;
+  const int n = (int)uniq.size();
+  if (n_kernels) *n_kernels = n < max_kernels ? n : max_kernels;
   for (int i = 0; i < n && i < max_kernels; ++i) {
-    ms[i] = (float)(acc[i] / reps);
-    names[i] = nm[i];
+    ms[i] = (float)(tot[i] / cnt[i]);
+    names[i] = uniq[i];
   }
   return 0;
 }

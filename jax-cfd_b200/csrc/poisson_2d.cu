@@ -243,6 +243,86 @@ irfft_rows_correct_kernel(const float2* __restrict__ T, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Q: gather ROWS rows of T, inverse real FFT, write q rows (coalesced).  No halo row, no
+// redundant transform; the pressure-gradient correction is applied either by correct2d_kernel or
+// lazily by the next step's explicit kernel (explicit_2d.cu, LAZY mode).
+template <int LM, int ROWS>
+__global__ void __launch_bounds__(ROWS * FftPlan<LM>::G)
+irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
+                  const float2* __restrict__ tw, const float2* __restrict__ rtw) {
+  using P = FftPlan<LM>;
+  constexpr int M = P::M, G = P::G, E = P::E;
+  constexpr int RS = row_stride(M, ROWS);
+  constexpr int NT = ROWS * G;
+  extern __shared__ float2 smem[];
+  const int tid = threadIdx.x;
+  const int row = tid / G, t = tid % G;
+  const int x0 = blockIdx.x * ROWS;
+  const size_t b = blockIdx.y;
+  float2* s = smem + row * RS;
+  {
+    const float2* Tb = T + b * (size_t)M * Nx + x0;
+#pragma unroll 4
+    for (int idx = tid; idx < ROWS * M; idx += NT) {
+      const int r = idx % ROWS, ky = idx / ROWS;
+      smem[r * RS + PAD(ky)] = __ldg(Tb + (size_t)ky * Nx + r);
+    }
+  }
+  __syncthreads();
+  for (int k = t; k <= M / 2; k += G) {
+    if (k == 0) {
+      const float2 x = s[0];
+      s[0] = make_float2(x.x + x.y, x.x - x.y);
+    } else if (k == M / 2) {
+      const float2 x = s[PAD(k)];
+      s[PAD(k)] = make_float2(2.f * x.x, -2.f * x.y);
+    } else {
+      const float2 xk = s[PAD(k)], xm = s[PAD(M - k)];
+      const float2 A = make_float2(xk.x + xm.x, xk.y - xm.y);
+      const float2 B = make_float2(xk.x - xm.x, xk.y + xm.y);
+      const float2 WB = cmulc(B, __ldg(rtw + k));
+      s[PAD(k)] = make_float2(A.x + WB.x, A.y + WB.y);
+      s[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
+    }
+  }
+  __syncthreads();
+  float2 v[E];
+  fft_load_regs<LM>(v, t, s);
+  FftRun<LM, +1>::run(v, t, s, tw);
+  // v[e] = (q[2m], q[2m+1]) with m = t + G*e: a warp writes 32 consecutive float2 = 256 B
+  float2* dst = reinterpret_cast<float2*>(q + (b * Nx + x0 + row) * (size_t)(2 * M));
+#pragma unroll
+  for (int e = 0; e < E; ++e) dst[t + G * e] = v[e];
+}
+
+// v' = u* - forward_difference(q)   (pressure.py:194-196), 4 columns per thread
+__global__ void correct2d_kernel(const float* __restrict__ us, const float* __restrict__ vs,
+                                 const float* __restrict__ q, float* __restrict__ uo,
+                                 float* __restrict__ vo, int Nx, int Ny, float inv_hx,
+                                 float inv_hy) {
+  const size_t b = blockIdx.z;
+  const int x = blockIdx.y;
+  const int j = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (j >= Ny) return;
+  const int xp = x == Nx - 1 ? 0 : x + 1;
+  const size_t row = (b * Nx + x) * (size_t)Ny, rowp = (b * Nx + xp) * (size_t)Ny;
+  const float4 q0 = ldg4(q + row + j), q1 = ldg4(q + rowp + j);
+  const float qr = __ldg(q + row + (j + 4 == Ny ? 0 : j + 4));
+  const float4 u4 = ldg4(us + row + j), v4 = ldg4(vs + row + j);
+  float4 ou, ov;
+  ou.x = u4.x - (q1.x - q0.x) * inv_hx;
+  ou.y = u4.y - (q1.y - q0.y) * inv_hx;
+  ou.z = u4.z - (q1.z - q0.z) * inv_hx;
+  ou.w = u4.w - (q1.w - q0.w) * inv_hx;
+  ov.x = v4.x - (q0.y - q0.x) * inv_hy;
+  ov.y = v4.y - (q0.z - q0.y) * inv_hy;
+  ov.z = v4.z - (q0.w - q0.z) * inv_hy;
+  ov.w = v4.w - (qr - q0.w) * inv_hy;
+  stg4(uo + row + j, ou);
+  stg4(vo + row + j, ov);
+}
+
 // rhs = divergence(v)   (finite_differences.py:136-143) -- used by cfd_project only
 __global__ void divergence2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
                                     float* __restrict__ rhs, int Nx, int Ny, float inv_hx,
@@ -347,6 +427,28 @@ int launch_irfft_correct_t(cudaStream_t st, const float2* T, const float* us, co
   }
 }
 
+template <int LM>
+int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, int Nx,
+                        const float2* tw, const float2* rtw) {
+  constexpr int ROWS_MAX = rows_for(LM);
+  using P = FftPlan<LM>;
+  auto go = [&](auto rows_c) -> int {
+    constexpr int ROWS = decltype(rows_c)::value;
+    constexpr size_t smem = (size_t)ROWS * row_stride(P::M, ROWS) * sizeof(float2);
+    auto k = irfft_rows_kernel<LM, ROWS>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(T, q, Nx, tw, rtw);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  if (Nx >= ROWS_MAX) return go(std::integral_constant<int, ROWS_MAX>{});
+  if constexpr (ROWS_MAX > 16) {
+    if (Nx >= 16) return go(std::integral_constant<int, 16>{});
+  }
+  return set_error_msg("grid axis 0 too small for the row FFT kernel (need >= 16)");
+}
+
 }  // namespace
 
 #define CFD_DISPATCH_LM(lm, LO, HI, CALL)                       \
@@ -396,4 +498,21 @@ int launch_divergence_2d(cudaStream_t st, const float* u, const float* v, float*
   return 0;
 }
 
+}  // namespace cfd
+
+namespace cfd {
+int launch_irfft_rows(cudaStream_t st, int lm_row, const float2* T, float* q, int batch, int Nx,
+                      const float2* tw, const float2* rtw) {
+  CFD_DISPATCH_LM(lm_row, 4, 14, return launch_irfft_rows_t<LM_>(st, T, q, batch, Nx, tw, rtw));
+  return 0;
+}
+int launch_correct_2d(cudaStream_t st, const float* us, const float* vs, const float* q, float* uo,
+                      float* vo, int batch, int Nx, int Ny, float inv_hx, float inv_hy) {
+  const int threads = 128;
+  dim3 grid((Ny / 4 + threads - 1) / threads, Nx, batch);
+  correct2d_kernel<<<grid, threads, 0, st>>>(us, vs, q, uo, vo, Nx, Ny, inv_hx, inv_hy);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 }  // namespace cfd

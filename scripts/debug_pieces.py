@@ -45,3 +45,9 @@ for shape in shapes:
   print(shape, 'explicit', ['%.1e' % e for e in e_exp], 'adv-only', ['%.1e' % e for e in e_adv],
         'q', '%.1e' % e_q, 'proj', ['%.1e' % e for e in e_p], 'step', ['%.1e' % e for e in e_s],
         'q1 %.1e' % gu.rel_l2(np.asarray(q1), wq1), flush=True)
+  # chained steps (lazy projection) vs oracle
+  vn = cfd.funcutils.repeated(step, 4)(wrap(grid, v0))
+  wn = v0
+  for _ in range(4):
+    wn = cfd_oracle.step(wn, dt, h, 1.0, nu, of)
+  print('   chain4', ['%.1e' % gu.rel_l2(np.asarray(a.data), b) for a, b in zip(vn, wn)], flush=True)
