@@ -24,7 +24,8 @@ int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const floa
 int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
                      const float2* tw, const float2* rtw);
 int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
-                  const double* lamx, const double* lamy, double cutoff, float norm);
+                  const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
+                  int fastd, double cutoff, float norm);
 int launch_irfft_correct(cudaStream_t, int lm_row, const float2* T, const float* us,
                          const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
                          const float2* tw, const float2* rtw, float inv_hx, float inv_hy);
@@ -94,6 +95,8 @@ struct cfd_plan {
   float2* tw_x = nullptr;
   float2* rtw = nullptr;
   double* lam[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* lamf[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // float32 copies for the fast path
+  int fastd = 0;  // 1: only the mean mode is below the pseudo-inverse cutoff
   double cutoff = 0;
   float norm = 0;
   // workspace
@@ -190,7 +193,7 @@ int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
   if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw)) return e;
   prof_mark(p, st, "rfft_rows");
   if (int e = launch_xlines(st, p->lm_x, p->T, p->batch, Ny / 2, p->tw_x, p->lam[0], p->lam[1],
-                            p->cutoff, p->norm))
+                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm))
     return e;
   prof_mark(p, st, "xlines");
   if (int e = launch_irfft_rows(st, p->lm_row, p->T, q, p->batch, Nx, p->tw_row, p->rtw)) return e;
@@ -283,8 +286,21 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
       lam[k] = (2.0 * cos(2.0 * M_PI * (double)k / (double)n) - 2.0) / (step[j] * step[j]);
     lam[0] = 0.0;
     err |= upload(&p->lam[j], lam);
+    std::vector<float> lamf(lam.begin(), lam.end());
+    err |= upload(&p->lamf[j], lamf);
   }
   p->cutoff = 10.0 * 1.1920928955078125e-07;  // 10 * finfo(float32).eps, fast_diagonalization.py:257-258
+  {
+    // Every eigenvalue sum except the mean mode has |L| >= min_j |lam_j[1]| (all lam <= 0).  If
+    // that exceeds the cutoff with a safety margin, only L(0,...,0) = 0 is discarded and the
+    // kernels may form the sum in float32 without testing it.
+    double minabs = 1e300;
+    for (int j = 0; j < ndim; ++j) {
+      const double l1 = fabs((2.0 * cos(2.0 * M_PI / (double)shape[j]) - 2.0) / (step[j] * step[j]));
+      if (l1 < minabs) minabs = l1;
+    }
+    p->fastd = (minabs > 4.0 * p->cutoff) ? 1 : 0;
+  }
   p->norm = (float)(1.0 / (2.0 * (double)p->cells));
   const size_t fbytes = (size_t)batch * p->cells * sizeof(float);
   for (int a = 0; a < ndim && !err; ++a) {
@@ -312,6 +328,7 @@ void cfd_plan_destroy(cfd_plan* p) {
   cudaFree(p->rtw);
   for (int j = 0; j < CFD_MAX_DIM; ++j) {
     cudaFree(p->lam[j]);
+    cudaFree(p->lamf[j]);
     cudaFree(p->us[j]);
     cudaFree(p->us2[j]);
     cudaFree(p->dev_a[j]);

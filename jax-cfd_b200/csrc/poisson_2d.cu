@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "fft_smem.cuh"
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace cfd {
@@ -87,10 +89,11 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
 
 // ------------------------------------------------------------------------------------------
 // X: lines T[line][0..Nx)  (line = b * My + ky), forward FFT * D * inverse FFT, in place.
-template <int LM, int LINES>
+template <int LM, int LINES, bool FASTD>
 __global__ void __launch_bounds__(LINES * FftPlan<LM>::G)
 xlines_kernel(float2* __restrict__ T, int My, const float2* __restrict__ tw,
-              const double* __restrict__ lamx, const double* __restrict__ lamy, double cutoff,
+              const double* __restrict__ lamx, const double* __restrict__ lamy,
+              const float* __restrict__ lamxf, const float* __restrict__ lamyf, double cutoff,
               float norm) {
   using P = FftPlan<LM>;
   constexpr int M = P::M, G = P::G, E = P::E;
@@ -111,13 +114,25 @@ xlines_kernel(float2* __restrict__ T, int My, const float2* __restrict__ tw,
 
   const bool cta_has_packed = (line0 % My) == 0;  // only the first line of a CTA can be ky = 0
   if (!cta_has_packed || ky != 0) {
-    const double ly = __ldg(lamy + ky);
+    if (FASTD) {
+      // only the mean mode is below the cutoff (checked on the host in f64): float eigenvalues,
+      // |lam| >= min nonzero |lam_x|, |lam_y| > cutoff, so no per-element test is needed here
+      const float ly = __ldg(lamyf + ky);
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const double lam = __ldg(lamx + t + G * e) + ly;
-      const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
-      v[e].x *= d;
-      v[e].y *= d;
+      for (int e = 0; e < E; ++e) {
+        const float d = norm * fast_rcp(__ldg(lamxf + t + G * e) + ly);
+        v[e].x *= d;
+        v[e].y *= d;
+      }
+    } else {
+      const double ly = __ldg(lamy + ky);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const double lam = __ldg(lamx + t + G * e) + ly;
+        const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
+        v[e].x *= d;
+        v[e].y *= d;
+      }
     }
   }
   if (cta_has_packed) {
@@ -366,6 +381,14 @@ constexpr int lines_for(int LM) {
   return lines;
 }
 
+static int rows_shift() {  // tuning knob: CFD_FFT_ROWS_SHIFT=k uses rows_for(LM) >> k rows per CTA
+  static const int v = [] {
+    const char* e = getenv("CFD_FFT_ROWS_SHIFT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 template <int LM>
 int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, int Nx,
                        const float2* tw, const float2* rtw) {
@@ -382,6 +405,12 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
     CFD_CUDA_OK(cudaGetLastError());
     return 0;
   };
+  if constexpr (ROWS_MAX >= 2) {
+    if (rows_shift() == 1) return go(std::integral_constant<int, ROWS_MAX / 2>{});
+  }
+  if constexpr (ROWS_MAX >= 4) {
+    if (rows_shift() == 2) return go(std::integral_constant<int, ROWS_MAX / 4>{});
+  }
   if (Nx >= ROWS_MAX) return go(std::integral_constant<int, ROWS_MAX>{});
   if constexpr (ROWS_MAX > 16) {
     if (Nx >= 16) return go(std::integral_constant<int, 16>{});
@@ -391,15 +420,24 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
 
 template <int LM>
 int launch_xlines_t(cudaStream_t st, float2* T, int batch, int My, const float2* tw,
-                    const double* lamx, const double* lamy, double cutoff, float norm) {
+                    const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
+                    int fastd, double cutoff, float norm) {
   constexpr int LINES = lines_for(LM);
   using P = FftPlan<LM>;
   constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
-  auto k = xlines_kernel<LM, LINES>;
-  if (int e = set_smem(k, smem)) return e;
   const size_t nlines = (size_t)batch * My;
   if (nlines % LINES) return set_error_msg("internal: line count not divisible");
-  k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, My, tw, lamx, lamy, cutoff, norm);
+  if (fastd) {
+    auto k = xlines_kernel<LM, LINES, true>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, My, tw, lamx, lamy, lamxf, lamyf,
+                                                            cutoff, norm);
+  } else {
+    auto k = xlines_kernel<LM, LINES, false>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, My, tw, lamx, lamy, lamxf, lamyf,
+                                                            cutoff, norm);
+  }
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;
@@ -442,6 +480,12 @@ int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, i
     CFD_CUDA_OK(cudaGetLastError());
     return 0;
   };
+  if constexpr (ROWS_MAX >= 2) {
+    if (rows_shift() == 1) return go(std::integral_constant<int, ROWS_MAX / 2>{});
+  }
+  if constexpr (ROWS_MAX >= 4) {
+    if (rows_shift() == 2) return go(std::integral_constant<int, ROWS_MAX / 4>{});
+  }
   if (Nx >= ROWS_MAX) return go(std::integral_constant<int, ROWS_MAX>{});
   if constexpr (ROWS_MAX > 16) {
     if (Nx >= 16) return go(std::integral_constant<int, 16>{});
@@ -475,9 +519,11 @@ int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, i
 }
 // lm_x = log2(Nx)
 int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const float2* tw,
-                  const double* lamx, const double* lamy, double cutoff, float norm) {
+                  const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
+                  int fastd, double cutoff, float norm) {
   CFD_DISPATCH_LM(lm_x, 4, 14,
-                  return launch_xlines_t<LM_>(st, T, batch, My, tw, lamx, lamy, cutoff, norm));
+                  return launch_xlines_t<LM_>(st, T, batch, My, tw, lamx, lamy, lamxf, lamyf, fastd,
+                                              cutoff, norm));
   return 0;
 }
 int launch_irfft_correct(cudaStream_t st, int lm_row, const float2* T, const float* us,
