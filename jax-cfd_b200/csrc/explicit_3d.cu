@@ -1,0 +1,323 @@
+// Sweep "E" (3-D): explicit terms + Euler update + divergence, and the Smagorinsky eddy viscosity.
+//
+// First 3-D implementation: one thread per cell (z fastest, coalesced), neighbours through L1/L2
+// (no register marching yet -- the 2-D kernel's design is the model for the next round).  Same
+// arithmetic as explicit_2d.cu per face (common.cuh: face_flux).
+//
+//   advection      advection.py:387-395 -> 81-116 -> 34-78, interpolation.py:36-303
+//   diffusion      diffusion.py:35-37, finite_differences.py:127-133
+//   forcing        forcings.py:35-129 (separable / field / linear), equations.py:108-109
+//   Smagorinsky    subgrid_models.py:40-98 (viscosity at cell centres: smag_nut3d_kernel),
+//                  subgrid_models.py:101-134 (evm_model: -div(tau), tau_ij = -2 nu_ij s_ij)
+//   update         time_stepping.py:101;   divergence   finite_differences.py:136-143
+#include "common.cuh"
+
+namespace cfd {
+
+namespace {
+
+struct Idx3 {
+  int ox[5], oy[5], oz[5];  // linear offsets of i-2..i+2 (wrapped) along each axis
+};
+
+__device__ __forceinline__ Idx3 make_idx(int i, int j, int k, int N0, int N1, int N2) {
+  Idx3 r;
+#pragma unroll
+  for (int d = -2; d <= 2; ++d) {
+    r.ox[d + 2] = wrap_idx(i + d, N0) * N1 * N2;
+    r.oy[d + 2] = wrap_idx(j + d, N1) * N2;
+    r.oz[d + 2] = wrap_idx(k + d, N2);
+  }
+  return r;
+}
+
+// value of f at the cell shifted by (d0, d1, d2)
+__device__ __forceinline__ float at(const float* __restrict__ f, const Idx3& ix, int d0, int d1, int d2) {
+  return __ldg(f + ix.ox[d0 + 2] + ix.oy[d1 + 2] + ix.oz[d2 + 2]);
+}
+// shift sA along axis A plus sB along axis B (A may equal B)
+template <int A, int B>
+__device__ __forceinline__ float at2(const float* __restrict__ f, const Idx3& ix, int sA, int sB) {
+  int d[3] = {0, 0, 0};
+  d[A] += sA;
+  d[B] += sB;
+  return at(f, ix, d[0], d[1], d[2]);
+}
+
+// (F_J(cell) - F_J(cell - e_J)) / h_J for component A advected along J   (advection.py:73-78)
+template <int A, int J>
+__device__ __forceinline__ float conv_dir(const float* __restrict__ c, const float* __restrict__ vj,
+                                          const Idx3& ix, float dth, float inv_h) {
+  const float Up = 0.5f * (at2<J, A>(vj, ix, 0, 0) + at2<J, A>(vj, ix, 0, 1));
+  const float Fp = face_flux(at2<J, J>(c, ix, -1, 0), at2<J, J>(c, ix, 0, 0), at2<J, J>(c, ix, 1, 0),
+                             at2<J, J>(c, ix, 2, 0), Up, dth);
+  const float Um = 0.5f * (at2<J, A>(vj, ix, -1, 0) + at2<J, A>(vj, ix, -1, 1));
+  const float Fm = face_flux(at2<J, J>(c, ix, -2, 0), at2<J, J>(c, ix, -1, 0), at2<J, J>(c, ix, 0, 0),
+                             at2<J, J>(c, ix, 1, 0), Um, dth);
+  return (Fp - Fm) * inv_h;
+}
+
+struct Vel3 {
+  const float* f[3];
+};
+
+// forward difference of component C along axis AX at the cell shifted by (p0,p1,p2)
+template <int AX>
+__device__ __forceinline__ float fwd(const float* __restrict__ f, const Idx3& ix, int p0, int p1,
+                                     int p2, float inv_h) {
+  int d[3] = {p0, p1, p2};
+  const float a = at(f, ix, d[0], d[1], d[2]);
+  d[AX] += 1;
+  return (at(f, ix, d[0], d[1], d[2]) - a) * inv_h;
+}
+// strain rate s_IJ at the cell shifted by p   (subgrid_models.py:124-128)
+template <int I, int J>
+__device__ __forceinline__ float strain(const Vel3& v, const Idx3& ix, int p0, int p1, int p2,
+                                        const float* inv_h) {
+  return 0.5f * (fwd<J>(v.f[I], ix, p0, p1, p2, inv_h[J]) + fwd<I>(v.f[J], ix, p0, p1, p2, inv_h[I]));
+}
+// s_IJ interpolated to the cell centre (subgrid_models.py:88-89 via interpolation.linear)
+template <int I, int J>
+__device__ __forceinline__ float strain_center(const Vel3& v, const Idx3& ix, const float* inv_h) {
+  if (I == J) {
+    int d[3] = {0, 0, 0};
+    d[I] = -1;
+    return strain<I, I>(v, ix, d[0], d[1], d[2], inv_h);
+  }
+  constexpr int A = I < J ? I : J, B = I < J ? J : I;  // ascending axis order
+  float r[2];
+#pragma unroll
+  for (int sb = 0; sb < 2; ++sb) {  // sb = 0: shifted -1 along B, 1: unshifted
+    int d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+    d0[B] = d1[B] = sb - 1;
+    d0[A] = -1;
+    const float lo = strain<I, J>(v, ix, d0[0], d0[1], d0[2], inv_h);
+    const float hi = strain<I, J>(v, ix, d1[0], d1[1], d1[2], inv_h);
+    r[sb] = 0.5f * lo + 0.5f * hi;
+  }
+  return 0.5f * r[0] + 0.5f * r[1];
+}
+
+// nu_t at cell centres   (subgrid_models.py:91-93)
+__global__ void smag_nut3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                  const float* __restrict__ w, float* __restrict__ nut, int N0,
+                                  int N1, int N2, StepConsts c) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cells) return;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const int k = (int)(gid % N2), j = (int)((gid / N2) % N1), i = (int)(gid / ((size_t)N1 * N2));
+  const Idx3 ix = make_idx(i, j, k, N0, N1, N2);
+  Vel3 vel = {{u + boff, v + boff, w + boff}};
+  const float s00 = strain_center<0, 0>(vel, ix, c.inv_h), s11 = strain_center<1, 1>(vel, ix, c.inv_h),
+              s22 = strain_center<2, 2>(vel, ix, c.inv_h);
+  const float s01 = strain_center<0, 1>(vel, ix, c.inv_h), s02 = strain_center<0, 2>(vel, ix, c.inv_h),
+              s12 = strain_center<1, 2>(vel, ix, c.inv_h);
+  // trace(S.S) row by row like np.trace(S.dot(S)); s_ji == s_ij bitwise
+  const float r0 = s00 * s00 + s01 * s01 + s02 * s02;
+  const float r1 = s01 * s01 + s11 * s11 + s12 * s12;
+  const float r2 = s02 * s02 + s12 * s12 + s22 * s22;
+  const float tr = (r0 + r1) + r2;
+  nut[boff + gid] = c.smag_coef * sqrtf(2.f * tr);
+}
+
+// nu interpolated from centres to the offset of s_IJ, at the cell shifted by p  (subgrid_models.py:94-97)
+template <int I, int J>
+__device__ __forceinline__ float nu_at(const float* __restrict__ nut, const Idx3& ix, int p0, int p1,
+                                       int p2) {
+  if (I == J) {
+    int d[3] = {p0, p1, p2};
+    d[I] += 1;
+    return at(nut, ix, d[0], d[1], d[2]);
+  }
+  constexpr int A = I < J ? I : J, B = I < J ? J : I;
+  float r[2];
+#pragma unroll
+  for (int sb = 0; sb < 2; ++sb) {
+    int d0[3] = {p0, p1, p2}, d1[3] = {p0, p1, p2};
+    d0[B] += sb;
+    d1[B] += sb;
+    d1[A] += 1;
+    r[sb] = 0.5f * at(nut, ix, d0[0], d0[1], d0[2]) + 0.5f * at(nut, ix, d1[0], d1[1], d1[2]);
+  }
+  return 0.5f * r[0] + 0.5f * r[1];
+}
+// tau_IJ = -2 nu_IJ s_IJ at the cell shifted by p
+template <int I, int J>
+__device__ __forceinline__ float tau(const Vel3& v, const float* __restrict__ nut, const Idx3& ix,
+                                     int p0, int p1, int p2, const float* inv_h) {
+  return -2.f * nu_at<I, J>(nut, ix, p0, p1, p2) * strain<I, J>(v, ix, p0, p1, p2, inv_h);
+}
+// -(divergence of row I of tau)   (subgrid_models.py:131-134)
+template <int I>
+__device__ __forceinline__ float smag_acc(const Vel3& v, const float* __restrict__ nut, const Idx3& ix,
+                                          const float* inv_h) {
+  float d = (tau<I, 0>(v, nut, ix, 0, 0, 0, inv_h) - tau<I, 0>(v, nut, ix, -1, 0, 0, inv_h)) * inv_h[0];
+  d += (tau<I, 1>(v, nut, ix, 0, 0, 0, inv_h) - tau<I, 1>(v, nut, ix, 0, -1, 0, inv_h)) * inv_h[1];
+  d += (tau<I, 2>(v, nut, ix, 0, 0, 0, inv_h) - tau<I, 2>(v, nut, ix, 0, 0, -1, inv_h)) * inv_h[2];
+  return -d;
+}
+
+template <int A>
+__device__ __forceinline__ float explicit_comp(const Vel3& vel, const float* __restrict__ nut,
+                                               const Idx3& ix, const StepConsts& c, int i, int j,
+                                               int k, size_t cell) {
+  const float* cc = vel.f[A];
+  const float c0 = at(cc, ix, 0, 0, 0);
+  float conv = conv_dir<A, 0>(cc, vel.f[0], ix, c.dth[0], c.inv_h[0]);
+  conv += conv_dir<A, 1>(cc, vel.f[1], ix, c.dth[1], c.inv_h[1]);
+  conv += conv_dir<A, 2>(cc, vel.f[2], ix, c.dth[2], c.inv_h[2]);
+  float dv = -conv;
+  if (c.has_nu) {
+    float l = (-2.f * c0) * c.lap_sum;
+    l += (at(cc, ix, -1, 0, 0) + at(cc, ix, 1, 0, 0)) * c.lap_s[0];
+    l += (at(cc, ix, 0, -1, 0) + at(cc, ix, 0, 1, 0)) * c.lap_s[1];
+    l += (at(cc, ix, 0, 0, -1) + at(cc, ix, 0, 0, 1)) * c.lap_s[2];
+    dv += c.nu * l;
+  }
+  if (c.n_terms > 0) {
+    float f = 0.f;
+    for (int t = 0; t < c.n_terms; ++t) {
+      const int kind = c.term_kind[t];
+      if (kind == CFD_FORCE_SEPARABLE) {
+        if (c.has_sep[A]) {
+          float p = 1.f;
+          if (c.sep_prof[A][0]) p = __ldg(c.sep_prof[A][0] + i);
+          if (c.sep_prof[A][1]) p = p * __ldg(c.sep_prof[A][1] + j);
+          if (c.sep_prof[A][2]) p = p * __ldg(c.sep_prof[A][2] + k);
+          f += p * c.sep_scale[A];
+        }
+      } else if (kind == CFD_FORCE_FIELD) {
+        if (c.field[A]) f += __ldg(c.field[A] + cell);
+      } else if (kind == CFD_FORCE_LINEAR) {
+        f += c.linear_coef * c0;
+      } else if (kind == CFD_FORCE_SMAGORINSKY) {
+        f += smag_acc<A>(vel, nut, ix, c.inv_h);
+      }
+    }
+    dv = fmaf(f, c.inv_rho, dv);
+  }
+  return dv;
+}
+
+// one thread per cell; writes u* (or dv/dt)
+__global__ void __launch_bounds__(128)
+explicit3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                  const float* __restrict__ w, const float* __restrict__ nut,
+                  float* __restrict__ us, float* __restrict__ vs, float* __restrict__ ws, int N0,
+                  int N1, int N2, StepConsts c, int dvdt_mode) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cells) return;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const int k = (int)(gid % N2), j = (int)((gid / N2) % N1), i = (int)(gid / ((size_t)N1 * N2));
+  const Idx3 ix = make_idx(i, j, k, N0, N1, N2);
+  Vel3 vel = {{u + boff, v + boff, w + boff}};
+  const float* nu_b = nut ? nut + boff : nullptr;
+  const float d0 = explicit_comp<0>(vel, nu_b, ix, c, i, j, k, gid);
+  const float d1 = explicit_comp<1>(vel, nu_b, ix, c, i, j, k, gid);
+  const float d2 = explicit_comp<2>(vel, nu_b, ix, c, i, j, k, gid);
+  if (dvdt_mode) {
+    us[boff + gid] = d0;
+    vs[boff + gid] = d1;
+    ws[boff + gid] = d2;
+  } else {
+    us[boff + gid] = __ldg(vel.f[0] + gid) + c.dt * d0;
+    vs[boff + gid] = __ldg(vel.f[1] + gid) + c.dt * d1;
+    ws[boff + gid] = __ldg(vel.f[2] + gid) + c.dt * d2;
+  }
+}
+
+// diagnostics: sum 0.5|v|^2, sum 0.5|curl|^2, max|div|, max|v|^2
+__device__ __forceinline__ double warp_sum_d(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void atomic_max_d(double* addr, double val) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double(assumed) >= val) break;
+    old = atomicCAS(a, assumed, __double_as_longlong(val));
+  } while (assumed != old);
+}
+__global__ void diag3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                              const float* __restrict__ w, int N0, int N1, int N2, size_t total,
+                              float ihx, float ihy, float ihz, double* __restrict__ out4) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  double ke = 0.0, ens = 0.0;
+  float mdiv = 0.f, msp = 0.f;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = idx / cells, gid = idx % cells;
+    const int k = (int)(gid % N2), j = (int)((gid / N2) % N1), i = (int)(gid / ((size_t)N1 * N2));
+    const Idx3 ix = make_idx(i, j, k, N0, N1, N2);
+    const float* ub = u + b * cells;
+    const float* vb = v + b * cells;
+    const float* wb = w + b * cells;
+    const float u0 = at(ub, ix, 0, 0, 0), v0 = at(vb, ix, 0, 0, 0), w0 = at(wb, ix, 0, 0, 0);
+    const float div = (u0 - at(ub, ix, -1, 0, 0)) * ihx + (v0 - at(vb, ix, 0, -1, 0)) * ihy +
+                      (w0 - at(wb, ix, 0, 0, -1)) * ihz;
+    // curl by forward differences (finite_differences.curl_3d convention)
+    const float cx = (at(wb, ix, 0, 1, 0) - w0) * ihy - (at(vb, ix, 0, 0, 1) - v0) * ihz;
+    const float cy = (at(ub, ix, 0, 0, 1) - u0) * ihz - (at(wb, ix, 1, 0, 0) - w0) * ihx;
+    const float cz = (at(vb, ix, 1, 0, 0) - v0) * ihx - (at(ub, ix, 0, 1, 0) - u0) * ihy;
+    const float sp = u0 * u0 + v0 * v0 + w0 * w0;
+    ke += 0.5 * (double)sp;
+    ens += 0.5 * ((double)cx * cx + (double)cy * cy + (double)cz * cz);
+    mdiv = fmaxf(mdiv, fabsf(div));
+    msp = fmaxf(msp, sp);
+  }
+  ke = warp_sum_d(ke);
+  ens = warp_sum_d(ens);
+  mdiv = warp_max_f(mdiv);
+  msp = warp_max_f(msp);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out4 + 0, ke);
+    atomicAdd(out4 + 1, ens);
+    atomic_max_d(out4 + 2, (double)mdiv);
+    atomic_max_d(out4 + 3, (double)msp);
+  }
+}
+
+}  // namespace
+
+int launch_smag_nut_3d(cudaStream_t st, const float* u, const float* v, const float* w, float* nut,
+                       int batch, int N0, int N1, int N2, const StepConsts& c) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  dim3 grid((unsigned)((cells + 127) / 128), batch);
+  smag_nut3d_kernel<<<grid, 128, 0, st>>>(u, v, w, nut, N0, N1, N2, c);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const float* w,
+                       const float* nut, float* us, float* vs, float* ws, int batch, int N0, int N1,
+                       int N2, const StepConsts& c, int dvdt_mode) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  dim3 grid((unsigned)((cells + 127) / 128), batch);
+  explicit3d_kernel<<<grid, 128, 0, st>>>(u, v, w, nut, us, vs, ws, N0, N1, N2, c, dvdt_mode);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_diag_3d(cudaStream_t st, const float* u, const float* v, const float* w, int batch, int N0,
+                   int N1, int N2, float ihx, float ihy, float ihz, double* out4) {
+  CFD_CUDA_OK(cudaMemsetAsync(out4, 0, 4 * sizeof(double), st));
+  const size_t total = (size_t)batch * N0 * N1 * N2;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  diag3d_kernel<<<(int)blocks, 256, 0, st>>>(u, v, w, N0, N1, N2, total, ihx, ihy, ihz, out4);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cfd

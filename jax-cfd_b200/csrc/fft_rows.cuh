@@ -1,0 +1,68 @@
+// Helpers shared by the row / line FFT kernels (poisson_2d.cu, poisson_3d.cu).
+#pragma once
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "fft_smem.cuh"
+
+namespace cfd {
+namespace {
+
+__host__ __device__ constexpr int row_stride(int M, int rows) {
+  // padded line length rounded up to 16 float2, plus a skew so that the transposed access
+  // (lane -> row fastest) is bank-conflict free.
+  return ((padded_len(M) + 15) & ~15) + (rows >= 16 ? 1 : 16 / rows);
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem)", e, __FILE__, __LINE__);
+  }
+  return 0;
+}
+
+// rows per CTA for the row kernels: as many as fit ~100 KB / 1024 threads, at most 32
+constexpr int rows_for(int LM) {
+  const int M = 1 << LM, G = (M < 16 ? 1 : M / 16);
+  int rows = 32;
+  while (rows > 1 && (rows * G > 1024 || rows * (long)row_stride(M, 16) * 8 > 140 * 1024)) rows /= 2;
+  return rows;
+}
+constexpr int lines_for(int LM) {
+  const int M = 1 << LM, G = (M < 16 ? 1 : M / 16);
+  int lines = 16;
+  while (lines > 1 && (lines * G > 256)) lines /= 2;
+  return lines;
+}
+
+static int rows_shift() {  // tuning knob: CFD_FFT_ROWS_SHIFT=k uses rows_for(LM) >> k rows per CTA
+  static const int v = [] {
+    const char* e = getenv("CFD_FFT_ROWS_SHIFT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+}  // namespace
+}  // namespace cfd
+
+#define CFD_DISPATCH_LM(lm, LO, HI, CALL)                       \
+  switch (lm) {                                                 \
+    case 4: { constexpr int LM_ = 4; CALL; } break;             \
+    case 5: { constexpr int LM_ = 5; CALL; } break;             \
+    case 6: { constexpr int LM_ = 6; CALL; } break;             \
+    case 7: { constexpr int LM_ = 7; CALL; } break;             \
+    case 8: { constexpr int LM_ = 8; CALL; } break;             \
+    case 9: { constexpr int LM_ = 9; CALL; } break;             \
+    case 10: { constexpr int LM_ = 10; CALL; } break;           \
+    case 11: { constexpr int LM_ = 11; CALL; } break;           \
+    case 12: { constexpr int LM_ = 12; CALL; } break;           \
+    case 13: { constexpr int LM_ = 13; CALL; } break;           \
+    case 14: { constexpr int LM_ = 14; CALL; } break;           \
+    default: return set_error_msg("unsupported FFT length (need 2^4 .. 2^14 complex points)"); \
+  }
+

@@ -36,6 +36,30 @@ int launch_axpy(cudaStream_t, const float* x, int nterms, const float* const* y,
 int launch_diag_2d(cudaStream_t, const float* u, const float* v, int batch, int Nx, int Ny,
                    float inv_hx, float inv_hy, double* out4);
 
+int launch_rfft_rows3(cudaStream_t, int lm, const float* rhs, float2* T, int batch, int NR,
+                      const float2* tw, const float2* rtw);
+int launch_irfft_rows3(cudaStream_t, int lm, const float2* T, float* q, int batch, int NR,
+                       const float2* tw, const float2* rtw);
+int launch_lines_scatter(cudaStream_t, int lm, const float2* A, float2* B, int planes, int NL,
+                         const float2* tw);
+int launch_lines_gather(cudaStream_t, int lm, const float2* B, float2* A, int planes, int NL,
+                        const float2* tw);
+int launch_xlines3(cudaStream_t, int lm, float2* T, size_t nlines, int N1, int NZP, const float2* tw,
+                   const double* const* lam, const float* const* lamf, int fastd, double cutoff,
+                   float norm);
+int launch_divergence_3d(cudaStream_t, const float* u, const float* v, const float* w, float* rhs,
+                         int batch, int N0, int N1, int N2, float ihx, float ihy, float ihz);
+int launch_correct_3d(cudaStream_t, const float* us, const float* vs, const float* ws, const float* q,
+                      float* uo, float* vo, float* wo, int batch, int N0, int N1, int N2, float ihx,
+                      float ihy, float ihz);
+int launch_smag_nut_3d(cudaStream_t, const float* u, const float* v, const float* w, float* nut,
+                       int batch, int N0, int N1, int N2, const StepConsts& c);
+int launch_explicit_3d(cudaStream_t, const float* u, const float* v, const float* w, const float* nut,
+                       float* us, float* vs, float* ws, int batch, int N0, int N1, int N2,
+                       const StepConsts& c, int dvdt_mode);
+int launch_diag_3d(cudaStream_t, const float* u, const float* v, const float* w, int batch, int N0,
+                   int N1, int N2, float ihx, float ihy, float ihz, double* out4);
+
 // ---- errors / counters ------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
@@ -90,9 +114,12 @@ struct cfd_plan {
   int device = 0;
   size_t cells = 0;  // per batch member
   // FFT tables
-  int lm_row = 0, lm_x = 0;
+  int lm_row = 0, lm_x = 0, lm_y = 0;  // log2 of: last axis / 2, axis 0, axis 1 (3-D only)
   float2* tw_row = nullptr;
   float2* tw_x = nullptr;
+  float2* tw_y = nullptr;   // 3-D: complex lines along axis 1
+  float2* T2 = nullptr;     // 3-D: second spectrum buffer
+  float* nut = nullptr;     // 3-D: Smagorinsky eddy viscosity at cell centres
   float2* rtw = nullptr;
   double* lam[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
   float* lamf[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // float32 copies for the fast path
@@ -164,7 +191,7 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
     if (k < CFD_FORCE_SEPARABLE || k > CFD_FORCE_SMAGORINSKY)
       return set_error_msg("cfd_params.term_kind: unknown forcing kind");
     if (k == CFD_FORCE_SMAGORINSKY && d == 2)
-      return set_error_msg("Smagorinsky closure is implemented for 3-D grids only in this build");
+      return set_error_msg("the Smagorinsky closure is implemented for 3-D grids only");
     c->term_kind[t] = k;
   }
   c->linear_coef = (float)prm->linear_coef;
@@ -210,6 +237,58 @@ int correct_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, c
   return 0;
 }
 
+// 3-D: q = pinv(rhs) in five sweeps (poisson_3d.cu)
+int solve_3d(cfd_plan* p, cudaStream_t st, float* q) {
+  const int N0 = (int)p->shape[0], N1 = (int)p->shape[1], N2 = (int)p->shape[2];
+  const int NZP = N2 / 2 + 1;
+  if (int e = launch_rfft_rows3(st, p->lm_row, p->rhs, p->T, p->batch, N0 * N1, p->tw_row, p->rtw)) return e;
+  prof_mark(p, st, "rfft_z");
+  if (int e = launch_lines_scatter(st, p->lm_y, p->T, p->T2, p->batch * NZP, N0, p->tw_y)) return e;
+  prof_mark(p, st, "fft_y");
+  const float norm = (float)(1.0 / (2.0 * (double)p->cells));
+  if (int e = launch_xlines3(st, p->lm_x, p->T2, (size_t)p->batch * NZP * N1, N1, NZP, p->tw_x, p->lam,
+                             p->lamf, p->fastd, p->cutoff, norm))
+    return e;
+  prof_mark(p, st, "xlines3");
+  if (int e = launch_lines_gather(st, p->lm_y, p->T2, p->T, p->batch * NZP, N0, p->tw_y)) return e;
+  prof_mark(p, st, "ifft_y");
+  if (int e = launch_irfft_rows3(st, p->lm_row, p->T, q, p->batch, N0 * N1, p->tw_row, p->rtw)) return e;
+  prof_mark(p, st, "irfft_z");
+  return 0;
+}
+
+int step_3d(cfd_plan* p, cudaStream_t st, const float* const* v_in, float* const* v_out, float* q_out,
+            const StepConsts& c) {
+  const int N0 = (int)p->shape[0], N1 = (int)p->shape[1], N2 = (int)p->shape[2];
+  const float ih[3] = {(float)(1.0 / p->step[0]), (float)(1.0 / p->step[1]), (float)(1.0 / p->step[2])};
+  float* nut = nullptr;
+  for (int t = 0; t < c.n_terms; ++t)
+    if (c.term_kind[t] == CFD_FORCE_SMAGORINSKY) {
+      if (!p->nut) CFD_CUDA_OK(cudaMalloc((void**)&p->nut, (size_t)p->batch * p->cells * sizeof(float)));
+      nut = p->nut;
+    }
+  prof_mark(p, st, "begin");
+  if (nut) {
+    if (int e = launch_smag_nut_3d(st, v_in[0], v_in[1], v_in[2], nut, p->batch, N0, N1, N2, c)) return e;
+    prof_mark(p, st, "smag_nut");
+  }
+  if (int e = launch_explicit_3d(st, v_in[0], v_in[1], v_in[2], nut, p->us[0], p->us[1], p->us[2],
+                                 p->batch, N0, N1, N2, c, 0))
+    return e;
+  prof_mark(p, st, "explicit_3d");
+  if (int e = launch_divergence_3d(st, p->us[0], p->us[1], p->us[2], p->rhs, p->batch, N0, N1, N2,
+                                   ih[0], ih[1], ih[2]))
+    return e;
+  prof_mark(p, st, "divergence_3d");
+  float* q = q_out ? q_out : p->qbuf;
+  if (int e = solve_3d(p, st, q)) return e;
+  if (int e = launch_correct_3d(st, p->us[0], p->us[1], p->us[2], q, v_out[0], v_out[1], v_out[2],
+                                p->batch, N0, N1, N2, ih[0], ih[1], ih[2]))
+    return e;
+  prof_mark(p, st, "correct_3d");
+  return 0;
+}
+
 int ensure_lazy_buffers(cfd_plan* p) {
   const size_t fbytes = (size_t)p->batch * p->cells * sizeof(float);
   for (int a = 0; a < p->ndim; ++a)
@@ -238,7 +317,7 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
                     int device) {
   if (out == nullptr || shape == nullptr || step == nullptr) return set_error_msg("null argument");
   *out = nullptr;
-  if (ndim != 2) return set_error_msg("cfd_plan_create: only ndim == 2 is implemented in this build");
+  if (ndim != 2 && ndim != 3) return set_error_msg("cfd_plan_create: ndim must be 2 or 3");
   if (batch < 1) return set_error_msg("batch must be >= 1");
   for (int j = 0; j < ndim; ++j) {
     if (!is_pow2(shape[j]) || shape[j] < 16)
@@ -267,6 +346,10 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   int err = 0;
   err |= upload(&p->tw_row, build_twiddles(p->lm_row));
   err |= upload(&p->tw_x, build_twiddles(p->lm_x));
+  if (ndim == 3) {
+    p->lm_y = ilog2(shape[1]);
+    err |= upload(&p->tw_y, build_twiddles(p->lm_y));
+  }
   {
     const int M = Ny / 2;
     std::vector<float2> rtw(M / 2 + 1);
@@ -308,7 +391,11 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   }
   if (!err && cudaMalloc((void**)&p->rhs, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   if (!err && cudaMalloc((void**)&p->qbuf, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
-  if (!err && cudaMalloc((void**)&p->T, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  // spectrum: packed Ny/2 columns in 2-D, unpacked N2/2 + 1 planes (two buffers) in 3-D
+  const size_t tbytes = ndim == 2 ? fbytes
+                                  : (size_t)batch * (shape[2] / 2 + 1) * shape[0] * shape[1] * sizeof(float2);
+  if (!err && cudaMalloc((void**)&p->T, tbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  if (!err && ndim == 3 && cudaMalloc((void**)&p->T2, tbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   if (!err && cudaMalloc((void**)&p->diag_dev, 8 * sizeof(double)) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   p->workspace_bytes = (size_t)(ndim + 3) * fbytes;
   if (err) {
@@ -325,6 +412,9 @@ void cfd_plan_destroy(cfd_plan* p) {
   cudaSetDevice(p->device);
   cudaFree(p->tw_row);
   cudaFree(p->tw_x);
+  cudaFree(p->tw_y);
+  cudaFree(p->T2);
+  cudaFree(p->nut);
   cudaFree(p->rtw);
   for (int j = 0; j < CFD_MAX_DIM; ++j) {
     cudaFree(p->lam[j]);
@@ -358,6 +448,7 @@ int cfd_step(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* co
   cudaStream_t st = (cudaStream_t)stream;
   StepConsts c;
   if (int e = make_consts(p, params, &c)) return e;
+  if (p->ndim == 3) return step_3d(p, st, v_in, v_out, q_out, c);
   const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
   float* q = q_out ? q_out : p->qbuf;
   prof_mark(p, st, "begin");
@@ -420,6 +511,14 @@ int cfd_repeated(cfd_plan* p, cfd_stream stream, float* const* v_a, float* const
   if (nsteps == 0) return 0;
   float* const* dst = (nsteps & 1) ? v_b : v_a;
   if (nsteps == 1) return cfd_step(p, stream, v_a, dst, nullptr, params);
+  if (p->ndim == 3) {  // 3-D: plain ping-pong (no lazy chain yet)
+    for (int n = 0; n < nsteps; ++n) {
+      float* const* src = (n & 1) ? v_b : v_a;
+      float* const* out = (n & 1) ? v_a : v_b;
+      if (int e = cfd_step(p, stream, src, out, nullptr, params)) return e;
+    }
+    return 0;
+  }
   // the chain reads v_a only in its first kernel, so writing the result back into v_a is safe
   return repeated_lazy(p, (cudaStream_t)stream, v_a, dst, nsteps, params);
 }
@@ -432,6 +531,20 @@ int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
   if (int e = make_consts(p, params, &c)) return e;
   for (int a = 0; a < p->ndim; ++a)
     if (v_in[a] == dvdt_out[a]) return set_error_msg("cfd_explicit_terms: output must not alias input");
+  if (p->ndim == 3) {
+    const int N0 = (int)p->shape[0], N1 = (int)p->shape[1], N2 = (int)p->shape[2];
+    float* nut = nullptr;
+    for (int t = 0; t < c.n_terms; ++t)
+      if (c.term_kind[t] == CFD_FORCE_SMAGORINSKY) {
+        if (!p->nut) CFD_CUDA_OK(cudaMalloc((void**)&p->nut, (size_t)p->batch * p->cells * sizeof(float)));
+        nut = p->nut;
+      }
+    if (nut)
+      if (int e = launch_smag_nut_3d((cudaStream_t)stream, v_in[0], v_in[1], v_in[2], nut, p->batch, N0, N1, N2, c))
+        return e;
+    return launch_explicit_3d((cudaStream_t)stream, v_in[0], v_in[1], v_in[2], nut, dvdt_out[0],
+                              dvdt_out[1], dvdt_out[2], p->batch, N0, N1, N2, c, 1);
+  }
   return launch_explicit_2d((cudaStream_t)stream, v_in[0], v_in[1], nullptr, dvdt_out[0],
                             dvdt_out[1], nullptr, p->batch, (int)p->shape[0], (int)p->shape[1], c, 1);
 }
@@ -441,6 +554,16 @@ int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float*
   if (int e = check_plan(p)) return e;
   if (!v_in || !v_out) return set_error_msg("null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->ndim == 3) {
+    const int N0 = (int)p->shape[0], N1 = (int)p->shape[1], N2 = (int)p->shape[2];
+    const float ih[3] = {(float)(1.0 / p->step[0]), (float)(1.0 / p->step[1]), (float)(1.0 / p->step[2])};
+    if (int e = launch_divergence_3d(st, v_in[0], v_in[1], v_in[2], p->rhs, p->batch, N0, N1, N2, ih[0], ih[1], ih[2]))
+      return e;
+    float* q3 = q_out ? q_out : p->qbuf;
+    if (int e = solve_3d(p, st, q3)) return e;
+    return launch_correct_3d(st, v_in[0], v_in[1], v_in[2], q3, v_out[0], v_out[1], v_out[2], p->batch,
+                             N0, N1, N2, ih[0], ih[1], ih[2]);
+  }
   const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
   if (int e = launch_divergence_2d(st, v_in[0], v_in[1], p->rhs, p->batch, Nx, Ny,
                                    (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1])))
@@ -471,8 +594,13 @@ int cfd_diagnostics(cfd_plan* p, cfd_stream stream, const float* const* v, cfd_d
   if (int e = check_plan(p)) return e;
   if (!v || !out) return set_error_msg("null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (int e = launch_diag_2d(st, v[0], v[1], p->batch, (int)p->shape[0], (int)p->shape[1],
-                             (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1]), p->diag_dev))
+  if (p->ndim == 3) {
+    if (int e = launch_diag_3d(st, v[0], v[1], v[2], p->batch, (int)p->shape[0], (int)p->shape[1],
+                               (int)p->shape[2], (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1]),
+                               (float)(1.0 / p->step[2]), p->diag_dev))
+      return e;
+  } else if (int e = launch_diag_2d(st, v[0], v[1], p->batch, (int)p->shape[0], (int)p->shape[1],
+                                    (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1]), p->diag_dev))
     return e;
   double h[4];
   CFD_CUDA_OK(cudaMemcpyAsync(h, p->diag_dev, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -542,7 +670,8 @@ int cfd_step_profile(cfd_plan* p, cfd_stream stream, const float* const* v_in, f
     p->prof_events.clear();
     p->prof_names.clear();
     p->profiling = true;
-    int e = repeated_lazy(p, st, v_in, v_out, 3, params);
+    int e = p->ndim == 3 ? cfd_step(p, stream, v_in, v_out, nullptr, params)
+                         : repeated_lazy(p, st, v_in, v_out, 3, params);
     p->profiling = false;
     if (e) return e;
     CFD_CUDA_OK(cudaStreamSynchronize(st));

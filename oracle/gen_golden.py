@@ -158,6 +158,12 @@ def main():
   run_case('s3d_16x8x32_kolm', (16, 8, 32), d3, 7, 1.0, 2, 1.0, 1e-2, 0.03,
            [('kolmogorov', dict(scale=1.0, k=2)), ('linear', -0.1)], 0.17, [1, 3])
   run_case('d3d_16', (16, 16, 16), d3, 8, 1.0, 2, 1.0, 1e-2, 0.05, None, None, [1, 3])
+  # 3-D cases at sizes the CUDA line FFTs accept (axes >= 16, last axis >= 32)
+  run_case('s3d_16x16x32', (16, 16, 32), d3, 14, 1.0, 2, 1.0, 1.0 / 1600, 0.04,
+           [('kolmogorov', dict(scale=1.0, k=2)), ('linear', -0.1)], 0.2, [1, 3])
+  run_case('d3d_32x16x32', (32, 16, 32), d3, 15, 1.0, 2, 1.0, 1e-2, 0.04, None, None, [1, 3])
+  run_case('tg3d_16x32x32', (16, 32, 32), d3, 16, 1.0, 2, 1.0, 5e-3, 0.03,
+           [('taylor_green', dict(scale=0.5, k=1))], 0.15, [1, 2])
   # RK steppers ("next" row f2)
   run_case('rk4_2d_32', (32, 32), d2, 9, 1.0, 2, 1.0, 1e-2, 0.04, kolm, None, [1, 3],
            stepper='classic_rk4')
@@ -165,6 +171,7 @@ def main():
            stepper='midpoint_rk2')
   run_projection_case('proj2d_64x32', (64, 32), d2, 11)
   run_projection_case('proj3d_16x8x32', (16, 8, 32), d3, 12)
+  run_projection_case('proj3d_32x16x64', (32, 16, 64), d3, 17)
   run_projection_case('proj2d_step1_30x20', (30, 20), ((0.0, 30.0), (0.0, 20.0)), 13)
 
 

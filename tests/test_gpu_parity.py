@@ -57,14 +57,15 @@ def build_step(cfd, rec, grid, stepper=None):
 
 
 GOLDEN_2D = ['k2d_64x32', 'd2d_128', 'k2d_32x64_rho', 'tg2d_32']
+GOLDEN_3D = ['s3d_16x16x32', 'd3d_32x16x32', 'tg3d_16x32x32']
 
 
-@pytest.mark.parametrize('name', GOLDEN_2D)
+@pytest.mark.parametrize('name', GOLDEN_2D + GOLDEN_3D)
 def test_step_matches_reference_golden(cfd, name):
   rec = gu.load(name)
   grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
   step = build_step(cfd, rec, grid)
-  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(2)])
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(rec['ndim'])])
   # first step, with q
   v1, q = step.advance(v, 1, return_q=True)
   for i, a in enumerate(to_np(v1)):
@@ -94,10 +95,11 @@ def test_rk_steppers_match_reference_golden(cfd, name):
       assert gu.rel_l2(a, rec[f'f32_v{n}_{i}']) < TOL * n
 
 
-def test_projection_matches_reference_golden(cfd):
-  rec = gu.load('proj2d_64x32')
+@pytest.mark.parametrize('name', ['proj2d_64x32', 'proj3d_32x16x64'])
+def test_projection_matches_reference_golden(cfd, name):
+  rec = gu.load(name)
   grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
-  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(2)])
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(rec['ndim'])])
   vp = cfd.pressure.projection(v)
   q = cfd.pressure.solve_fast_diag(v)
   assert q.offset == grid.cell_center
@@ -242,3 +244,33 @@ def test_unsupported_options_raise(cfd):
              for o in g3.cell_faces)
   with pytest.raises(cfd.CfdError):
     s3(v3)  # non power-of-two axis
+
+
+@pytest.mark.parametrize('shape,cs', [((64, 32, 64), 0.2), ((32, 64, 128), None)])
+def test_step_3d_matches_oracle(cfd, shape, cs):
+  """Config #5 in miniature: Taylor-Green-like field, Smagorinsky closure, vs the oracle."""
+  dom = ((0.0, 2 * np.pi),) * 3
+  grid = cfd.grids.Grid(shape, domain=dom)
+  v0 = cfd_oracle.filtered_velocity_field(7, shape, dom, 1.0, 2)
+  dt = 0.5 * min(grid.step) / 1.0
+  nu = 1.0 / 1600
+  lin = cfd.forcings.linear_forcing(grid, 0.05)
+  if cs is not None:
+    step = cfd.subgrid_models.explicit_smagorinsky_navier_stokes(
+        dt=dt, cs=cs, forcing=lin, density=1.0, viscosity=nu, grid=grid)
+    of = cfd_oracle.Forcing((('linear', 0.05), ('smagorinsky', cs)))
+  else:
+    step = cfd.equations.semi_implicit_navier_stokes(1.0, nu, dt, grid, forcing=lin)
+    of = cfd_oracle.Forcing((('linear', 0.05),))
+  got, q = step.advance(wrap(cfd, grid, v0), 2, return_q=True)
+  want = v0
+  for _ in range(2):
+    want, wq = cfd_oracle.step(want, dt, grid.step, 1.0, nu, of, return_q=True)
+  for a, b in zip(to_np(got), want):
+    assert gu.rel_l2(a, b) < TOL
+  assert gu.rel_l2(np.asarray(q), wq) < TOL
+  assert np.abs(cfd_oracle.divergence(to_np(got), grid.step)).max() < 1e-3
+  d = cfd.diagnostics(got)
+  wd = cfd_oracle.diagnostics(to_np(got), grid.step)
+  assert abs(d['kinetic_energy'] - wd['kinetic_energy']) < 1e-6 * wd['kinetic_energy']
+  assert abs(d['max_speed_sq'] - wd['max_speed_sq']) < 1e-6 * wd['max_speed_sq']
