@@ -31,12 +31,12 @@ class Plan:
 
   def __del__(self):
     h = getattr(self, 'handle', None)
-    if h and _lib._lib is not None:
-      try:
+    try:
+      if h and _lib is not None and _lib._lib is not None:
         _lib._lib.cfd_plan_destroy(h)
-      except Exception:
-        pass
-      self.handle = None
+    except Exception:  # interpreter shutdown
+      pass
+    self.handle = None
 
 
 def get_plan(grid: grids.Grid, batch: int = 1, device: int = 0) -> Plan:
