@@ -124,6 +124,23 @@ int cfd_diagnostics(cfd_plan* plan, cfd_stream stream, const float* const* v, cf
 int cfd_step_host(cfd_plan* plan, const float* const* v_in_host, float* const* v_out_host,
                   float* q_out_host, int nsteps, const cfd_params* params);
 
+/* ---- slab-decomposed multi-GPU step (one process per GPU) -----------
+ * The reference has no distributed solver; this is the new path for
+ * BASELINE config #4.  The grid is split along axis 0; halo rows and the FFT transpose move over
+ * NVLink through CUDA-IPC peer mappings inside the kernels.  Protocol per rank:
+ *   cfd_dist_plan_create -> cfd_dist_export (64-byte blob) -> [host all-gathers the blobs]
+ *   -> cfd_dist_connect(all blobs) -> cfd_dist_load(local rows) -> cfd_dist_advance(n) ...
+ *   -> cfd_dist_store(local rows).  Every rank must make the same calls (device-side barriers). */
+int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const double* step, int rank,
+                         int world, int device);
+size_t cfd_dist_handle_bytes(void);
+int cfd_dist_export(cfd_plan* plan, void* blob);
+int cfd_dist_connect(cfd_plan* plan, const void* all_blobs);
+int cfd_dist_load(cfd_plan* plan, cfd_stream stream, const float* const* v_local);
+int cfd_dist_advance(cfd_plan* plan, cfd_stream stream, int nsteps, const cfd_params* params);
+int cfd_dist_store(cfd_plan* plan, cfd_stream stream, float* const* v_local_out, float* q_local_out);
+int cfd_dist_check(cfd_plan* plan); /* non-zero if a device-side barrier ever timed out */
+
 /* ---- thin device-memory helpers so hosts without a CUDA array library can drive the ABI --- */
 int cfd_malloc(void** dptr, size_t bytes);
 int cfd_free(void* dptr);

@@ -88,6 +88,18 @@ _SIGS = {
                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                         ctypes.POINTER(ctypes.c_char_p),
                                         ctypes.POINTER(ctypes.c_int)]),
+    'cfd_dist_plan_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                            ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int]),
+    'cfd_dist_handle_bytes': (ctypes.c_size_t, []),
+    'cfd_dist_export': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'cfd_dist_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'cfd_dist_load': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'cfd_dist_advance': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.POINTER(Params)]),
+    'cfd_dist_store': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                      ctypes.c_void_p]),
+    'cfd_dist_check': (ctypes.c_int, [ctypes.c_void_p]),
     'cfd_malloc': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
     'cfd_free': (ctypes.c_int, [ctypes.c_void_p]),
     'cfd_malloc_host': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),

@@ -32,6 +32,20 @@ struct StepConsts {
   const float* field[CFD_MAX_DIM];
 };
 
+// One input field of a slab-decomposed grid: this rank's rows and the neighbouring ranks' buffers
+// (peer-mapped); on a single GPU all three point at the same array.
+struct SlabSrc {
+  const float* prev;
+  const float* own;
+  const float* next;
+};
+
+// Slab-local spectrum buffers of all ranks of a distributed FFT (peer-mapped with CUDA IPC).
+#define CFD_MAX_PEERS 8
+struct LinePeers {
+  float2* p[CFD_MAX_PEERS];
+};
+
 __device__ __forceinline__ int wrap_idx(int i, int n) {  // i in [-n, 2n)
   i = i < 0 ? i + n : i;
   return i >= n ? i - n : i;

@@ -59,11 +59,16 @@ __device__ __forceinline__ void strow(float* p, const FC<2>& f) {
 // LAZY: the inputs are the UNPROJECTED state of the previous step (u*, v*) plus its pressure q;
 // the projection  v = u* - forward_difference(q)  (pressure.py:194-196) is applied while the
 // window rows are loaded, so that chained steps never materialise the projected state in HBM.
+//
+// Slab decomposition (multi-GPU): Nx is the number of LOCAL rows; rows -3..-1 and Nx..Nx+2 are read
+// straight from the neighbouring ranks' buffers over NVLink (SlabSrc::prev / next, peer-mapped
+// with CUDA IPC) -- the halo exchange is fused into the stencil loads.  On one GPU prev = next =
+// own, which is the periodic wrap.
 template <int TX, int PATTERN, int C, bool LAZY>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
-explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
-                  const float* __restrict__ qprev, float* __restrict__ us, float* __restrict__ vs,
-                  float* __restrict__ rhs, int Nx, int Ny, StepConsts c, int dvdt_mode) {
+explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
+                  float* __restrict__ vs, float* __restrict__ rhs, int Nx, int Ny, int row0,
+                  int nx_global, StepConsts c, int dvdt_mode) {
   using Row = FC<C>;
   // Halo lanes: the divergence needs v* one column to the left of the first stored column, whose
   // own stencil reaches 2 further columns: 4 columns = 1 lane (C = 4) or 2 lanes (C = 2) on the
@@ -81,24 +86,28 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
   if (jg < 0) jg += Ny;
   const bool store_ok = (lane >= kHaloL) && (lane < 32 - kHaloR) && (jbase < Ny);
   const size_t boff = (size_t)blockIdx.z * (size_t)Nx * (size_t)Ny;
-  u += boff;
-  v += boff;
-  if (LAZY) qprev += boff;
   const int i0 = blockIdx.y * TX;
   const int iend = min(i0 + TX, Nx);  // exclusive
 
-  auto rowptr = [&](const float* base, int i) {
-    int iw = i % Nx;
-    if (iw < 0) iw += Nx;
-    return base + (size_t)iw * Ny + jg;
+  // row i in [-Nx, 2 Nx) of a slab-decomposed field
+  auto rowptr = [&](const SlabSrc& f, int i) -> const float* {
+    const float* base = f.own;
+    if (i < 0) {
+      base = f.prev;
+      i += Nx;
+    } else if (i >= Nx) {
+      base = f.next;
+      i -= Nx;
+    }
+    return base + boff + (size_t)i * Ny + jg;
   };
 
   // window rows i-2 .. i+2 for the first processed row i = i0 - 1
   Row ua[5], va[5];
 #pragma unroll
   for (int r = 0; r < 5; ++r) {
-    ua[r] = ldrow<C>(rowptr(u, i0 - 3 + r));
-    va[r] = ldrow<C>(rowptr(v, i0 - 3 + r));
+    ua[r] = ldrow<C>(rowptr(su, i0 - 3 + r));
+    va[r] = ldrow<C>(rowptr(sv, i0 - 3 + r));
   }
   // lazily projected input: row r of (u, v) = (u*, v*)[r] - grad q, needs q rows r and r+1 and
   // the column to the right (from lane+1; lane 31's last column is never used by lane 30)
@@ -117,7 +126,7 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
   if (LAZY) {
     Row qa[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) qa[r] = ldrow<C>(rowptr(qprev, i0 - 3 + r));
+    for (int r = 0; r < 6; ++r) qa[r] = ldrow<C>(rowptr(sq, i0 - 3 + r));
 #pragma unroll
     for (int r = 0; r < 5; ++r) project_row(ua[r], va[r], qa[r], qa[r + 1]);
     qkeep = qa[5];
@@ -140,10 +149,6 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
   for (int k = 0; k < C; ++k) us_prev.a[k] = 0.f;
   float vL1_cur = __shfl_up_sync(FULLMASK, va[2].a[C - 1], 1);  // v[i][-1] for i = i0-1
 
-  // incrementally wrapped row indices (no integer modulo inside the loop)
-  int inext = (i0 + 2) % Nx;       // row i + 3 of the current iteration
-  int inextq = (i0 + 3) % Nx;      // row i + 4 (LAZY: the q row below the prefetched state row)
-  int iwrow = (i0 - 1 + Nx) % Nx;  // row i
 
   // forcing tables: the column profiles of the separable term are fixed per thread
   constexpr bool kHasSep = ((PATTERN & 3) == 1) || (((PATTERN >> 2) & 3) == 1) || (((PATTERN >> 4) & 3) == 1);
@@ -182,8 +187,8 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
   if (has_px) {
 #pragma unroll
     for (int sgm = 0; sgm < 3; ++sgm) {
-      int iw = (i0 - 1 + 32 * sgm + lane) % Nx;
-      if (iw < 0) iw += Nx;
+      int iw = (row0 + i0 - 1 + 32 * sgm + lane) % nx_global;  // GLOBAL row of the profile
+      if (iw < 0) iw += nx_global;
       if (px_u) pxu_tab[sgm] = __ldg(px_u + iw);
       if (px_v) pxv_tab[sgm] = __ldg(px_v + iw);
     }
@@ -193,8 +198,10 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
 #pragma unroll
   for (int k = 0; k < C; ++k) nfu.a[k] = nfv.a[k] = 0.f;
   if (kHasField) {
-    if (c.field[0]) nfu = ldrow<C>(rowptr(c.field[0], i0 - 1));
-    if (c.field[1]) nfv = ldrow<C>(rowptr(c.field[1], i0 - 1));
+    // (field forcing is single-GPU only: rows wrap inside the local array)
+    const int iwf = (i0 - 1 + Nx) % Nx;
+    if (c.field[0]) nfu = ldrow<C>(c.field[0] + (size_t)iwf * Ny + jg);
+    if (c.field[1]) nfv = ldrow<C>(c.field[1] + (size_t)iwf * Ny + jg);
   }
 
 #pragma unroll 1
@@ -222,9 +229,9 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
 #pragma unroll
     for (int k = 0; k < C; ++k) nu.a[k] = nv.a[k] = nq.a[k] = 0.f;
     if (i + 1 < iend) {
-      nu = ldrow<C>(u + (size_t)inext * Ny + jg);
-      nv = ldrow<C>(v + (size_t)inext * Ny + jg);
-      if (LAZY) nq = ldrow<C>(qprev + (size_t)inextq * Ny + jg);
+      nu = ldrow<C>(rowptr(su, i + 3));
+      nv = ldrow<C>(rowptr(sv, i + 3));
+      if (LAZY) nq = ldrow<C>(rowptr(sq, i + 4));
     }
 
     // ---- face fluxes
@@ -247,7 +254,7 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
     }
 
     // ---- assemble
-    const int iw = iwrow;
+    const int iw = i < 0 ? i + Nx : i;  // local row (the warm-up row -1 is never stored)
     Row us_cur, vs_cur;
     float pxu_row = 1.f, pxv_row = 1.f;
     if (has_px) {
@@ -330,26 +337,25 @@ explicit2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
     if (LAZY) {
       project_row(nu, nv, qkeep, nq);
       qkeep = nq;
-      inextq = (inextq + 1 == Nx) ? 0 : inextq + 1;
     }
     ua[4] = nu;
     va[4] = nv;
-    iwrow = (iwrow + 1 == Nx) ? 0 : iwrow + 1;
     if (kHasField && i + 1 < iend) {
-      if (c.field[0]) nfu = ldrow<C>(c.field[0] + (size_t)iwrow * Ny + jg);
-      if (c.field[1]) nfv = ldrow<C>(c.field[1] + (size_t)iwrow * Ny + jg);
+      if (c.field[0]) nfu = ldrow<C>(c.field[0] + (size_t)(i + 1) * Ny + jg);
+      if (c.field[1]) nfv = ldrow<C>(c.field[1] + (size_t)(i + 1) * Ny + jg);
     }
-    inext = (inext + 1 == Nx) ? 0 : inext + 1;
   }
 }
 
 }  // namespace
 
-// qprev == nullptr: (u, v) is a projected state.  qprev != nullptr: LAZY mode, (u, v) = (u*, v*) of
-// the previous step and qprev its pressure.
-int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, const float* qprev,
-                       float* us, float* vs, float* rhs, int batch, int Nx, int Ny,
-                       const StepConsts& c, int dvdt_mode) {
+// sq.own == nullptr: (u, v) is a projected state.  sq.own != nullptr: LAZY mode, (u, v) = (u*, v*)
+// of the previous step and q its pressure.  Nx = local rows; row0 / nx_global place the slab.
+int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc sq, float* us,
+                            float* vs, float* rhs, int batch, int Nx, int Ny, int row0,
+                            int nx_global, const StepConsts& c, int dvdt_mode) {
+  const float* qprev = sq.own;
+  if (Nx < 3) return set_error_msg("a slab needs at least 3 rows");
   constexpr int TX = 64;
   static const int forced_cols = [] {  // tuning knob: CFD_EXPLICIT_COLS=2|4 columns per lane
     const char* e = getenv("CFD_EXPLICIT_COLS");
@@ -371,9 +377,8 @@ int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, cons
     pattern |= code << (2 * nt++);
   }
 #define CFD_EXPL_LAUNCH(P, CC, LZ)                                                          \
-  explicit2d_kernel<TX, P, CC, LZ><<<grid, 32 * kWarpsPerCta, 0, stream>>>(u, v, qprev, us, vs, \
-                                                                            rhs, Nx, Ny, c,     \
-                                                                            dvdt_mode)
+  explicit2d_kernel<TX, P, CC, LZ><<<grid, 32 * kWarpsPerCta, 0, stream>>>(                    \
+      su, sv, sq, us, vs, rhs, Nx, Ny, row0, nx_global, c, dvdt_mode)
 #define CFD_EXPL_CASE(P)                    \
   case P:                                   \
     if (cols == 2) {                        \
@@ -400,6 +405,14 @@ int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, cons
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+
+int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, const float* qprev,
+                       float* us, float* vs, float* rhs, int batch, int Nx, int Ny,
+                       const StepConsts& c, int dvdt_mode) {
+  const SlabSrc su = {u, u, u}, sv = {v, v, v}, sq = {qprev, qprev, qprev};
+  return launch_explicit_2d_slab(stream, su, sv, sq, us, vs, rhs, batch, Nx, Ny, 0, Nx, c, dvdt_mode);
 }
 
 }  // namespace cfd

@@ -1,0 +1,284 @@
+// Slab-decomposed multi-GPU time step: one process per GPU, the grid is
+// split along axis 0, and ALL inter-GPU data movement is done by the compute kernels themselves
+// through peer-mapped (CUDA IPC) memory over NVLink:
+//   * stencil halo: explicit2d_kernel reads rows -3..-1 / Nloc..Nloc+3 of (u*, v*, q) directly
+//     from the neighbouring ranks' buffers (SlabSrc::prev / next);
+//   * distributed FFT: every rank row-transforms its slab into its local T[ky][x_loc]; the
+//     x-direction kernel of rank r then assembles each of ITS ky lines from all ranks' T, applies
+//     fwd * D * inv and writes the line back in place -- the all-to-all transpose and its inverse
+//     are the loads and stores of xlines_kernel (LinePeers), large contiguous peer accesses;
+//   * ordering: a one-CTA flag barrier kernel (system-scope stores/loads on peer-mapped flags)
+//     between the phases.  No NCCL on the data path; the host side only exchanges 64-byte IPC
+//     handles once (any transport: torch.distributed in jax_cfd_b200.distributed).
+#include <string.h>
+
+#include "common.cuh"
+#include "plan_struct.cuh"
+
+namespace cfd {
+
+int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc sq, float* us,
+                            float* vs, float* rhs, int batch, int Nx, int Ny, int row0,
+                            int nx_global, const StepConsts& c, int dvdt_mode);
+int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
+                     const float2* tw, const float2* rtw);
+int launch_irfft_rows(cudaStream_t, int lm_row, const float2* T, float* q, int batch, int Nx,
+                      const float2* tw, const float2* rtw);
+int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int lnloc,
+                        size_t line_begin, size_t nlines, int My, const float2* tw,
+                        const double* lamx, const double* lamy, const float* lamxf,
+                        const float* lamyf, int fastd, double cutoff, float norm);
+int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
+                      const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
+                      float inv_hx, float inv_hy);
+
+namespace {
+
+struct FlagPeers {
+  unsigned long long* p[CFD_MAX_PEERS];
+};
+
+// All-to-all flag barrier: rank r publishes `epoch` in slot r of every peer's flag array, then
+// waits until every peer has published it in r's own array.  The kernels before it on the stream
+// have completed (their stores are performed), so observing a peer's flag implies its data is
+// visible.  A cycle budget bounds the spin so that a lost peer cannot hang the GPU.
+__global__ void slab_barrier_kernel(FlagPeers fp, int rank, int world, unsigned long long epoch,
+                                    unsigned long long* err) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  __threadfence_system();
+  volatile unsigned long long* remote = fp.p[p] + rank;
+  *remote = epoch;
+  __threadfence_system();
+  volatile unsigned long long* mine = fp.p[rank] + p;
+  const long long t0 = clock64();
+  while (*mine < epoch) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s
+      *err = epoch;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+// layout of the shared (IPC-exported) allocation, identical on every rank; units = floats
+struct SharedLayout {
+  size_t field;  // floats per local field
+  size_t off_vin[2], off_us[2][2], off_q[2], off_T, off_flags, total_bytes;
+};
+SharedLayout shared_layout(size_t nloc, size_t ny) {
+  SharedLayout L;
+  L.field = nloc * ny;
+  size_t o = 0;
+  for (int a = 0; a < 2; ++a) { L.off_vin[a] = o; o += L.field; }
+  for (int s = 0; s < 2; ++s)
+    for (int a = 0; a < 2; ++a) { L.off_us[s][a] = o; o += L.field; }
+  for (int s = 0; s < 2; ++s) { L.off_q[s] = o; o += L.field; }
+  L.off_T = o; o += L.field;  // My * Nloc float2 = Nloc * Ny floats
+  L.off_flags = o; o += 64;   // 16 x 8-byte flags + error word
+  L.total_bytes = o * sizeof(float);
+  return L;
+}
+
+float* fptr(void* base, size_t off) { return reinterpret_cast<float*>(base) + off; }
+
+int barrier(cfd_plan* p, cudaStream_t st) {
+  if (p->world == 1) return 0;
+  const SharedLayout L = shared_layout((size_t)p->shape[0], (size_t)p->shape[1]);
+  FlagPeers fp;
+  for (int r = 0; r < CFD_MAX_PEERS; ++r)
+    fp.p[r] = reinterpret_cast<unsigned long long*>(fptr(p->peer_shared[r < p->world ? r : p->rank], L.off_flags));
+  p->epoch += 1;
+  unsigned long long* err = reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + 16;
+  slab_barrier_kernel<<<1, 32, 0, st>>>(fp, p->rank, p->world, p->epoch, err);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+}  // namespace cfd
+
+using namespace cfd;
+
+extern "C" {
+
+int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const double* step, int rank,
+                         int world, int device) {
+  if (!out || !global_shape || !step) return set_error_msg("null argument");
+  *out = nullptr;
+  if (world < 1 || world > CFD_MAX_PEERS || (world & (world - 1)))
+    return set_error_msg("world size must be 1, 2, 4 or 8");
+  if (rank < 0 || rank >= world) return set_error_msg("bad rank");
+  const int64_t Nxg = global_shape[0], Ny = global_shape[1];
+  if (Nxg % world) return set_error_msg("axis 0 must be divisible by the number of ranks");
+  const int64_t nloc = Nxg / world;
+  if (nloc < 16 || (nloc & (nloc - 1))) return set_error_msg("local slab must be a power of two >= 16 rows");
+  if ((Ny / 2) % world || (Ny / 2 / world) % 16) return set_error_msg("Ny/2 lines must split evenly over the ranks");
+  if (Nxg > (1 << 14)) return set_error_msg("global axis 0 longer than 16384 is not supported yet");
+  // an ordinary plan for the LOCAL slab gives the row tables + local workspace ...
+  int64_t local_shape[2] = {nloc, Ny};
+  cfd_plan* p = nullptr;
+  if (int e = cfd_plan_create(&p, 2, local_shape, step, 1, device)) return e;
+  // ... then replace what depends on the GLOBAL x extent (x-line twiddles, eigenvalues, norm)
+  if (int e = plan_tables_create(p, 2, global_shape, step)) {
+    cfd_plan_destroy(p);
+    return e;
+  }
+  p->rank = rank;
+  p->world = world;
+  p->nx_global = Nxg;
+  const SharedLayout L = shared_layout((size_t)nloc, (size_t)Ny);
+  if (cudaMalloc(&p->shared, L.total_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    cfd_plan_destroy(p);
+    return set_error_msg("shared slab allocation failed");
+  }
+  cudaMemset(p->shared, 0, L.total_bytes);
+  p->shared_bytes = L.total_bytes;
+  for (int r = 0; r < CFD_MAX_PEERS; ++r) p->peer_shared[r] = p->shared;
+  *out = p;
+  return 0;
+}
+
+size_t cfd_dist_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+int cfd_dist_export(cfd_plan* p, void* blob) {
+  if (!p || !p->shared || !blob) return set_error_msg("not a distributed plan");
+  cudaIpcMemHandle_t h;
+  CFD_CUDA_OK(cudaSetDevice(p->device));
+  CFD_CUDA_OK(cudaIpcGetMemHandle(&h, p->shared));
+  memcpy(blob, &h, sizeof h);
+  return 0;
+}
+
+int cfd_dist_connect(cfd_plan* p, const void* all_blobs) {
+  if (!p || !p->shared || !all_blobs) return set_error_msg("not a distributed plan");
+  CFD_CUDA_OK(cudaSetDevice(p->device));
+  const char* b = reinterpret_cast<const char*>(all_blobs);
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) {
+      p->peer_shared[r] = p->shared;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, b + (size_t)r * sizeof h, sizeof h);
+    void* ptr = nullptr;
+    CFD_CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_shared[r] = ptr;
+  }
+  return 0;
+}
+
+// dist_state: 0 = nothing loaded, 1 = projected state in VIN, 2 = lazy (u*, v*, q) in slot dist_cur
+int cfd_dist_load(cfd_plan* p, cfd_stream stream, const float* const* v_local) {
+  if (!p || !p->shared) return set_error_msg("not a distributed plan");
+  CFD_CUDA_OK(cudaSetDevice(p->device));
+  const SharedLayout L = shared_layout((size_t)p->shape[0], (size_t)p->shape[1]);
+  for (int a = 0; a < 2; ++a)
+    CFD_CUDA_OK(cudaMemcpyAsync(fptr(p->shared, L.off_vin[a]), v_local[a], L.field * sizeof(float),
+                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  p->dist_state = 1;
+  p->dist_cur = 0;
+  return 0;
+}
+
+int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_params* params) {
+  if (!p || !p->shared || !params) return set_error_msg("not a distributed plan");
+  if (p->dist_state == 0) return set_error_msg("cfd_dist_advance: no state loaded");
+  CFD_CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  StepConsts c;
+  if (int e = make_consts(p, params, &c)) return e;
+  for (int t = 0; t < c.n_terms; ++t)
+    if (c.term_kind[t] == CFD_FORCE_FIELD && p->world > 1)
+      return set_error_msg("field forcing is not supported on slab-decomposed grids");
+  const int nloc = (int)p->shape[0], Ny = (int)p->shape[1], My = Ny / 2;
+  const SharedLayout L = shared_layout((size_t)nloc, (size_t)Ny);
+  const int prev = (p->rank + p->world - 1) % p->world, next = (p->rank + 1) % p->world;
+  auto src3 = [&](size_t off) {
+    return SlabSrc{fptr(p->peer_shared[prev], off), fptr(p->shared, off), fptr(p->peer_shared[next], off)};
+  };
+  LinePeers peers;
+  for (int r = 0; r < CFD_MAX_PEERS; ++r)
+    peers.p[r] = reinterpret_cast<float2*>(fptr(p->peer_shared[r < p->world ? r : p->rank], L.off_T));
+  int lnloc = 0;
+  while ((1 << lnloc) < nloc) ++lnloc;
+  const size_t lines_per_rank = (size_t)My / p->world;
+  for (int n = 0; n < nsteps; ++n) {
+    const int cur = p->dist_cur, nxt = cur ^ 1;
+    if (int e = barrier(p, st)) return e;  // neighbours' inputs (VIN or u*, v*, q) are complete
+    prof_mark(p, st, "begin");
+    if (p->dist_state == 1) {
+      const SlabSrc none = {nullptr, nullptr, nullptr};
+      if (int e = launch_explicit_2d_slab(st, src3(L.off_vin[0]), src3(L.off_vin[1]), none,
+                                          fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]),
+                                          p->rhs, 1, nloc, Ny, p->rank * nloc, (int)p->nx_global, c, 0))
+        return e;
+    } else {
+      if (int e = launch_explicit_2d_slab(st, src3(L.off_us[cur][0]), src3(L.off_us[cur][1]),
+                                          src3(L.off_q[cur]), fptr(p->shared, L.off_us[nxt][0]),
+                                          fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1, nloc, Ny,
+                                          p->rank * nloc, (int)p->nx_global, c, 0))
+        return e;
+    }
+    prof_mark(p, st, "explicit_2d_slab");
+    float2* Tloc = reinterpret_cast<float2*>(fptr(p->shared, L.off_T));
+    if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, Tloc, 1, nloc, p->tw_row, p->rtw)) return e;
+    prof_mark(p, st, "rfft_rows");
+    if (int e = barrier(p, st)) return e;  // every rank's slab spectrum is complete
+    if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
+                                    lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1], p->lamf[0],
+                                    p->lamf[1], p->fastd, p->cutoff, p->norm))
+      return e;
+    prof_mark(p, st, "xlines_peers");
+    if (int e = barrier(p, st)) return e;  // every rank has written its lines back into my slab
+    if (int e = launch_irfft_rows(st, p->lm_row, Tloc, fptr(p->shared, L.off_q[nxt]), 1, nloc,
+                                  p->tw_row, p->rtw))
+      return e;
+    prof_mark(p, st, "irfft_rows");
+    p->dist_cur = nxt;
+    p->dist_state = 2;
+  }
+  return 0;
+}
+
+int cfd_dist_store(cfd_plan* p, cfd_stream stream, float* const* v_local_out, float* q_local_out) {
+  if (!p || !p->shared) return set_error_msg("not a distributed plan");
+  if (p->dist_state == 0) return set_error_msg("cfd_dist_store: no state loaded");
+  CFD_CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nloc = (int)p->shape[0], Ny = (int)p->shape[1];
+  const SharedLayout L = shared_layout((size_t)nloc, (size_t)Ny);
+  if (p->dist_state == 1) {
+    for (int a = 0; a < 2; ++a)
+      CFD_CUDA_OK(cudaMemcpyAsync(v_local_out[a], fptr(p->shared, L.off_vin[a]), L.field * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (int e = barrier(p, st)) return e;  // the next rank's q is complete
+  const int cur = p->dist_cur, next = (p->rank + 1) % p->world;
+  if (int e = launch_correct_2d(st, fptr(p->shared, L.off_us[cur][0]), fptr(p->shared, L.off_us[cur][1]),
+                                fptr(p->shared, L.off_q[cur]), fptr(p->peer_shared[next], L.off_q[cur]),
+                                v_local_out[0], v_local_out[1], 1, nloc, Ny, (float)(1.0 / p->step[0]),
+                                (float)(1.0 / p->step[1])))
+    return e;
+  if (q_local_out)
+    CFD_CUDA_OK(cudaMemcpyAsync(q_local_out, fptr(p->shared, L.off_q[cur]), L.field * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+  // peers may still be reading my q for their own store: fence before anyone advances again
+  return barrier(p, st);
+}
+
+// 0 when no barrier ever timed out
+int cfd_dist_check(cfd_plan* p) {
+  if (!p || !p->shared) return set_error_msg("not a distributed plan");
+  const SharedLayout L = shared_layout((size_t)p->shape[0], (size_t)p->shape[1]);
+  unsigned long long err = 0;
+  CFD_CUDA_OK(cudaMemcpy(&err, reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + 16,
+                         sizeof err, cudaMemcpyDeviceToHost));
+  if (err) return set_error_msg("a slab barrier timed out (a peer rank did not arrive)");
+  return 0;
+}
+
+}  // extern "C"

@@ -19,8 +19,9 @@ int launch_explicit_2d(cudaStream_t, const float* u, const float* v, const float
                        int dvdt_mode);
 int launch_irfft_rows(cudaStream_t, int lm_row, const float2* T, float* q, int batch, int Nx,
                       const float2* tw, const float2* rtw);
-int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q, float* uo,
-                      float* vo, int batch, int Nx, int Ny, float inv_hx, float inv_hy);
+int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
+                      const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
+                      float inv_hx, float inv_hy);
 int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
                      const float2* tw, const float2* rtw);
 int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
@@ -106,45 +107,7 @@ static std::vector<float2> build_twiddles(int lm) {
 
 using namespace cfd;
 
-struct cfd_plan {
-  int ndim = 0;
-  int64_t shape[CFD_MAX_DIM] = {1, 1, 1};
-  double step[CFD_MAX_DIM] = {1, 1, 1};
-  int batch = 1;
-  int device = 0;
-  size_t cells = 0;  // per batch member
-  // FFT tables
-  int lm_row = 0, lm_x = 0, lm_y = 0;  // log2 of: last axis / 2, axis 0, axis 1 (3-D only)
-  float2* tw_row = nullptr;
-  float2* tw_x = nullptr;
-  float2* tw_y = nullptr;   // 3-D: complex lines along axis 1
-  float2* T2 = nullptr;     // 3-D: second spectrum buffer
-  float* nut = nullptr;     // 3-D: Smagorinsky eddy viscosity at cell centres
-  float2* rtw = nullptr;
-  double* lam[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
-  float* lamf[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // float32 copies for the fast path
-  int fastd = 0;  // 1: only the mean mode is below the pseudo-inverse cutoff
-  double cutoff = 0;
-  float norm = 0;
-  // workspace
-  float* us[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};   // unprojected state (ping)
-  float* us2[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // unprojected state (pong), lazy chains
-  float* rhs = nullptr;
-  float* qbuf = nullptr;   // pressure of the latest step
-  float* qbuf2 = nullptr;  // pong
-  float2* T = nullptr;
-  size_t workspace_bytes = 0;
-  // host-call staging
-  float* dev_a[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
-  float* dev_b[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
-  float* dev_q = nullptr;
-  cudaStream_t host_stream = nullptr;
-  double* diag_dev = nullptr;
-  // per-kernel timing
-  bool profiling = false;
-  std::vector<cudaEvent_t> prof_events;
-  std::vector<const char*> prof_names;
-};
+#include "plan_struct.cuh"
 
 namespace {
 
@@ -155,6 +118,9 @@ int upload(T** dst, const std::vector<T>& src) {
   return 0;
 }
 
+}  // namespace
+
+namespace cfd {
 void prof_mark(cfd_plan* p, cudaStream_t st, const char* name) {
   if (!p->profiling) return;
   cudaEvent_t ev;
@@ -208,6 +174,38 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
   return 0;
 }
 
+int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double* step) {
+  const int Nxg = (int)shape[0];
+  cudaFree(p->tw_x);
+  cudaFree(p->lam[0]);
+  cudaFree(p->lamf[0]);
+  p->tw_x = nullptr;
+  p->lam[0] = nullptr;
+  p->lamf[0] = nullptr;
+  p->lm_x = ilog2(Nxg);
+  int err = upload(&p->tw_x, build_twiddles(p->lm_x));
+  std::vector<double> lam(Nxg);
+  for (int k = 0; k < Nxg; ++k)
+    lam[k] = (2.0 * cos(2.0 * M_PI * (double)k / (double)Nxg) - 2.0) / (step[0] * step[0]);
+  lam[0] = 0.0;
+  err |= upload(&p->lam[0], lam);
+  std::vector<float> lamf(lam.begin(), lam.end());
+  err |= upload(&p->lamf[0], lamf);
+  double minabs = 1e300;
+  for (int j = 0; j < ndim; ++j) {
+    const double l1 = fabs((2.0 * cos(2.0 * M_PI / (double)shape[j]) - 2.0) / (step[j] * step[j]));
+    if (l1 < minabs) minabs = l1;
+  }
+  p->fastd = (minabs > 4.0 * p->cutoff) ? 1 : 0;
+  double cells = 1.0;
+  for (int j = 0; j < ndim; ++j) cells *= (double)shape[j];
+  p->norm = (float)(1.0 / (2.0 * cells));
+  return err;
+}
+}  // namespace cfd
+
+namespace {
+
 int check_plan(const cfd_plan* p) {
   if (p == nullptr) return set_error_msg("null plan");
   CFD_CUDA_OK(cudaSetDevice(p->device));
@@ -230,7 +228,7 @@ int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
 
 int correct_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, const float* q,
                float* uo, float* vo) {
-  if (int e = launch_correct_2d(st, us, vs, q, uo, vo, p->batch, (int)p->shape[0], (int)p->shape[1],
+  if (int e = launch_correct_2d(st, us, vs, q, nullptr, uo, vo, p->batch, (int)p->shape[0], (int)p->shape[1],
                                 (float)(1.0 / p->step[0]), (float)(1.0 / p->step[1])))
     return e;
   prof_mark(p, st, "correct");
@@ -411,6 +409,12 @@ void cfd_plan_destroy(cfd_plan* p) {
   if (p == nullptr) return;
   cudaSetDevice(p->device);
   cudaFree(p->tw_row);
+  if (p->shared) {
+    for (int r = 0; r < p->world; ++r)
+      if (r != p->rank && p->peer_shared[r] && p->peer_shared[r] != p->shared)
+        cudaIpcCloseMemHandle(p->peer_shared[r]);
+    cudaFree(p->shared);
+  }
   cudaFree(p->tw_x);
   cudaFree(p->tw_y);
   cudaFree(p->T2);

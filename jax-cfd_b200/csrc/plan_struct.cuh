@@ -1,0 +1,62 @@
+// The plan object behind the opaque cfd_plan handle (shared by plan.cu and multi_gpu.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct cfd_plan {
+  int ndim = 0;
+  int64_t shape[CFD_MAX_DIM] = {1, 1, 1};
+  double step[CFD_MAX_DIM] = {1, 1, 1};
+  int batch = 1;
+  int device = 0;
+  size_t cells = 0;  // per batch member
+  // FFT tables
+  int lm_row = 0, lm_x = 0, lm_y = 0;  // log2 of: last axis / 2, axis 0, axis 1 (3-D only)
+  float2* tw_row = nullptr;
+  float2* tw_x = nullptr;
+  float2* tw_y = nullptr;   // 3-D: complex lines along axis 1
+  float2* T2 = nullptr;     // 3-D: second spectrum buffer
+  float* nut = nullptr;     // 3-D: Smagorinsky eddy viscosity at cell centres
+  float2* rtw = nullptr;
+  double* lam[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* lamf[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // float32 copies for the fast path
+  int fastd = 0;  // 1: only the mean mode is below the pseudo-inverse cutoff
+  double cutoff = 0;
+  float norm = 0;
+  // workspace
+  float* us[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};   // unprojected state (ping)
+  float* us2[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // unprojected state (pong), lazy chains
+  float* rhs = nullptr;
+  float* qbuf = nullptr;   // pressure of the latest step
+  float* qbuf2 = nullptr;  // pong
+  float2* T = nullptr;
+  size_t workspace_bytes = 0;
+  // host-call staging
+  float* dev_a[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* dev_b[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
+  float* dev_q = nullptr;
+  cudaStream_t host_stream = nullptr;
+  double* diag_dev = nullptr;
+  // slab decomposition (multi_gpu.cu); world == 1 for ordinary plans
+  int rank = 0, world = 1;
+  int64_t nx_global = 0;    // global rows (shape[0] holds the LOCAL rows of a distributed plan)
+  void* shared = nullptr;   // one IPC-exported allocation holding every peer-visible buffer
+  size_t shared_bytes = 0;
+  void* peer_shared[CFD_MAX_PEERS] = {nullptr};  // peers' `shared` mapped here (own entry = shared)
+  unsigned long long epoch = 0;                   // barrier generation
+  int dist_state = 0, dist_cur = 0;               // see multi_gpu.cu
+  // per-kernel timing
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<const char*> prof_names;
+};
+
+
+namespace cfd {
+void prof_mark(cfd_plan* p, cudaStream_t st, const char* name);
+int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c);
+// (re)builds the tables that depend on the x extent for a slab plan: x-line twiddles, lambda_x,
+// fast-path flag and the 1/(2 Nx Ny) normalisation, from the GLOBAL shape
+int plan_tables_create(cfd_plan* p, int ndim, const int64_t* global_shape, const double* step);
+}  // namespace cfd

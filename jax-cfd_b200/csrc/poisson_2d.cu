@@ -84,27 +84,34 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
 
 // ------------------------------------------------------------------------------------------
 // X: lines T[line][0..Nx)  (line = b * My + ky), forward FFT * D * inverse FFT, in place.
+//
+// Multi-GPU: the line is assembled from the slab-local spectra of all ranks -- element x lives in
+// rank (x >> lnloc)'s buffer at [line][x & (Nloc-1)] -- so the loads/stores below ARE the
+// all-to-all transpose of the distributed FFT, done with peer accesses over NVLink inside the
+// kernel (each rank transforms its own range of ky lines).  One GPU: a single peer, Nloc = M.
 template <int LM, int LINES, bool FASTD>
 __global__ void __launch_bounds__(LINES * FftPlan<LM>::G)
-xlines_kernel(float2* __restrict__ T, int My, const float2* __restrict__ tw,
-              const double* __restrict__ lamx, const double* __restrict__ lamy,
-              const float* __restrict__ lamxf, const float* __restrict__ lamyf, double cutoff,
-              float norm) {
+xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
+              const float2* __restrict__ tw, const double* __restrict__ lamx,
+              const double* __restrict__ lamy, const float* __restrict__ lamxf,
+              const float* __restrict__ lamyf, double cutoff, float norm) {
   using P = FftPlan<LM>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, 16);
   extern __shared__ float2 smem[];
   const int tid = threadIdx.x;
   const int ln = tid / G, t = tid % G;
-  const size_t line0 = (size_t)blockIdx.x * LINES;
+  const size_t line0 = line_begin + (size_t)blockIdx.x * LINES;
   const size_t line = line0 + ln;
   const int ky = (int)(line % My);
   float2* s = smem + ln * RS;
-  float2* Tl = T + line * M;
+  const int nloc_mask = (1 << lnloc) - 1;
+  const size_t loff = line << lnloc;  // this line's offset inside every rank's buffer
+  auto elem = [&](int x) -> float2* { return peers.p[x >> lnloc] + loff + (x & nloc_mask); };
 
   float2 v[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) v[e] = Tl[t + G * e];
+  for (int e = 0; e < E; ++e) v[e] = *elem(t + G * e);
   FftRun<LM, -1>::run(v, t, s, tw);
 
   const bool cta_has_packed = (line0 % My) == 0;  // only the first line of a CTA can be ky = 0
@@ -159,7 +166,7 @@ xlines_kernel(float2* __restrict__ T, int My, const float2* __restrict__ tw,
   }
   FftRun<LM, +1>::run(v, t, s, tw);
 #pragma unroll
-  for (int e = 0; e < E; ++e) Tl[t + G * e] = v[e];
+  for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -307,17 +314,18 @@ irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
 }
 
 // v' = u* - forward_difference(q)   (pressure.py:194-196), 4 columns per thread
+// (qnext: the array holding row Nx of q -- the next rank's slab, or q itself on one GPU)
 __global__ void correct2d_kernel(const float* __restrict__ us, const float* __restrict__ vs,
-                                 const float* __restrict__ q, float* __restrict__ uo,
-                                 float* __restrict__ vo, int Nx, int Ny, float inv_hx,
-                                 float inv_hy) {
+                                 const float* __restrict__ q, const float* __restrict__ qnext,
+                                 float* __restrict__ uo, float* __restrict__ vo, int Nx, int Ny,
+                                 float inv_hx, float inv_hy) {
   const size_t b = blockIdx.z;
   const int x = blockIdx.y;
   const int j = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (j >= Ny) return;
-  const int xp = x == Nx - 1 ? 0 : x + 1;
-  const size_t row = (b * Nx + x) * (size_t)Ny, rowp = (b * Nx + xp) * (size_t)Ny;
-  const float4 q0 = ldg4(q + row + j), q1 = ldg4(q + rowp + j);
+  const size_t row = (b * Nx + x) * (size_t)Ny;
+  const float* qrow1 = (x == Nx - 1) ? qnext + (b * Nx) * (size_t)Ny : q + row + Ny;
+  const float4 q0 = ldg4(q + row + j), q1 = ldg4(qrow1 + j);
   const float qr = __ldg(q + row + (j + 4 == Ny ? 0 : j + 4));
   const float4 u4 = ldg4(us + row + j), v4 = ldg4(vs + row + j);
   float4 ou, ov;
@@ -383,24 +391,23 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
 }
 
 template <int LM>
-int launch_xlines_t(cudaStream_t st, float2* T, int batch, int My, const float2* tw,
-                    const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
-                    int fastd, double cutoff, float norm) {
+int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
+                    size_t nlines, int My, const float2* tw, const double* lamx, const double* lamy,
+                    const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
   constexpr int LINES = lines_for(LM);
   using P = FftPlan<LM>;
   constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
-  const size_t nlines = (size_t)batch * My;
-  if (nlines % LINES) return set_error_msg("internal: line count not divisible");
+  if (nlines % LINES || line_begin % LINES) return set_error_msg("internal: line count not divisible");
   if (fastd) {
     auto k = xlines_kernel<LM, LINES, true>;
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, My, tw, lamx, lamy, lamxf, lamyf,
-                                                            cutoff, norm);
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx,
+                                                            lamy, lamxf, lamyf, cutoff, norm);
   } else {
     auto k = xlines_kernel<LM, LINES, false>;
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, My, tw, lamx, lamy, lamxf, lamyf,
-                                                            cutoff, norm);
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx,
+                                                            lamy, lamxf, lamyf, cutoff, norm);
   }
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
@@ -466,13 +473,22 @@ int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, i
   return 0;
 }
 // lm_x = log2(Nx)
+int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int lnloc,
+                        size_t line_begin, size_t nlines, int My, const float2* tw,
+                        const double* lamx, const double* lamy, const float* lamxf,
+                        const float* lamyf, int fastd, double cutoff, float norm) {
+  CFD_DISPATCH_LM(lm_x, 4, 14,
+                  return launch_xlines_t<LM_>(st, peers, lnloc, line_begin, nlines, My, tw, lamx, lamy,
+                                              lamxf, lamyf, fastd, cutoff, norm));
+  return 0;
+}
 int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
                   int fastd, double cutoff, float norm) {
-  CFD_DISPATCH_LM(lm_x, 4, 14,
-                  return launch_xlines_t<LM_>(st, T, batch, My, tw, lamx, lamy, lamxf, lamyf, fastd,
-                                              cutoff, norm));
-  return 0;
+  LinePeers peers;
+  for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
+  return launch_xlines_peers(st, lm_x, peers, lm_x, 0, (size_t)batch * My, My, tw, lamx, lamy, lamxf,
+                             lamyf, fastd, cutoff, norm);
 }
 int launch_irfft_correct(cudaStream_t st, int lm_row, const float2* T, const float* us,
                          const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
@@ -500,11 +516,13 @@ int launch_irfft_rows(cudaStream_t st, int lm_row, const float2* T, float* q, in
   CFD_DISPATCH_LM(lm_row, 4, 14, return launch_irfft_rows_t<LM_>(st, T, q, batch, Nx, tw, rtw));
   return 0;
 }
-int launch_correct_2d(cudaStream_t st, const float* us, const float* vs, const float* q, float* uo,
-                      float* vo, int batch, int Nx, int Ny, float inv_hx, float inv_hy) {
+int launch_correct_2d(cudaStream_t st, const float* us, const float* vs, const float* q,
+                      const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
+                      float inv_hx, float inv_hy) {
   const int threads = 128;
   dim3 grid((Ny / 4 + threads - 1) / threads, Nx, batch);
-  correct2d_kernel<<<grid, threads, 0, st>>>(us, vs, q, uo, vo, Nx, Ny, inv_hx, inv_hy);
+  correct2d_kernel<<<grid, threads, 0, st>>>(us, vs, q, qnext ? qnext : q, uo, vo, Nx, Ny, inv_hx,
+                                             inv_hy);
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;

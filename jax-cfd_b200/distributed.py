@@ -1,0 +1,120 @@
+"""Slab-decomposed multi-GPU stepping (one process per GPU), SURVEY.md section 8(e).
+
+The reference has no distributed solver; this module is the host side of the new path.  Each rank
+owns `grid.shape[0] / world` rows of every field.  All data movement between GPUs happens inside
+the CUDA kernels over NVLink (csrc/multi_gpu.cu); the host only exchanges one 64-byte CUDA-IPC
+handle per rank at start-up -- `exchange` is any all-gather of bytes (default:
+torch.distributed.all_gather_object, plumbing only).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _engine
+from . import _lib
+from . import grids
+from ._lib import check, lib
+
+
+def slab_rows(nx: int, rank: int, world: int) -> Tuple[int, int]:
+  """[start, stop) of the rows owned by `rank` (axis 0 split evenly)."""
+  if nx % world:
+    raise ValueError(f'axis 0 ({nx}) is not divisible by the number of ranks ({world})')
+  n = nx // world
+  return rank * n, (rank + 1) * n
+
+
+def line_range(ny: int, rank: int, world: int) -> Tuple[int, int]:
+  """[start, stop) of the packed ky lines (Ny/2 of them) whose x-direction transform `rank` owns."""
+  my = ny // 2
+  if my % world:
+    raise ValueError(f'Ny/2 ({my}) is not divisible by the number of ranks ({world})')
+  n = my // world
+  return rank * n, (rank + 1) * n
+
+
+def check_decomposition(shape: Sequence[int], world: int) -> None:
+  """The constraints cfd_dist_plan_create enforces, checked on the host (same messages)."""
+  nx, ny = shape
+  if world not in (1, 2, 4, 8):
+    raise ValueError('world size must be 1, 2, 4 or 8')
+  nloc = nx // world
+  if nx % world or nloc < 16 or nloc & (nloc - 1):
+    raise ValueError('local slab must be a power of two >= 16 rows')
+  if (ny // 2) % world or (ny // 2 // world) % 16:
+    raise ValueError('Ny/2 lines must split evenly over the ranks')
+  if nx > (1 << 14):
+    raise NotImplementedError('global axis 0 longer than 16384 is not supported yet')
+
+
+def torch_exchange(blob: bytes) -> List[bytes]:
+  import torch.distributed as dist  # plumbing: bootstrap only
+  out = [None] * dist.get_world_size()
+  dist.all_gather_object(out, blob)
+  return out
+
+
+class SlabStepper:
+  """Distributed counterpart of `funcutils.repeated(equations.semi_implicit_navier_stokes(...))`."""
+
+  def __init__(self, grid: grids.Grid, dt: float, density: float, viscosity: Optional[float],
+               forcing=None, *, rank: int, world: int, device: int,
+               exchange: Callable[[bytes], List[bytes]] = torch_exchange):
+    if grid.ndim != 2:
+      raise NotImplementedError('slab decomposition is implemented for 2-D grids')
+    check_decomposition(grid.shape, world)
+    _lib.require_device()
+    self.grid, self.rank, self.world, self.device = grid, rank, world, device
+    self.rows = slab_rows(grid.shape[0], rank, world)
+    self.local_shape = (self.rows[1] - self.rows[0], grid.shape[1])
+    check(lib().cfd_set_device(device))
+    shape = (ctypes.c_int64 * 2)(*grid.shape)
+    step = (ctypes.c_double * 2)(*grid.step)
+    self.handle = ctypes.c_void_p()
+    check(lib().cfd_dist_plan_create(ctypes.byref(self.handle), shape, step, rank, world, device))
+    nb = lib().cfd_dist_handle_bytes()
+    blob = ctypes.create_string_buffer(nb)
+    check(lib().cfd_dist_export(self.handle, blob))
+    blobs = exchange(bytes(blob.raw))
+    assert len(blobs) == world and all(len(b) == nb for b in blobs)
+    allb = ctypes.create_string_buffer(b''.join(blobs), nb * world)
+    check(lib().cfd_dist_connect(self.handle, allb))
+    local_grid = grids.Grid(self.local_shape, domain=(
+        (grid.domain[0][0] + self.rows[0] * grid.step[0], grid.domain[0][0] + self.rows[1] * grid.step[0]),
+        grid.domain[1]))
+    del local_grid
+    self.params, self._keep = _engine.make_params(grid, dt, density, viscosity,
+                                                  _engine.as_forcing(forcing))
+    self.stream = _lib.Stream()
+
+  def load(self, v_local):
+    """v_local: the rank's rows of (u, v): numpy or device arrays of shape local_shape."""
+    arrs = [a if _lib.is_device_array(a) else _lib.DeviceArray.from_numpy(np.ascontiguousarray(a, np.float32))
+            for a in v_local]
+    for a in arrs:
+      assert tuple(a.shape) == self.local_shape, (a.shape, self.local_shape)
+    check(lib().cfd_dist_load(self.handle, self.stream.handle, _lib.ptr_array(arrs)))
+    self.stream.sync()
+
+  def advance(self, nsteps: int):
+    check(lib().cfd_dist_advance(self.handle, self.stream.handle, nsteps, ctypes.byref(self.params)))
+
+  def store(self, want_q: bool = False):
+    outs = [_lib.DeviceArray(self.local_shape) for _ in range(2)]
+    q = _lib.DeviceArray(self.local_shape) if want_q else None
+    check(lib().cfd_dist_store(self.handle, self.stream.handle, _lib.ptr_array(outs),
+                               None if q is None else q.ptr))
+    self.stream.sync()
+    check(lib().cfd_dist_check(self.handle))
+    return (outs, q) if want_q else outs
+
+  def sync(self):
+    self.stream.sync()
+
+  def close(self):
+    if self.handle:
+      lib().cfd_plan_destroy(self.handle)
+      self.handle = None

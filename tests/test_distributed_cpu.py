@@ -1,0 +1,58 @@
+"""Host-side logic of the slab decomposition, including a world_size-2 gloo run (CPU only)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import jax_cfd_b200 as cfd
+from jax_cfd_b200 import distributed as D
+
+
+def test_partition_arithmetic():
+  assert D.slab_rows(8192, 0, 8) == (0, 1024) and D.slab_rows(8192, 7, 8) == (7168, 8192)
+  assert D.line_range(8192, 3, 4) == (3072, 4096)
+  rows = [D.slab_rows(256, r, 4) for r in range(4)]
+  assert rows[0][0] == 0 and rows[-1][1] == 256 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+  with pytest.raises(ValueError):
+    D.slab_rows(100, 0, 8)
+  D.check_decomposition((8192, 8192), 8)
+  D.check_decomposition((16384, 8192), 2)
+  with pytest.raises(ValueError):
+    D.check_decomposition((64, 64), 8)       # 8 rows per rank
+  with pytest.raises(ValueError):
+    D.check_decomposition((8192, 64), 4)     # 8 lines per rank
+  with pytest.raises(NotImplementedError):
+    D.check_decomposition((32768, 32768), 8)
+
+
+def _worker(rank, world, port, q):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  import torch.distributed as dist
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  blob = bytes([rank]) * 64
+  blobs = D.torch_exchange(blob)
+  ok = blobs == [bytes([r]) * 64 for r in range(world)]
+  # every rank derives a consistent, disjoint cover of rows and lines
+  rows = D.slab_rows(256, rank, world)
+  lines = D.line_range(512, rank, world)
+  allr = [None] * world
+  dist.all_gather_object(allr, (rows, lines))
+  ok = ok and sorted(r for r, _ in allr) == [D.slab_rows(256, r, world) for r in range(world)]
+  ok = ok and sum(l[1] - l[0] for _, l in allr) == 256
+  q.put((rank, ok))
+  dist.destroy_process_group()
+
+
+def test_handle_exchange_world2_gloo():
+  import torch.multiprocessing as mp
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = 29500 + (os.getpid() % 400)
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=120) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+  assert sorted(res) == [(0, True), (1, True)]

@@ -274,3 +274,27 @@ def test_step_3d_matches_oracle(cfd, shape, cs):
   wd = cfd_oracle.diagnostics(to_np(got), grid.step)
   assert abs(d['kinetic_energy'] - wd['kinetic_energy']) < 1e-6 * wd['kinetic_energy']
   assert abs(d['max_speed_sq'] - wd['max_speed_sq']) < 1e-6 * wd['max_speed_sq']
+
+
+def test_slab_stepper_world1_equals_single_gpu_path(cfd):
+  """The distributed code path (slab sources, peer-aware x lines, correct with q-next) with one
+  rank must reproduce the ordinary path bit for bit."""
+  shape = (128, 256)
+  dom = ((0.0, 2 * np.pi), (0.0, 2 * np.pi))
+  grid = cfd.grids.Grid(shape, domain=dom)
+  v0 = cfd_oracle.filtered_velocity_field(3, shape, dom, 3.0, 3)
+  dt = 0.5 * min(grid.step) / 3.0
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  st = cfd.distributed.SlabStepper(grid, dt, 1.0, 1e-3, forcing, rank=0, world=1, device=0,
+                                   exchange=lambda b: [b])
+  st.load(list(v0))
+  st.advance(3)
+  st.advance(2)
+  outs, q = st.store(want_q=True)
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, dt, grid, forcing=forcing)
+  ref, rq = step.advance(wrap(cfd, grid, v0), 5, return_q=True)
+  for a, b in zip(outs, to_np(ref)):
+    np.testing.assert_array_equal(a.numpy(), b)
+  np.testing.assert_array_equal(q.numpy(), np.asarray(rq))
+  st.close()
