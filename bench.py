@@ -161,12 +161,144 @@ def run_reference(args, wl, name):
   print(json.dumps(line), flush=True)
 
 
+# weak scaling of the slab-decomposed path: 8192^2 cells per GPU (x lines <= 16384 points for now)
+SLAB_SHAPES = {1: (8192, 8192), 2: (16384, 8192), 4: (16384, 16384), 8: (16384, 32768)}
+
+
+def analytic_ic(shape, rows, vmax):
+  """Smooth, globally consistent, nearly divergence-free field evaluated on a slab of rows
+  (sum of Taylor-Green-like modes on the staggered grid); cheap at any size."""
+  nx, ny = shape
+  r0, r1 = rows
+  x = (np.arange(r0, r1, dtype=np.float64) + 1.0) * (TWO_PI / nx)      # u: offset (1, .5)
+  xc = (np.arange(r0, r1, dtype=np.float64) + 0.5) * (TWO_PI / nx)
+  y = (np.arange(ny, dtype=np.float64) + 1.0) * (TWO_PI / ny)          # v: offset (.5, 1)
+  yc = (np.arange(ny, dtype=np.float64) + 0.5) * (TWO_PI / ny)
+  u = np.zeros((r1 - r0, ny))
+  v = np.zeros((r1 - r0, ny))
+  for a, b, amp in ((3, 4, 1.0), (5, 2, 0.6), (7, 9, 0.4), (11, 6, 0.25)):
+    u += amp * b * np.sin(a * x)[:, None] * np.cos(b * yc)[None, :] / max(a, b)
+    v -= amp * a * np.cos(a * xc)[:, None] * np.sin(b * y)[None, :] / max(a, b)
+  scale = vmax / 2.3
+  return (u * scale).astype(np.float32), (v * scale).astype(np.float32)
+
+
+def run_gpu_slab(args, wl, name):
+  """N > 1: one rank per GPU, slab decomposition along axis 0 (jax_cfd_b200.distributed)."""
+  import ctypes
+  import torch
+  import torch.distributed as dist
+  import jax_cfd_b200 as cfd
+  from jax_cfd_b200 import _lib
+  rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+  local_rank = int(os.environ.get('LOCAL_RANK', rank))
+  torch.cuda.set_device(local_rank)
+  dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  lib = _lib.lib()
+  _lib.check(lib.cfd_set_device(local_rank))
+  shape = SLAB_SHAPES[world]
+  grid = cfd.grids.Grid(shape, domain=((0.0, TWO_PI * shape[0] / 8192.0), (0.0, TWO_PI * shape[1] / 8192.0)))
+  dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  st = cfd.distributed.SlabStepper(grid, dt, 1.0, wl['nu'], forcing, rank=rank, world=world,
+                                   device=local_rank)
+  u0, v0 = analytic_ic(shape, st.rows, wl['vmax'])
+  st.load([u0, v0])
+  cells_local = int(np.prod(st.local_shape))
+
+  def barrier():
+    st.sync()
+    _lib.check(lib.cfd_device_sync())
+    dist.barrier()
+
+  st.advance(args.warmup)
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+    time.sleep(0.25)
+  e0, e1 = _lib.Event(), _lib.Event()
+  launches0 = lib.cfd_launch_count()
+  barrier()
+  e0.record(st.stream.handle)
+  st.advance(args.steps)
+  e1.record(st.stream.handle)
+  barrier()
+  ms_total = e0.elapsed_ms(e1)
+  launches = lib.cfd_launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  t = torch.tensor([ms_total], device='cuda')
+  dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total = float(t.item())
+  outs = st.store()
+  loc = outs[0].numpy()
+  # e2e at N GPUs: every step copies the rank's slab host->device, steps once, copies it back
+  hu, hv = outs[0].numpy(), outs[1].numpy()
+  e2e_steps = 3
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    st.load([hu, hv])
+    st.advance(1)
+    o = st.store()
+    hu, hv = o[0].numpy(), o[1].numpy()
+  barrier()
+  e2e_s = time.perf_counter() - t0
+  te = torch.tensor([e2e_s], device='cuda')
+  dist.all_reduce(te, op=dist.ReduceOp.MAX)
+  e2e_s = float(te.item())
+  finite = bool(np.isfinite(loc).all())
+  umax = float(np.abs(loc).max())
+  t2 = torch.tensor([0.0 if finite else 1.0], device='cuda')
+  dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+  assert float(t2.item()) == 0.0, 'non-finite state after the timed steps'
+  if rank == 0:
+    peak, peak_src = peaks()
+    ms_step = ms_total / args.steps
+    cells = cells_local * world
+    value = cells * args.steps / (ms_total * 1e-3) / 1e9
+    step_gbs = STEP_BYTES_PER_CELL * cells_local / (ms_step * 1e-3) / 1e9
+    # NVLink bytes per rank per step: x-line kernel reads and writes (world-1)/world of its lines
+    nvl = 2 * (shape[1] // 2 // world) * shape[0] * 8 * (world - 1) / world
+    line = {
+        'metric': 'cell-updates/sec', 'value': value, 'unit': 'Gcell*step/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': f'{name}-slab', 'description': wl['desc'] + f' -- weak-scaled to {shape[0]}x{shape[1]}',
+                   'grid': list(shape), 'cells_per_gpu': cells_local,
+                   'l2_policy': 'per-GPU working set (9 fields x 268 MB) larger than L2 (126 MB)',
+                   'parallelism': f'slab decomposition along axis 0 over {world} GPUs; halo rows and the FFT '
+                                  'all-to-all are peer loads/stores inside the kernels (CUDA IPC over NVLink), '
+                                  'device-side flag barriers, no NCCL on the data path'},
+        'roofline': {'bound': 'hbm', 'kernel': 'whole step (per GPU)', 'achieved': step_gbs, 'peak': peak,
+                     'unit': 'GB/s', 'frac': step_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                     'bytes_per_cell_model': STEP_BYTES_PER_CELL},
+        'nvlink': {'bytes_per_gpu_per_step_each_direction': nvl,
+                   'lower_bound_ms_at_770GBs': nvl / 770e9 * 1e3},
+        'cpu_baseline': None,
+        'e2e': {'value': cells * e2e_steps / e2e_s / 1e9, 'unit': 'Gcell*step/s',
+                'h2d_bytes_per_step': 2 * cells * 4, 'd2h_bytes_per_step': 2 * cells * 4,
+                'steps': e2e_steps, 'ms_per_step': e2e_s / e2e_steps * 1e3,
+                'api': 'SlabStepper.load(numpy) / advance(1) / store() -> numpy on every rank'},
+        'gpu_launches': int(launches), 'clocks': clocks,
+        'diagnostics_after': {'finite': finite, 'max_abs_u_rank0': umax},
+    }
+    print(json.dumps(line), flush=True)
+  dist.barrier()
+  st.close()
+  dist.destroy_process_group()
+
+
 def run_gpu(args, wl, name):
   import jax_cfd_b200 as cfd
   from jax_cfd_b200 import _lib
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1 and name == 'K8192':
+    return run_gpu_slab(args, wl, name)
   dist = None
   if world > 1:
     import torch
