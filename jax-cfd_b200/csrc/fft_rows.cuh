@@ -39,6 +39,18 @@ constexpr int lines_for(int LM) {
   return lines;
 }
 
+// points per thread (log2) of the x-line kernel: 16 by default; CFD_XLINES_LE=5 selects 32 points
+// per thread (radix-32 passes, fewer exchanges, half the threads per line).
+inline int xlines_lemax(int lm) {
+  static const int forced = [] {
+    const char* e = getenv("CFD_XLINES_LE");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 4 || forced == 5) return forced;
+  (void)lm;
+  return 4;  // 32 points per thread measured no faster (register pressure); kept as an option
+}
+
 static int rows_shift() {  // tuning knob: CFD_FFT_ROWS_SHIFT=k uses rows_for(LM) >> k rows per CTA
   static const int v = [] {
     const char* e = getenv("CFD_FFT_ROWS_SHIFT");

@@ -128,19 +128,64 @@ struct Dft<16, DIR> {
   static __device__ __forceinline__ void run(float2 (&a)[16]) { dft16<DIR>(a); }
 };
 
+template <int DIR>
+__device__ __forceinline__ void dft32(float2 (&a)[32]) {
+  float2 e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    e[i] = a[2 * i];
+    o[i] = a[2 * i + 1];
+  }
+  dft16<DIR>(e);
+  dft16<DIR>(o);
+  // forward twiddles exp(-2 pi i k / 32), k = 1..15
+  constexpr float c1 = 0.98078528040323044913f, s1 = 0.19509032201612826785f;
+  constexpr float c2 = 0.92387953251128675613f, s2 = 0.38268343236508977173f;
+  constexpr float c3 = 0.83146961230254523708f, s3 = 0.55557023301960222474f;
+  constexpr float h = 0.70710678118654752440f;
+  o[1] = twmul<DIR>(o[1], make_float2(c1, -s1));
+  o[2] = twmul<DIR>(o[2], make_float2(c2, -s2));
+  o[3] = twmul<DIR>(o[3], make_float2(c3, -s3));
+  o[4] = twmul<DIR>(o[4], make_float2(h, -h));
+  o[5] = twmul<DIR>(o[5], make_float2(s3, -c3));
+  o[6] = twmul<DIR>(o[6], make_float2(s2, -c2));
+  o[7] = twmul<DIR>(o[7], make_float2(s1, -c1));
+  o[8] = mul_dir_i<DIR>(o[8]);
+  o[9] = twmul<DIR>(o[9], make_float2(-s1, -c1));
+  o[10] = twmul<DIR>(o[10], make_float2(-s2, -c2));
+  o[11] = twmul<DIR>(o[11], make_float2(-s3, -c3));
+  o[12] = twmul<DIR>(o[12], make_float2(-h, -h));
+  o[13] = twmul<DIR>(o[13], make_float2(-c3, -s3));
+  o[14] = twmul<DIR>(o[14], make_float2(-c2, -s2));
+  o[15] = twmul<DIR>(o[15], make_float2(-c1, -s1));
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    a[k] = cadd(e[k], o[k]);
+    a[k + 16] = csub(e[k], o[k]);
+  }
+}
+
+template <int DIR>
+struct Dft<32, DIR> {
+  static __device__ __forceinline__ void run(float2 (&a)[32]) { dft32<DIR>(a); }
+};
+
 // ---- radix plan -------------------------------------------------------------------------------
-// M = 2^LM points, E = min(16, M) points per thread.  Passes use radix 16 while possible and one
-// final smaller radix.  Forward and inverse share the pass order and the twiddle table (the
-// inverse conjugates).  Every transform starts from registers v[e] = x[t + G*e] and ends with
-// v[slot] = X[t + G*slot], so a forward transform can be scaled in registers and fed straight
-// into an inverse transform without an exchange.
-template <int LM>
+// M = 2^LM points, E = min(2^LEMAX, M) points per thread (LEMAX = 4: 16 points, radix-16 passes;
+// LEMAX = 5: 32 points, radix-32 passes -- fewer exchanges and half the threads per line).
+// Passes use the largest radix while possible and one final smaller radix.  Forward and inverse
+// share the pass order and the twiddle table (the inverse conjugates).  Every transform starts from
+// registers v[e] = x[t + G*e] and ends with v[slot] = X[t + G*slot], so a forward transform can be
+// scaled in registers and fed straight into an inverse transform without an exchange.
+template <int LM, int LEMAX = 4>
 struct FftPlan {
   static constexpr int M = 1 << LM;
-  static constexpr int E = M < 16 ? M : 16;
+  static constexpr int LE = LM < LEMAX ? LM : LEMAX;
+  static constexpr int E = 1 << LE;
   static constexpr int G = M / E;  // threads per line
-  static constexpr int LE = LM < 4 ? LM : 4;
   static constexpr int NP = (LM + LE - 1) / LE;  // passes
+  static constexpr int LPAD = LE < 4 ? 4 : LE;   // one padding slot per 2^LPAD points
+  __host__ __device__ static constexpr int pad(int i) { return i + (i >> LPAD); }
   // log2 radix of forward pass p
   __host__ __device__ static constexpr int lr_fwd(int p) {
     return (p < LM / LE) ? LE : (LM - (LM / LE) * LE);
@@ -161,10 +206,9 @@ struct FftPlan {
 
 // One radix pass on the E register-resident points of thread t.
 //   v[e] holds x[t + G*e] on entry; on exit v[q + r*NB] holds output r of butterfly j = t + G*q.
-template <int LM, int LR, int LNS, int DIR>
-__device__ __forceinline__ void fft_pass_compute(float2 (&v)[FftPlan<LM>::E], int t,
+template <class P, int LR, int LNS, int DIR>
+__device__ __forceinline__ void fft_pass_compute(float2 (&v)[P::E], int t,
                                                  const float2* __restrict__ tw) {
-  using P = FftPlan<LM>;
   constexpr int R = 1 << LR, NB = P::E / R, NS = 1 << LNS;
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
@@ -183,9 +227,8 @@ __device__ __forceinline__ void fft_pass_compute(float2 (&v)[FftPlan<LM>::E], in
 }
 
 // Scatter the outputs of a pass to their Stockham positions in the (padded) line buffer.
-template <int LM, int LR, int LNS>
-__device__ __forceinline__ void fft_pass_store(const float2 (&v)[FftPlan<LM>::E], int t, float2* s) {
-  using P = FftPlan<LM>;
+template <class P, int LR, int LNS>
+__device__ __forceinline__ void fft_pass_store(const float2 (&v)[P::E], int t, float2* s) {
   constexpr int R = 1 << LR, NB = P::E / R, NS = 1 << LNS;
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
@@ -193,32 +236,22 @@ __device__ __forceinline__ void fft_pass_store(const float2 (&v)[FftPlan<LM>::E]
     const int k = j & (NS - 1);
     const int base = ((j - k) << LR) + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) s[PAD(base + r * NS)] = v[q + r * NB];
+    for (int r = 0; r < R; ++r) s[P::pad(base + r * NS)] = v[q + r * NB];
   }
 }
 
-template <int LM>
-__device__ __forceinline__ void fft_load_regs(float2 (&v)[FftPlan<LM>::E], int t, const float2* s) {
-  using P = FftPlan<LM>;
+template <class P>
+__device__ __forceinline__ void fft_load_regs(float2 (&v)[P::E], int t, const float2* s) {
 #pragma unroll
-  for (int e = 0; e < P::E; ++e) v[e] = s[PAD(t + P::G * e)];
+  for (int e = 0; e < P::E; ++e) v[e] = s[P::pad(t + P::G * e)];
 }
 
-// Logical index (frequency for a finished forward transform / sample for a finished inverse) held
-// in v[slot] after the LAST pass: the last pass has Ns = M / R so output r of butterfly j sits at
-// j + r * Ns = t + G*q + r*(M/R) = t + G*(q + r*NB): slot q + r*NB  <->  index t + G*slot.
-template <int LM>
-__device__ __forceinline__ int fft_final_index(int t, int slot) {
-  return t + FftPlan<LM>::G * slot;
-}
-
-// Full transforms.  `SYNC` is a functor synchronising the G threads that own the line (all
-// threads of the CTA call these functions in lock-step, so __syncthreads is always valid).
-// Forward: data taken from registers v (x[t + G e]); result left in registers, natural index
-// t + G*slot.   Exchanges through `s`.
-template <int LM, int DIR, int P0 = 0>
+// Full transforms (all threads of the CTA call these in lock-step, so __syncthreads is valid).
+// Data is taken from registers v (x[t + G e]); the result is left in registers with natural index
+// t + G*slot: the last pass has Ns = M / R, so output r of butterfly j = t + G*q sits at
+// j + r*Ns = t + G*(q + r*NB).  Exchanges go through the padded line buffer `s`.
+template <class P, int DIR>
 struct FftRun {
-  using P = FftPlan<LM>;
   template <int PASS>
   static __device__ __forceinline__ void passes(float2 (&v)[P::E], int t, float2* s,
                                                 const float2* __restrict__ tw) {
@@ -226,12 +259,12 @@ struct FftRun {
       constexpr int LR = P::lr_fwd(PASS);
       constexpr int LNS = P::lns_fwd(PASS);
       constexpr int OFF = P::tw_off_fwd(PASS);
-      fft_pass_compute<LM, LR, LNS, DIR>(v, t, tw + OFF);
+      fft_pass_compute<P, LR, LNS, DIR>(v, t, tw + OFF);
       if constexpr (PASS + 1 < P::NP) {
         __syncthreads();  // all reads of the previous layout are done
-        fft_pass_store<LM, LR, LNS>(v, t, s);
+        fft_pass_store<P, LR, LNS>(v, t, s);
         __syncthreads();
-        fft_load_regs<LM>(v, t, s);
+        fft_load_regs<P>(v, t, s);
         passes<PASS + 1>(v, t, s, tw);
       }
     }

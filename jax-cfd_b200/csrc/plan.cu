@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "fft_smem.cuh"
+#include "fft_rows.cuh"
 
 namespace cfd {
 
@@ -85,8 +86,8 @@ static int ilog2(int64_t n) {
 static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 
 // Twiddle table for a 2^lm-point transform, same pass structure as FftPlan<LM>.
-static std::vector<float2> build_twiddles(int lm) {
-  const int le = lm < 4 ? lm : 4;
+static std::vector<float2> build_twiddles(int lm, int lemax = 4) {
+  const int le = lm < lemax ? lm : lemax;
   const int np = (lm + le - 1) / le;
   std::vector<float2> tw;
   int lns = 0;
@@ -183,7 +184,7 @@ int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double
   p->lam[0] = nullptr;
   p->lamf[0] = nullptr;
   p->lm_x = ilog2(Nxg);
-  int err = upload(&p->tw_x, build_twiddles(p->lm_x));
+  int err = upload(&p->tw_x, build_twiddles(p->lm_x, xlines_lemax(p->lm_x)));
   std::vector<double> lam(Nxg);
   for (int k = 0; k < Nxg; ++k)
     lam[k] = (2.0 * cos(2.0 * M_PI * (double)k / (double)Nxg) - 2.0) / (step[0] * step[0]);
@@ -343,7 +344,7 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   p->lm_x = ilog2(Nx);
   int err = 0;
   err |= upload(&p->tw_row, build_twiddles(p->lm_row));
-  err |= upload(&p->tw_x, build_twiddles(p->lm_x));
+  err |= upload(&p->tw_x, build_twiddles(p->lm_x, ndim == 2 ? xlines_lemax(p->lm_x) : 4));
   if (ndim == 3) {
     p->lm_y = ilog2(shape[1]);
     err |= upload(&p->tw_y, build_twiddles(p->lm_y));

@@ -49,7 +49,7 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = __ldg(src + t + G * e);
   }
-  FftRun<LM, -1>::run(v, t, s, tw);
+  FftRun<P, -1>::run(v, t, s, tw);
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
@@ -89,13 +89,13 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
 // rank (x >> lnloc)'s buffer at [line][x & (Nloc-1)] -- so the loads/stores below ARE the
 // all-to-all transpose of the distributed FFT, done with peer accesses over NVLink inside the
 // kernel (each rank transforms its own range of ky lines).  One GPU: a single peer, Nloc = M.
-template <int LM, int LINES, bool FASTD>
-__global__ void __launch_bounds__(LINES * FftPlan<LM>::G)
+template <int LM, int LINES, bool FASTD, int LEMAX>
+__global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX>::G, (LEMAX == 5 && LINES * FftPlan<LM, LEMAX>::G <= 256) ? 2 : 1)
 xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
               const float* __restrict__ lamyf, double cutoff, float norm) {
-  using P = FftPlan<LM>;
+  using P = FftPlan<LM, LEMAX>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, 16);
   extern __shared__ float2 smem[];
@@ -107,12 +107,23 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   float2* s = smem + ln * RS;
   const int nloc_mask = (1 << lnloc) - 1;
   const size_t loff = line << lnloc;  // this line's offset inside every rank's buffer
-  auto elem = [&](int x) -> float2* { return peers.p[x >> lnloc] + loff + (x & nloc_mask); };
+  // One GPU (lnloc == LM): plain contiguous line.  Several GPUs: peer table in shared memory (a
+  // dynamically indexed kernel parameter would live in local memory).
+  __shared__ float2* s_peer[CFD_MAX_PEERS];
+  const bool single = (lnloc == LM);
+  if (!single) {
+    if (tid < CFD_MAX_PEERS) s_peer[tid] = peers.p[tid];
+    __syncthreads();
+  }
+  float2* const Tl = peers.p[0] + loff;
+  auto elem = [&](int x) -> float2* {
+    return single ? Tl + x : s_peer[x >> lnloc] + loff + (x & nloc_mask);
+  };
 
   float2 v[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) v[e] = *elem(t + G * e);
-  FftRun<LM, -1>::run(v, t, s, tw);
+  FftRun<P, -1>::run(v, t, s, tw);
 
   const bool cta_has_packed = (line0 % My) == 0;  // only the first line of a CTA can be ky = 0
   if (!cta_has_packed || ky != 0) {
@@ -144,7 +155,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
     __syncthreads();
     if (ky == 0) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
+      for (int e = 0; e < E; ++e) s[P::pad(t + G * e)] = v[e];
     }
     __syncthreads();
     if (ky == 0) {
@@ -152,7 +163,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int kx = t + G * e;
-        const float2 cp = s[PAD((M - kx) & (M - 1))];
+        const float2 cp = s[P::pad((M - kx) & (M - 1))];
         const double lx = __ldg(lamx + kx);
         const double l0 = lx + ly0, lM = lx + lyM;
         const float d0 = (fabs(l0) > cutoff) ? 0.5f * norm * fast_rcp((float)l0) : 0.f;
@@ -164,7 +175,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
       }
     }
   }
-  FftRun<LM, +1>::run(v, t, s, tw);
+  FftRun<P, +1>::run(v, t, s, tw);
 #pragma unroll
   for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
 }
@@ -221,8 +232,8 @@ irfft_rows_correct_kernel(const float2* __restrict__ T, const float* __restrict_
   }
   __syncthreads();
   float2 v[E];
-  fft_load_regs<LM>(v, t, s);
-  FftRun<LM, +1>::run(v, t, s, tw);
+  fft_load_regs<P>(v, t, s);
+  FftRun<P, +1>::run(v, t, s, tw);
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];  // (q[2m], q[2m+1]) at PAD(m)
@@ -305,8 +316,8 @@ irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
   }
   __syncthreads();
   float2 v[E];
-  fft_load_regs<LM>(v, t, s);
-  FftRun<LM, +1>::run(v, t, s, tw);
+  fft_load_regs<P>(v, t, s);
+  FftRun<P, +1>::run(v, t, s, tw);
   // v[e] = (q[2m], q[2m+1]) with m = t + G*e: a warp writes 32 consecutive float2 = 256 B
   float2* dst = reinterpret_cast<float2*>(q + (b * Nx + x0 + row) * (size_t)(2 * M));
 #pragma unroll
@@ -390,21 +401,21 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
   return set_error_msg("grid axis 0 too small for the row FFT kernel (need >= 16)");
 }
 
-template <int LM>
-int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
-                    size_t nlines, int My, const float2* tw, const double* lamx, const double* lamy,
-                    const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
-  constexpr int LINES = lines_for(LM);
-  using P = FftPlan<LM>;
+template <int LM, int LEMAX>
+int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
+                     size_t nlines, int My, const float2* tw, const double* lamx, const double* lamy,
+                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
+  using P = FftPlan<LM, LEMAX>;
+  constexpr int LINES = (P::G >= 256) ? 1 : (256 / P::G > 16 ? 16 : 256 / P::G);
   constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
   if (nlines % LINES || line_begin % LINES) return set_error_msg("internal: line count not divisible");
   if (fastd) {
-    auto k = xlines_kernel<LM, LINES, true>;
+    auto k = xlines_kernel<LM, LINES, true, LEMAX>;
     if (int e = set_smem(k, smem)) return e;
     k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx,
                                                             lamy, lamxf, lamyf, cutoff, norm);
   } else {
-    auto k = xlines_kernel<LM, LINES, false>;
+    auto k = xlines_kernel<LM, LINES, false, LEMAX>;
     if (int e = set_smem(k, smem)) return e;
     k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx,
                                                             lamy, lamxf, lamyf, cutoff, norm);
@@ -412,6 +423,17 @@ int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t l
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int LM>
+int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
+                    size_t nlines, int My, const float2* tw, const double* lamx, const double* lamy,
+                    const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
+  if (xlines_lemax(LM) == 5)
+    return launch_xlines_le<LM, 5>(st, peers, lnloc, line_begin, nlines, My, tw, lamx, lamy, lamxf,
+                                   lamyf, fastd, cutoff, norm);
+  return launch_xlines_le<LM, 4>(st, peers, lnloc, line_begin, nlines, My, tw, lamx, lamy, lamxf,
+                                 lamyf, fastd, cutoff, norm);
 }
 
 template <int LM>

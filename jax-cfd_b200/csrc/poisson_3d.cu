@@ -38,7 +38,7 @@ rfft_rows3_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int NR,
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = __ldg(src + t + G * e);
   }
-  FftRun<LM, -1>::run(v, t, s, tw);
+  FftRun<P, -1>::run(v, t, s, tw);
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
@@ -112,8 +112,8 @@ irfft_rows3_kernel(const float2* __restrict__ T, float* __restrict__ q, int NR,
   }
   __syncthreads();
   float2 v[E];
-  fft_load_regs<LM>(v, t, s);
-  FftRun<LM, +1>::run(v, t, s, tw);
+  fft_load_regs<P>(v, t, s);
+  FftRun<P, +1>::run(v, t, s, tw);
   float2* dst = reinterpret_cast<float2*>(q + (b * NR + r0 + row) * (size_t)(2 * M));
 #pragma unroll
   for (int e = 0; e < E; ++e) dst[t + G * e] = v[e];
@@ -140,7 +140,7 @@ cfft_lines_scatter_kernel(const float2* __restrict__ A, float2* __restrict__ B, 
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = __ldg(src + t + G * e);
   }
-  FftRun<LM, -1>::run(v, t, s, tw);
+  FftRun<P, -1>::run(v, t, s, tw);
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
@@ -178,8 +178,8 @@ cfft_lines_gather_kernel(const float2* __restrict__ B, float2* __restrict__ A, i
   }
   __syncthreads();
   float2 v[E];
-  fft_load_regs<LM>(v, t, s);
-  FftRun<LM, +1>::run(v, t, s, tw);
+  fft_load_regs<P>(v, t, s);
+  FftRun<P, +1>::run(v, t, s, tw);
   float2* dst = A + (plane * NL + l0 + row) * (size_t)M;
 #pragma unroll
   for (int e = 0; e < E; ++e) dst[t + G * e] = v[e];
@@ -207,7 +207,7 @@ xlines3_kernel(float2* __restrict__ T, int N1, int NZP, const float2* __restrict
   float2 v[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) v[e] = Tl[t + G * e];
-  FftRun<LM, -1>::run(v, t, s, tw);
+  FftRun<P, -1>::run(v, t, s, tw);
   if (FASTD) {
     const float lyz = __ldg(lamyf + ky) + __ldg(lamzf + kz);
     const bool mean_line = (ky == 0) && (kz == 0);
@@ -229,7 +229,7 @@ xlines3_kernel(float2* __restrict__ T, int N1, int NZP, const float2* __restrict
       v[e].y *= d;
     }
   }
-  FftRun<LM, +1>::run(v, t, s, tw);
+  FftRun<P, +1>::run(v, t, s, tw);
 #pragma unroll
   for (int e = 0; e < E; ++e) Tl[t + G * e] = v[e];
 }
