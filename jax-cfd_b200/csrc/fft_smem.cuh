@@ -250,28 +250,46 @@ __device__ __forceinline__ void fft_load_regs(float2 (&v)[P::E], int t, const fl
 // Data is taken from registers v (x[t + G e]); the result is left in registers with natural index
 // t + G*slot: the last pass has Ns = M / R, so output r of butterfly j = t + G*q sits at
 // j + r*Ns = t + G*(q + r*NB).  Exchanges go through the padded line buffer `s`.
-template <class P, int DIR>
+// Synchronisation of the G threads that own one line.  SyncCta: the whole CTA (always valid when
+// every thread runs the same sequence).  SyncLine<G>: only the line's threads -- a warp-level sync
+// when a line fits in a warp, otherwise a named barrier (id = 1 + line index, at most 15 lines) --
+// so that the lines of a CTA drift apart and overlap each other's memory and compute phases.
+struct SyncCta {
+  static __device__ __forceinline__ void sync(int) { __syncthreads(); }
+};
+template <int G>
+struct SyncLine {
+  static __device__ __forceinline__ void sync(int line) {
+    if (G <= 32) {
+      __syncwarp();
+    } else {
+      asm volatile("bar.sync %0, %1;" ::"r"(line + 1), "n"(G) : "memory");
+    }
+  }
+};
+
+template <class P, int DIR, class SYNC = SyncCta>
 struct FftRun {
   template <int PASS>
   static __device__ __forceinline__ void passes(float2 (&v)[P::E], int t, float2* s,
-                                                const float2* __restrict__ tw) {
+                                                const float2* __restrict__ tw, int line) {
     if constexpr (PASS < P::NP) {
       constexpr int LR = P::lr_fwd(PASS);
       constexpr int LNS = P::lns_fwd(PASS);
       constexpr int OFF = P::tw_off_fwd(PASS);
       fft_pass_compute<P, LR, LNS, DIR>(v, t, tw + OFF);
       if constexpr (PASS + 1 < P::NP) {
-        __syncthreads();  // all reads of the previous layout are done
+        SYNC::sync(line);  // all reads of the previous layout are done
         fft_pass_store<P, LR, LNS>(v, t, s);
-        __syncthreads();
+        SYNC::sync(line);
         fft_load_regs<P>(v, t, s);
-        passes<PASS + 1>(v, t, s, tw);
+        passes<PASS + 1>(v, t, s, tw, line);
       }
     }
   }
   static __device__ __forceinline__ void run(float2 (&v)[P::E], int t, float2* s,
-                                             const float2* __restrict__ tw) {
-    passes<0>(v, t, s, tw);
+                                             const float2* __restrict__ tw, int line = 0) {
+    passes<0>(v, t, s, tw, line);
   }
 };
 

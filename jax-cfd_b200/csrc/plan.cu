@@ -325,8 +325,10 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   }
   if (shape[ndim - 1] < 32) return set_error_msg("last grid axis must be >= 32");
   if (shape[0] > (1 << 14)) return set_error_msg("axis 0 longer than 16384 is not supported yet");
-  if (shape[ndim - 1] > (1 << 14))
-    return set_error_msg("last axis longer than 16384 is not supported yet");
+  if (shape[ndim - 1] > (1 << 15))
+    return set_error_msg("last axis longer than 32768 is not supported yet");
+  for (int j = 1; j + 1 < ndim; ++j)
+    if (shape[j] > (1 << 14)) return set_error_msg("middle axis longer than 16384 is not supported yet");
   if (cfd_device_count() <= device) return set_error_msg("no such CUDA device (no CPU fallback)");
   CFD_CUDA_OK(cudaSetDevice(device));
   cfd_plan* p = new cfd_plan();

@@ -49,11 +49,12 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = __ldg(src + t + G * e);
   }
-  FftRun<P, -1>::run(v, t, s, tw);
-  __syncthreads();
+  using LSYNC = std::conditional_t<(ROWS <= 15), SyncLine<G>, SyncCta>;
+  FftRun<P, -1, LSYNC>::run(v, t, s, tw, row);
+  LSYNC::sync(row);
 #pragma unroll
   for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
-  __syncthreads();
+  LSYNC::sync(row);
   // split the half-size complex transform into the real-input spectrum (in place, pairs k, M-k)
   for (int k = t; k <= M / 2; k += G) {
     if (k == 0) {
@@ -314,10 +315,11 @@ irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
       s[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
     }
   }
-  __syncthreads();
+  using LSYNC = std::conditional_t<(ROWS <= 15), SyncLine<G>, SyncCta>;
+  LSYNC::sync(row);
   float2 v[E];
   fft_load_regs<P>(v, t, s);
-  FftRun<P, +1>::run(v, t, s, tw);
+  FftRun<P, +1, LSYNC>::run(v, t, s, tw, row);
   // v[e] = (q[2m], q[2m+1]) with m = t + G*e: a warp writes 32 consecutive float2 = 256 B
   float2* dst = reinterpret_cast<float2*>(q + (b * Nx + x0 + row) * (size_t)(2 * M));
 #pragma unroll
