@@ -32,10 +32,18 @@ WORKLOADS = {
                  desc='demo 2D Kolmogorov flow 256x256, float32'),
     'E1024': dict(shape=(256, 256), batch=1024, nu=1e-3, vmax=7.0, kolmogorov=True, kpeak=4,
                   desc='ensemble of 1024 Kolmogorov 256x256 trajectories, float32'),
+    'TGV512': dict(shape=(512, 512, 512), batch=1, nu=1.0 / 1600, vmax=1.0, kolmogorov=False, kpeak=2,
+                   smagorinsky=0.2,
+                   desc='3D periodic Taylor-Green vortex 512^3 with Smagorinsky closure (cs 0.2), float32'),
+    'TGV256': dict(shape=(256, 256, 256), batch=1, nu=1.0 / 1600, vmax=1.0, kolmogorov=False, kpeak=2,
+                   smagorinsky=0.2, desc='3D Taylor-Green vortex 256^3 with Smagorinsky closure, float32'),
 }
 # algorithmic HBM bytes per cell of each kernel (its inputs read once + outputs written once)
 KERNEL_BYTES = {'explicit_2d': 20.0, 'explicit_2d_lazy': 24.0, 'rfft_rows': 8.0, 'xlines': 8.0,
-                'irfft_rows': 8.0, 'correct': 20.0}
+                'irfft_rows': 8.0, 'correct': 20.0,
+                # 3-D (first implementation: unfused divergence / correction, five FFT sweeps)
+                'smag_nut': 16.0, 'explicit_3d': 28.0, 'divergence_3d': 16.0, 'rfft_z': 8.0, 'fft_y': 8.0,
+                'xlines3': 8.0, 'ifft_y': 8.0, 'irfft_z': 8.0, 'correct_3d': 28.0}
 CHAIN_KERNELS = ('explicit_2d_lazy', 'rfft_rows', 'xlines', 'irfft_rows')  # one chained step
 STEP_BYTES_PER_CELL = 40.0  # 2-D, working set > L2
 
@@ -310,15 +318,29 @@ def run_gpu(args, wl, name):
   _lib.require_device()
 
   shape, batch = wl['shape'], wl['batch']
-  grid = cfd.grids.Grid(shape, domain=((0.0, TWO_PI), (0.0, TWO_PI)))
+  ndim = len(shape)
+  if batch > 1 and world > 1:
+    batch = batch // world  # ensemble members are independent: shard the batch, no collective
+  grid = cfd.grids.Grid(shape, domain=((0.0, TWO_PI),) * ndim)
   dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
   forcing = None
   if wl['kolmogorov']:
     forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
                                         cfd.forcings.linear_forcing(grid, -0.1))
-  step = cfd.equations.semi_implicit_navier_stokes(1.0, wl['nu'], dt, grid, forcing=forcing)
-  bc = cfd.boundaries.periodic_boundary_conditions(2)
-  host = synth_ic(shape, batch, 1000 + rank, wl['vmax'], wl['kpeak'])
+  if wl.get('smagorinsky'):
+    step = cfd.subgrid_models.explicit_smagorinsky_navier_stokes(
+        dt=dt, cs=wl['smagorinsky'], forcing=forcing, density=1.0, viscosity=wl['nu'], grid=grid)
+  else:
+    step = cfd.equations.semi_implicit_navier_stokes(1.0, wl['nu'], dt, grid, forcing=forcing)
+  bc = cfd.boundaries.periodic_boundary_conditions(ndim)
+  if ndim == 3:
+    # Taylor-Green vortex sampled at the staggered offsets
+    ax = [grid.axes(o) for o in grid.cell_faces]
+    host = [(np.sin(ax[0][0])[:, None, None] * np.cos(ax[0][1])[None, :, None] * np.cos(ax[0][2])[None, None, :]).astype(np.float32),
+            (-np.cos(ax[1][0])[:, None, None] * np.sin(ax[1][1])[None, :, None] * np.cos(ax[1][2])[None, None, :]).astype(np.float32),
+            np.zeros(shape, np.float32)]
+  else:
+    host = synth_ic(shape, batch, 1000 + rank, wl['vmax'], wl['kpeak'])
   full = ((batch,) if batch > 1 else ()) + tuple(shape)
   cells = int(np.prod(full))
 
@@ -388,23 +410,30 @@ def run_gpu(args, wl, name):
     _lib.check(lib.cfd_step_profile(plan.handle, stream.handle, src, dst, ctypes.byref(params), 5, 8,
                                     ms, names, ctypes.byref(nk)))
     kern = {names[i].decode(): float(ms[i]) for i in range(nk.value)}
-    chain = {k: kern[k] for k in CHAIN_KERNELS if k in kern}
+    chain = {k: kern[k] for k in CHAIN_KERNELS if k in kern} or dict(kern)
     dom = max(chain, key=chain.get)
-    dom_bytes = KERNEL_BYTES[dom] * cells
+    dom_bytes = KERNEL_BYTES.get(dom, 0.0) * cells
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath):
+      tj = json.load(open(tpath))
+      if tj.get('workload') == name:
+        traffic = tj['bytes_per_launch'].get(dom)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': dom_bytes, 'kernel_ms': kern[dom],
                 'share_of_step': kern[dom] / sum(chain.values())}
-    step_gbs = STEP_BYTES_PER_CELL * cells / (ms_step * 1e-3) / 1e9
-    roofline_step = {'bound': 'hbm', 'bytes_per_cell_model': STEP_BYTES_PER_CELL,
+    bpc = 52.0 if ndim == 3 else (16.0 if cells * 4 * 7 <= 126e6 and batch > 1 else STEP_BYTES_PER_CELL)
+    step_gbs = bpc * cells / (ms_step * 1e-3) / 1e9
+    roofline_step = {'bound': 'hbm', 'bytes_per_cell_model': bpc,
                      'achieved': step_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': step_gbs / peak,
                      'kernel_ms': kern,
-                     'kernel_gbs': {k: KERNEL_BYTES[k] * cells / (t * 1e-3) / 1e9 for k, t in kern.items()}}
+                     'kernel_gbs': {k: KERNEL_BYTES.get(k, 0.0) * cells / (t * 1e-3) / 1e9 for k, t in kern.items()}}
 
     # e2e: public host-array API, pinned host buffers, H2D + D2H of the whole state every step
-    hin = [_lib.PinnedArray(full) for _ in range(2)]
-    hout = [_lib.PinnedArray(full) for _ in range(2)]
+    hin = [_lib.PinnedArray(full) for _ in range(ndim)]
+    hout = [_lib.PinnedArray(full) for _ in range(ndim)]
     for p, src_arr in zip(hin, host):
       p.array[...] = src_arr
     nb = cells * 4
@@ -421,12 +450,12 @@ def run_gpu(args, wl, name):
       hin, hout = hout, hin
     e2e_s = time.perf_counter() - t0
     e2e = {'value': cells * e2e_steps / e2e_s / 1e9, 'unit': 'Gcell*step/s',
-           'h2d_bytes_per_step': 2 * nb, 'd2h_bytes_per_step': 2 * nb, 'steps': e2e_steps,
+           'h2d_bytes_per_step': ndim * nb, 'd2h_bytes_per_step': ndim * nb, 'steps': e2e_steps,
            'ms_per_step': e2e_s / e2e_steps * 1e3,
            'api': 'cfd_step_host (C ABI, pinned numpy in/out) == step_fn on host arrays'}
     cb = None
     if not args.no_cpu_baseline:
-      cb, _ = cpu_reference(wl, 3, 1, sample_rows=min(shape[0], 2048))
+      cb, _ = cpu_reference(wl, 3, 1, sample_rows=min(shape[0], 2048)) if ndim == 2 else (None, None)
     line = {
         'metric': 'cell-updates/sec', 'value': value, 'unit': 'Gcell*step/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
@@ -435,7 +464,9 @@ def run_gpu(args, wl, name):
         'config': {'workload': name, 'description': wl['desc'], 'grid': list(shape), 'batch': batch,
                    'cells_per_gpu': cells, 'l2_policy': 'working set (7 fields x %.0f MB) %s L2 (126 MB)' % (
                        cells * 4 / 1e6, 'larger than' if cells * 4 * 7 > 126e6 else 'fits in'),
-                   'parallelism': 'single GPU' if world == 1 else f'{world} independent domain replicas'},
+                   'parallelism': 'single GPU' if world == 1 else (
+                       f'ensemble sharded over {world} GPUs ({batch} members each), no collective' if batch > 1
+                       else f'{world} independent domain replicas')},
         'roofline': roofline, 'roofline_step': roofline_step, 'cpu_baseline': cb, 'e2e': e2e,
         'gpu_launches': int(launches), 'clocks': clocks,
         'diagnostics_after': diag,

@@ -298,3 +298,52 @@ def test_slab_stepper_world1_equals_single_gpu_path(cfd):
     np.testing.assert_array_equal(a.numpy(), b)
   np.testing.assert_array_equal(q.numpy(), np.asarray(rq))
   st.close()
+
+
+def test_filtered_velocity_field_is_divergence_free_with_requested_speed(cfd):
+  """initial_conditions.py:71-121 ("next" row f3): projection + fused max-speed reduction."""
+  grid = cfd.grids.Grid((256, 256), domain=((0.0, 2 * np.pi), (0.0, 2 * np.pi)))
+  v = cfd.initial_conditions.filtered_velocity_field(0, grid, maximum_velocity=2.0, peak_wavenumber=3)
+  arrs = to_np(v)
+  speed = np.sqrt((arrs[0] ** 2 + arrs[1] ** 2).max())
+  assert abs(speed - 2.0) < 1e-3
+  assert np.abs(cfd_oracle.divergence(arrs, grid.step)).max() < 2e-3
+  for u, o in zip(v, grid.cell_faces):
+    assert u.offset == o and u.data.dtype == np.float32
+  # dynamic_time_step (equations.py:62-70) uses the same reduction
+  dt = cfd.equations.dynamic_time_step(v, 0.5, 1e-3, grid)
+  assert abs(dt - 0.5 * grid.step[0] / speed) < 1e-6
+
+
+def test_trajectory_on_device_matches_repeated(cfd):
+  """funcutils.trajectory (funcutils.py:95-126) with inner repeated steps, device-resident state."""
+  rec = gu.load('k2d_64x32')
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  step = build_step(cfd, rec, grid)
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(2)])
+  inner = cfd.funcutils.repeated(step, 5)
+  final, traj = cfd.funcutils.trajectory(inner, 2, post_process=lambda s: s)(v)
+  assert traj[0].data.shape == (2, 64, 32)
+  for i, a in enumerate(to_np(final)):
+    assert gu.rel_l2(a, rec[f'f32_v10_{i}']) < TOL * 5
+    np.testing.assert_array_equal(traj[i].data[-1], a)
+
+
+def test_rk4_3d_runs_and_stays_divergence_free(cfd):
+  """equations_test.py:101-128 style: RK stepper in 3-D, momentum and divergence invariants."""
+  shape = (32, 32, 32)
+  dom = ((0.0, 2 * np.pi),) * 3
+  grid = cfd.grids.Grid(shape, domain=dom)
+  v0 = cfd_oracle.filtered_velocity_field(5, shape, dom, 1.0, 2)
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-2, 0.02, grid,
+                                                   time_stepper=cfd.time_stepping.classic_rk4)
+  v = wrap(cfd, grid, v0)
+  for _ in range(3):
+    v = step(v)
+  want = v0
+  a, b = gu.TABLEAUS['classic_rk4']
+  for _ in range(3):
+    want = cfd_oracle.rk_step(want, 0.02, grid.step, a, b, 1.0, 1e-2, None)
+  for x, y in zip(to_np(v), want):
+    assert gu.rel_l2(x, y) < TOL
+  assert np.abs(cfd_oracle.divergence(to_np(v), grid.step)).max() < 1e-4
