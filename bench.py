@@ -28,6 +28,8 @@ WORKLOADS = {
                   desc='2D Kolmogorov flow 8192x8192 (scale 1, k 4, linear -0.1, nu 1e-4), float32'),
     'D2048': dict(shape=(2048, 2048), batch=1, nu=1e-3, vmax=2.0, kolmogorov=False, kpeak=3,
                   desc='2D decaying turbulence 2048x2048 periodic (nu 1e-3, vmax 2), float32'),
+    'K32768': dict(shape=(32768, 32768), batch=1, nu=1e-4, vmax=7.0, kolmogorov=True, kpeak=4,
+                   desc='2D Kolmogorov flow 32768x32768 slab-sharded (nu 1e-4, vmax 7), float32'),
     'K256': dict(shape=(256, 256), batch=1, nu=1e-3, vmax=7.0, kolmogorov=True, kpeak=4,
                  desc='demo 2D Kolmogorov flow 256x256, float32'),
     'E1024': dict(shape=(256, 256), batch=1024, nu=1e-3, vmax=7.0, kolmogorov=True, kpeak=4,
@@ -169,8 +171,10 @@ def run_reference(args, wl, name):
   print(json.dumps(line), flush=True)
 
 
-# weak scaling of the slab-decomposed path: 8192^2 cells per GPU (x lines <= 16384 points for now)
-SLAB_SHAPES = {1: (8192, 8192), 2: (16384, 8192), 4: (16384, 16384), 8: (16384, 32768)}
+# weak scaling of the slab-decomposed path: 8192^2 cells per GPU
+SLAB_SHAPES = {1: (8192, 8192), 2: (16384, 8192), 4: (32768, 8192), 8: (32768, 16384)}
+# the north-star multi-GPU configuration (BASELINE config #4): 32768^2 over the GPUs of the box
+SLAB_SHAPES_32K = {1: (32768, 32768), 2: (32768, 32768), 4: (32768, 32768), 8: (32768, 32768)}
 
 
 def analytic_ic(shape, rows, vmax):
@@ -198,13 +202,18 @@ def run_gpu_slab(args, wl, name):
   import torch.distributed as dist
   import jax_cfd_b200 as cfd
   from jax_cfd_b200 import _lib
-  rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+  rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
   local_rank = int(os.environ.get('LOCAL_RANK', rank))
   torch.cuda.set_device(local_rank)
-  dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  if world == 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29533')
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', local_rank))
+  else:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
   lib = _lib.lib()
   _lib.check(lib.cfd_set_device(local_rank))
-  shape = SLAB_SHAPES[world]
+  shape = (SLAB_SHAPES_32K if name == 'K32768' else SLAB_SHAPES)[world]
   grid = cfd.grids.Grid(shape, domain=((0.0, TWO_PI * shape[0] / 8192.0), (0.0, TWO_PI * shape[1] / 8192.0)))
   dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
   forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
@@ -305,7 +314,7 @@ def run_gpu(args, wl, name):
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-  if world > 1 and name == 'K8192':
+  if (world > 1 and name == 'K8192') or name == 'K32768':
     return run_gpu_slab(args, wl, name)
   dist = None
   if world > 1:

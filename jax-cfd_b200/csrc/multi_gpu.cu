@@ -27,7 +27,8 @@ int launch_irfft_rows(cudaStream_t, int lm_row, const float2* T, float* q, int b
 int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int lnloc,
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
-                        const float* lamyf, int fastd, double cutoff, float norm);
+                        const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
+                        const float2* wbig);
 int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
                       const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
                       float inv_hx, float inv_hy);
@@ -115,12 +116,14 @@ int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const doub
   const int64_t nloc = Nxg / world;
   if (nloc < 16 || (nloc & (nloc - 1))) return set_error_msg("local slab must be a power of two >= 16 rows");
   if ((Ny / 2) % world || (Ny / 2 / world) % 16) return set_error_msg("Ny/2 lines must split evenly over the ranks");
-  if (Nxg > (1 << 14)) return set_error_msg("global axis 0 longer than 16384 is not supported yet");
+  if (Nxg > (1 << 15)) return set_error_msg("global axis 0 longer than 32768 is not supported");
   // an ordinary plan for the LOCAL slab gives the row tables + local workspace ...
   int64_t local_shape[2] = {nloc, Ny};
   cfd_plan* p = nullptr;
   if (int e = cfd_plan_create(&p, 2, local_shape, step, 1, device)) return e;
   // ... then replace what depends on the GLOBAL x extent (x-line twiddles, eigenvalues, norm)
+  p->rank = rank;
+  p->world = world;
   if (int e = plan_tables_create(p, 2, global_shape, step)) {
     cfd_plan_destroy(p);
     return e;
@@ -229,7 +232,7 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
     if (int e = barrier(p, st)) return e;  // every rank's slab spectrum is complete
     if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
                                     lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1], p->lamf[0],
-                                    p->lamf[1], p->fastd, p->cutoff, p->norm))
+                                    p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig))
       return e;
     prof_mark(p, st, "xlines_peers");
     if (int e = barrier(p, st)) return e;  // every rank has written its lines back into my slab

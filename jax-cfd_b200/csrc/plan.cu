@@ -27,7 +27,7 @@ int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int 
                      const float2* tw, const float2* rtw);
 int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
-                  int fastd, double cutoff, float norm);
+                  int fastd, double cutoff, float norm, float2* scratch, const float2* wbig);
 int launch_irfft_correct(cudaStream_t, int lm_row, const float2* T, const float* us,
                          const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
                          const float2* tw, const float2* rtw, float inv_hx, float inv_hy);
@@ -175,6 +175,24 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
   return 0;
 }
 
+// 32768-point x lines: w_N^m table and the scratch of the split transform (nlines lines per launch)
+int big_line_tables(cfd_plan* p, size_t nlines) {
+  const int half = 1 << 14;
+  std::vector<float2> w(half);
+  for (int m = 0; m < half; ++m) {
+    const double ang = -2.0 * M_PI * (double)m / (double)(2 * half);
+    w[m] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  cudaFree(p->wbig);
+  cudaFree(p->xscratch);
+  p->wbig = nullptr;
+  p->xscratch = nullptr;
+  int err = upload(&p->wbig, w);
+  if (cudaMalloc((void**)&p->xscratch, nlines * (size_t)(2 * half) * sizeof(float2)) != cudaSuccess)
+    err |= set_error_msg("scratch allocation for 32768-point lines failed");
+  return err;
+}
+
 int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double* step) {
   const int Nxg = (int)shape[0];
   cudaFree(p->tw_x);
@@ -184,7 +202,8 @@ int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double
   p->lam[0] = nullptr;
   p->lamf[0] = nullptr;
   p->lm_x = ilog2(Nxg);
-  int err = upload(&p->tw_x, build_twiddles(p->lm_x, xlines_lemax(p->lm_x)));
+  int err = upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x, xlines_lemax(p->lm_x)));
+  if (p->lm_x == 15) err |= big_line_tables(p, (size_t)(shape[1] / 2) / (p->world > 0 ? p->world : 1));
   std::vector<double> lam(Nxg);
   for (int k = 0; k < Nxg; ++k)
     lam[k] = (2.0 * cos(2.0 * M_PI * (double)k / (double)Nxg) - 2.0) / (step[0] * step[0]);
@@ -219,7 +238,7 @@ int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
   if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw)) return e;
   prof_mark(p, st, "rfft_rows");
   if (int e = launch_xlines(st, p->lm_x, p->T, p->batch, Ny / 2, p->tw_x, p->lam[0], p->lam[1],
-                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm))
+                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig))
     return e;
   prof_mark(p, st, "xlines");
   if (int e = launch_irfft_rows(st, p->lm_row, p->T, q, p->batch, Nx, p->tw_row, p->rtw)) return e;
@@ -324,7 +343,8 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
     if (!(step[j] > 0)) return set_error_msg("grid step must be positive");
   }
   if (shape[ndim - 1] < 32) return set_error_msg("last grid axis must be >= 32");
-  if (shape[0] > (1 << 14)) return set_error_msg("axis 0 longer than 16384 is not supported yet");
+  if (shape[0] > (ndim == 2 ? (1 << 15) : (1 << 14)))
+    return set_error_msg("axis 0 longer than 32768 (2-D) / 16384 (3-D) is not supported");
   if (shape[ndim - 1] > (1 << 15))
     return set_error_msg("last axis longer than 32768 is not supported yet");
   for (int j = 1; j + 1 < ndim; ++j)
@@ -346,7 +366,8 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   p->lm_x = ilog2(Nx);
   int err = 0;
   err |= upload(&p->tw_row, build_twiddles(p->lm_row));
-  err |= upload(&p->tw_x, build_twiddles(p->lm_x, ndim == 2 ? xlines_lemax(p->lm_x) : 4));
+  err |= upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x, ndim == 2 ? xlines_lemax(p->lm_x) : 4));
+  if (p->lm_x == 15 && ndim == 2) err |= big_line_tables(p, (size_t)batch * (Ny / 2));
   if (ndim == 3) {
     p->lm_y = ilog2(shape[1]);
     err |= upload(&p->tw_y, build_twiddles(p->lm_y));
@@ -419,6 +440,8 @@ void cfd_plan_destroy(cfd_plan* p) {
     cudaFree(p->shared);
   }
   cudaFree(p->tw_x);
+  cudaFree(p->wbig);
+  cudaFree(p->xscratch);
   cudaFree(p->tw_y);
   cudaFree(p->T2);
   cudaFree(p->nut);

@@ -15,6 +15,8 @@ struct cfd_plan {
   int lm_row = 0, lm_x = 0, lm_y = 0;  // log2 of: last axis / 2, axis 0, axis 1 (3-D only)
   float2* tw_row = nullptr;
   float2* tw_x = nullptr;
+  float2* wbig = nullptr;      // 32768-point x lines: exp(-2 pi i m / 32768)
+  float2* xscratch = nullptr;  // ... and the scratch of the split transform
   float2* tw_y = nullptr;   // 3-D: complex lines along axis 1
   float2* T2 = nullptr;     // 3-D: second spectrum buffer
   float* nut = nullptr;     // 3-D: Smagorinsky eddy viscosity at cell centres

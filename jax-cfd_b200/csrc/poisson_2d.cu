@@ -83,6 +83,70 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
   }
 }
 
+// Multiply the spectrum of one x line (held in registers, v[slot] <-> sub-index d = t + G*slot) by
+// the pseudo-inverse table D(kx, ky) = norm / (lam_x[kx] + lam_y[ky]),  kx = kmul * d + kadd.
+// (kmul, kadd) = (1, 0) for a whole line; (2, 0) / (2, 1) for the even / odd half-spectra of the
+// split 32768-point transform.  The packed line ky = 0 (ky = 0 in Re, ky = Ny/2 in Im) is split
+// into its two real sequences by symmetry: with C the line spectrum and C~ = conj C[N - kx],
+//   C'[kx] = D(kx,0)/2 (C + C~) + D(kx,Ny/2)/2 (C - C~);   N - kx stays in the same half-spectrum.
+template <class P, bool FASTD>
+__device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, int ky, int My,
+                                           bool cta_has_packed, int kmul, int kadd,
+                                           const double* __restrict__ lamx,
+                                           const double* __restrict__ lamy,
+                                           const float* __restrict__ lamxf,
+                                           const float* __restrict__ lamyf, double cutoff,
+                                           float norm) {
+  constexpr int M = P::M, G = P::G, E = P::E;
+  if (!cta_has_packed || ky != 0) {
+    if (FASTD) {
+      // only the mean mode is below the cutoff (checked on the host in f64): float eigenvalues,
+      // |lam| >= min nonzero |lam_x|, |lam_y| > cutoff, so no per-element test is needed here
+      const float ly = __ldg(lamyf + ky);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float d = norm * fast_rcp(__ldg(lamxf + kmul * (t + G * e) + kadd) + ly);
+        v[e].x *= d;
+        v[e].y *= d;
+      }
+    } else {
+      const double ly = __ldg(lamy + ky);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const double lam = __ldg(lamx + kmul * (t + G * e) + kadd) + ly;
+        const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
+        v[e].x *= d;
+        v[e].y *= d;
+      }
+    }
+  }
+  if (cta_has_packed) {
+    __syncthreads();
+    if (ky == 0) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) s[P::pad(t + G * e)] = v[e];
+    }
+    __syncthreads();
+    if (ky == 0) {
+      const double ly0 = __ldg(lamy + 0), lyM = __ldg(lamy + My);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int d = t + G * e;
+        const int dp = kadd ? (M - 1 - d) : ((M - d) & (M - 1));  // sub-index of N - kx
+        const float2 cp = s[P::pad(dp)];
+        const double lx = __ldg(lamx + kmul * d + kadd);
+        const double l0 = lx + ly0, lM = lx + lyM;
+        const float d0 = (fabs(l0) > cutoff) ? 0.5f * norm * fast_rcp((float)l0) : 0.f;
+        const float dM = (fabs(lM) > cutoff) ? 0.5f * norm * fast_rcp((float)lM) : 0.f;
+        const float2 c = v[e];
+        const float2 sum = make_float2(c.x + cp.x, c.y - cp.y);
+        const float2 dif = make_float2(c.x - cp.x, c.y + cp.y);
+        v[e] = make_float2(d0 * sum.x + dM * dif.x, d0 * sum.y + dM * dif.y);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // X: lines T[line][0..Nx)  (line = b * My + ky), forward FFT * D * inverse FFT, in place.
 //
@@ -92,7 +156,7 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
 // kernel (each rank transforms its own range of ky lines).  One GPU: a single peer, Nloc = M.
 template <int LM, int LINES, bool FASTD, int LEMAX>
 __global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX>::G, (LEMAX == 5 && LINES * FftPlan<LM, LEMAX>::G <= 256) ? 2 : 1)
-xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
+xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My, int split,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
               const float* __restrict__ lamyf, double cutoff, float norm) {
@@ -102,12 +166,17 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   extern __shared__ float2 smem[];
   const int tid = threadIdx.x;
   const int ln = tid / G, t = tid % G;
-  const size_t line0 = line_begin + (size_t)blockIdx.x * LINES;
-  const size_t line = line0 + ln;
+  // split == 1: the "lines" are the half-length lines (y0, y1 interleaved per original line) of
+  // the 32768-point transform in a local scratch; original line = line_begin + (index >> 1).
+  const size_t idx0 = (size_t)blockIdx.x * LINES;
+  const size_t line0 = split ? line_begin + (idx0 >> 1) : line_begin + idx0;
+  const size_t line = split ? line_begin + ((idx0 + ln) >> 1) : line0 + ln;
   const int ky = (int)(line % My);
+  const int kmul = split ? 2 : 1, kadd = split ? (int)((idx0 + ln) & 1) : 0;
   float2* s = smem + ln * RS;
   const int nloc_mask = (1 << lnloc) - 1;
-  const size_t loff = line << lnloc;  // this line's offset inside every rank's buffer
+  // this line's offset inside every rank's buffer (split: inside the scratch)
+  const size_t loff = split ? (idx0 + ln) << LM : line << lnloc;
   // One GPU (lnloc == LM): plain contiguous line.  Several GPUs: peer table in shared memory (a
   // dynamically indexed kernel parameter would live in local memory).
   __shared__ float2* s_peer[CFD_MAX_PEERS];
@@ -126,59 +195,58 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   for (int e = 0; e < E; ++e) v[e] = *elem(t + G * e);
   FftRun<P, -1>::run(v, t, s, tw);
 
-  const bool cta_has_packed = (line0 % My) == 0;  // only the first line of a CTA can be ky = 0
-  if (!cta_has_packed || ky != 0) {
-    if (FASTD) {
-      // only the mean mode is below the cutoff (checked on the host in f64): float eigenvalues,
-      // |lam| >= min nonzero |lam_x|, |lam_y| > cutoff, so no per-element test is needed here
-      const float ly = __ldg(lamyf + ky);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float d = norm * fast_rcp(__ldg(lamxf + t + G * e) + ly);
-        v[e].x *= d;
-        v[e].y *= d;
-      }
-    } else {
-      const double ly = __ldg(lamy + ky);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const double lam = __ldg(lamx + t + G * e) + ly;
-        const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
-        v[e].x *= d;
-        v[e].y *= d;
-      }
-    }
-  }
-  if (cta_has_packed) {
-    // Line ky = 0 carries two real sequences (ky = 0 in Re, ky = Ny/2 in Im).  Their spectra are
-    // A = (C[k] + conj C[N-k]) / 2 and B = (C[k] - conj C[N-k]) / 2i; scale them with D(kx, 0) and
-    // D(kx, Ny/2) and recombine:  C'[k] = D0/2 (C[k] + conj C[N-k]) + DM/2 (C[k] - conj C[N-k]).
-    __syncthreads();
-    if (ky == 0) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) s[P::pad(t + G * e)] = v[e];
-    }
-    __syncthreads();
-    if (ky == 0) {
-      const double ly0 = __ldg(lamy + 0), lyM = __ldg(lamy + My);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int kx = t + G * e;
-        const float2 cp = s[P::pad((M - kx) & (M - 1))];
-        const double lx = __ldg(lamx + kx);
-        const double l0 = lx + ly0, lM = lx + lyM;
-        const float d0 = (fabs(l0) > cutoff) ? 0.5f * norm * fast_rcp((float)l0) : 0.f;
-        const float dM = (fabs(lM) > cutoff) ? 0.5f * norm * fast_rcp((float)lM) : 0.f;
-        const float2 c = v[e];
-        const float2 sum = make_float2(c.x + cp.x, c.y - cp.y);
-        const float2 dif = make_float2(c.x - cp.x, c.y + cp.y);
-        v[e] = make_float2(d0 * sum.x + dM * dif.x, d0 * sum.y + dM * dif.y);
-      }
-    }
-  }
+  // only the first line(s) of a CTA can be ky = 0 (split: both halves of that line)
+  const bool cta_has_packed = (line0 % My) == 0;
+  scale_line<P, FASTD>(v, t, s, ky, My, cta_has_packed, kmul, kadd, lamx, lamy, lamxf, lamyf, cutoff,
+                       norm);
   FftRun<P, +1>::run(v, t, s, tw);
 #pragma unroll
   for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// Lines of 2^15 points (Nx = 32768) do not fit one CTA: one radix-2 decimation-in-frequency step
+//   y0[m] = x[m] + x[m + N/2],  y1[m] = (x[m] - x[m + N/2]) w_N^m              (split_lines_kernel)
+// turns a line into two half-length lines whose transforms are the even / odd frequencies; they
+// are scaled and inverse-transformed by xlines_kernel (split mode: kx = 2 d + parity) in a local
+// scratch, and  x'[m] = y0' + y1' conj(w^m),  x'[m + N/2] = y0' - y1' conj(w^m)   (merge_lines_kernel).
+// The spectrum itself (peer memory on several GPUs) is still read once and written once.
+__global__ void split_lines_kernel(LinePeers peers, int lnloc, size_t line_begin, int half,
+                                   float2* __restrict__ scratch, const float2* __restrict__ wbig) {
+  __shared__ float2* s_peer[CFD_MAX_PEERS];
+  if (threadIdx.x < CFD_MAX_PEERS) s_peer[threadIdx.x] = peers.p[threadIdx.x];
+  __syncthreads();
+  const size_t li = blockIdx.y;
+  const size_t loff = (line_begin + li) << lnloc;
+  const int nloc_mask = (1 << lnloc) - 1;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= half) return;
+  const int x1 = m + half;
+  const float2 a = s_peer[m >> lnloc][loff + (m & nloc_mask)];
+  const float2 b = s_peer[x1 >> lnloc][loff + (x1 & nloc_mask)];
+  const float2 w = __ldg(wbig + m);
+  const float2 d = make_float2(a.x - b.x, a.y - b.y);
+  float2* y = scratch + li * (size_t)(2 * half);
+  y[m] = make_float2(a.x + b.x, a.y + b.y);
+  y[half + m] = cmul(d, w);
+}
+
+__global__ void merge_lines_kernel(LinePeers peers, int lnloc, size_t line_begin, int half,
+                                   const float2* __restrict__ scratch, const float2* __restrict__ wbig) {
+  __shared__ float2* s_peer[CFD_MAX_PEERS];
+  if (threadIdx.x < CFD_MAX_PEERS) s_peer[threadIdx.x] = peers.p[threadIdx.x];
+  __syncthreads();
+  const size_t li = blockIdx.y;
+  const size_t loff = (line_begin + li) << lnloc;
+  const int nloc_mask = (1 << lnloc) - 1;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= half) return;
+  const int x1 = m + half;
+  const float2* y = scratch + li * (size_t)(2 * half);
+  const float2 y0 = y[m];
+  const float2 y1 = cmulc(y[half + m], __ldg(wbig + m));  // * conj(w^m)
+  s_peer[m >> lnloc][loff + (m & nloc_mask)] = make_float2(y0.x + y1.x, y0.y + y1.y);
+  s_peer[x1 >> lnloc][loff + (x1 & nloc_mask)] = make_float2(y0.x - y1.x, y0.y - y1.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -405,21 +473,21 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
 
 template <int LM, int LEMAX>
 int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
-                     size_t nlines, int My, const float2* tw, const double* lamx, const double* lamy,
+                     size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
                      const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
   using P = FftPlan<LM, LEMAX>;
   constexpr int LINES = (P::G >= 256) ? 1 : (256 / P::G > 16 ? 16 : 256 / P::G);
   constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
-  if (nlines % LINES || line_begin % LINES) return set_error_msg("internal: line count not divisible");
+  if (nlines % LINES || (!split && line_begin % LINES)) return set_error_msg("internal: line count not divisible");
   if (fastd) {
     auto k = xlines_kernel<LM, LINES, true, LEMAX>;
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx,
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, split, tw, lamx,
                                                             lamy, lamxf, lamyf, cutoff, norm);
   } else {
     auto k = xlines_kernel<LM, LINES, false, LEMAX>;
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx,
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, split, tw, lamx,
                                                             lamy, lamxf, lamyf, cutoff, norm);
   }
   count_launch();
@@ -429,12 +497,12 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
 
 template <int LM>
 int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
-                    size_t nlines, int My, const float2* tw, const double* lamx, const double* lamy,
+                    size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
   if (xlines_lemax(LM) == 5)
-    return launch_xlines_le<LM, 5>(st, peers, lnloc, line_begin, nlines, My, tw, lamx, lamy, lamxf,
+    return launch_xlines_le<LM, 5>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
                                    lamyf, fastd, cutoff, norm);
-  return launch_xlines_le<LM, 4>(st, peers, lnloc, line_begin, nlines, My, tw, lamx, lamy, lamxf,
+  return launch_xlines_le<LM, 4>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
                                  lamyf, fastd, cutoff, norm);
 }
 
@@ -497,22 +565,42 @@ int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, i
   return 0;
 }
 // lm_x = log2(Nx)
+// `scratch` / `wbig` are only needed for lm_x == 15 (32768-point lines): scratch holds
+// nlines * 32768 float2, wbig[m] = exp(-2 pi i m / 32768), m < 16384.
 int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int lnloc,
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
-                        const float* lamyf, int fastd, double cutoff, float norm) {
+                        const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
+                        const float2* wbig) {
+  if (lm_x == 15) {
+    if (!scratch || !wbig) return set_error_msg("internal: 32768-point lines need the split scratch");
+    const int half = 1 << 14;
+    dim3 grid(half / 256, (unsigned)nlines);
+    split_lines_kernel<<<grid, 256, 0, st>>>(peers, lnloc, line_begin, half, scratch, wbig);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    LinePeers local;
+    for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = scratch;
+    if (int e = launch_xlines_t<14>(st, local, 14, line_begin, 2 * nlines, My, 1, tw, lamx, lamy, lamxf,
+                                    lamyf, fastd, cutoff, norm))
+      return e;
+    merge_lines_kernel<<<grid, 256, 0, st>>>(peers, lnloc, line_begin, half, scratch, wbig);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   CFD_DISPATCH_LM(lm_x, 4, 14,
-                  return launch_xlines_t<LM_>(st, peers, lnloc, line_begin, nlines, My, tw, lamx, lamy,
+                  return launch_xlines_t<LM_>(st, peers, lnloc, line_begin, nlines, My, 0, tw, lamx, lamy,
                                               lamxf, lamyf, fastd, cutoff, norm));
   return 0;
 }
 int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
-                  int fastd, double cutoff, float norm) {
+                  int fastd, double cutoff, float norm, float2* scratch, const float2* wbig) {
   LinePeers peers;
   for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
   return launch_xlines_peers(st, lm_x, peers, lm_x, 0, (size_t)batch * My, My, tw, lamx, lamy, lamxf,
-                             lamyf, fastd, cutoff, norm);
+                             lamyf, fastd, cutoff, norm, scratch, wbig);
 }
 int launch_irfft_correct(cudaStream_t st, int lm_row, const float2* T, const float* us,
                          const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,

@@ -46,8 +46,8 @@ def check_decomposition(shape: Sequence[int], world: int) -> None:
     raise ValueError('local slab must be a power of two >= 16 rows')
   if (ny // 2) % world or (ny // 2 // world) % 16:
     raise ValueError('Ny/2 lines must split evenly over the ranks')
-  if nx > (1 << 14):
-    raise NotImplementedError('global axis 0 longer than 16384 is not supported yet')
+  if nx > (1 << 15):
+    raise NotImplementedError('global axis 0 longer than 32768 is not supported')
 
 
 def torch_exchange(blob: bytes) -> List[bytes]:

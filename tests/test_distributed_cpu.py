@@ -18,12 +18,13 @@ def test_partition_arithmetic():
     D.slab_rows(100, 0, 8)
   D.check_decomposition((8192, 8192), 8)
   D.check_decomposition((16384, 8192), 2)
+  D.check_decomposition((32768, 32768), 8)
   with pytest.raises(ValueError):
     D.check_decomposition((64, 64), 8)       # 8 rows per rank
   with pytest.raises(ValueError):
     D.check_decomposition((8192, 64), 4)     # 8 lines per rank
   with pytest.raises(NotImplementedError):
-    D.check_decomposition((32768, 32768), 8)
+    D.check_decomposition((65536, 32768), 8)
 
 
 def _worker(rank, world, port, q):
