@@ -214,6 +214,8 @@ def run_gpu_slab(args, wl, name):
   lib = _lib.lib()
   _lib.check(lib.cfd_set_device(local_rank))
   shape = (SLAB_SHAPES_32K if name == 'K32768' else SLAB_SHAPES)[world]
+  if os.environ.get('CFD_SLAB_SHAPE'):  # tuning aid, e.g. CFD_SLAB_SHAPE=32768x8192
+    shape = tuple(int(x) for x in os.environ['CFD_SLAB_SHAPE'].split('x'))
   grid = cfd.grids.Grid(shape, domain=((0.0, TWO_PI * shape[0] / 8192.0), (0.0, TWO_PI * shape[1] / 8192.0)))
   dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
   forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
@@ -248,6 +250,7 @@ def run_gpu_slab(args, wl, name):
   t = torch.tensor([ms_total], device='cuda')
   dist.all_reduce(t, op=dist.ReduceOp.MAX)
   ms_total = float(t.item())
+  kern = st.profile(2)
   outs = st.store()
   loc = outs[0].numpy()
   # e2e at N GPUs: every step copies the rank's slab host->device, steps once, copies it back
@@ -277,7 +280,7 @@ def run_gpu_slab(args, wl, name):
     value = cells * args.steps / (ms_total * 1e-3) / 1e9
     step_gbs = STEP_BYTES_PER_CELL * cells_local / (ms_step * 1e-3) / 1e9
     # NVLink bytes per rank per step: x-line kernel reads and writes (world-1)/world of its lines
-    nvl = 2 * (shape[1] // 2 // world) * shape[0] * 8 * (world - 1) / world
+    nvl = (shape[1] // 2 // world) * shape[0] * 8 * (world - 1) / world
     line = {
         'metric': 'cell-updates/sec', 'value': value, 'unit': 'Gcell*step/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
@@ -292,6 +295,7 @@ def run_gpu_slab(args, wl, name):
         'roofline': {'bound': 'hbm', 'kernel': 'whole step (per GPU)', 'achieved': step_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': step_gbs / peak, 'traffic': None, 'peak_source': peak_src,
                      'bytes_per_cell_model': STEP_BYTES_PER_CELL},
+        'kernel_ms_rank0': kern,
         'nvlink': {'bytes_per_gpu_per_step_each_direction': nvl,
                    'lower_bound_ms_at_770GBs': nvl / 770e9 * 1e3},
         'cpu_baseline': None,

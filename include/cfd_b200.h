@@ -140,6 +140,8 @@ int cfd_dist_load(cfd_plan* plan, cfd_stream stream, const float* const* v_local
 int cfd_dist_advance(cfd_plan* plan, cfd_stream stream, int nsteps, const cfd_params* params);
 int cfd_dist_store(cfd_plan* plan, cfd_stream stream, float* const* v_local_out, float* q_local_out);
 int cfd_dist_check(cfd_plan* plan); /* non-zero if a device-side barrier ever timed out */
+int cfd_dist_profile(cfd_plan* plan, cfd_stream stream, int nsteps, const cfd_params* params,
+                     int max_kernels, float* ms, const char** names, int* n_kernels);
 
 /* ---- thin device-memory helpers so hosts without a CUDA array library can drive the ABI --- */
 int cfd_malloc(void** dptr, size_t bytes);

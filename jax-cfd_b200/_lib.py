@@ -100,6 +100,9 @@ _SIGS = {
     'cfd_dist_store': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                       ctypes.c_void_p]),
     'cfd_dist_check': (ctypes.c_int, [ctypes.c_void_p]),
+    'cfd_dist_profile': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Params),
+                                        ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                        ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int)]),
     'cfd_malloc': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
     'cfd_free': (ctypes.c_int, [ctypes.c_void_p]),
     'cfd_malloc_host': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),

@@ -12,6 +12,8 @@
 //     handles once (any transport: torch.distributed in jax_cfd_b200.distributed).
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "plan_struct.cuh"
 
@@ -94,6 +96,7 @@ int barrier(cfd_plan* p, cudaStream_t st) {
   slab_barrier_kernel<<<1, 32, 0, st>>>(fp, p->rank, p->world, p->epoch, err);
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
+  prof_mark(p, st, "barrier");
   return 0;
 }
 
@@ -210,8 +213,8 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
   const size_t lines_per_rank = (size_t)My / p->world;
   for (int n = 0; n < nsteps; ++n) {
     const int cur = p->dist_cur, nxt = cur ^ 1;
-    if (int e = barrier(p, st)) return e;  // neighbours' inputs (VIN or u*, v*, q) are complete
     prof_mark(p, st, "begin");
+    if (int e = barrier(p, st)) return e;  // neighbours' inputs (VIN or u*, v*, q) are complete
     if (p->dist_state == 1) {
       const SlabSrc none = {nullptr, nullptr, nullptr};
       if (int e = launch_explicit_2d_slab(st, src3(L.off_vin[0]), src3(L.off_vin[1]), none,
@@ -271,6 +274,47 @@ int cfd_dist_store(cfd_plan* p, cfd_stream stream, float* const* v_local_out, fl
                                 cudaMemcpyDeviceToDevice, st));
   // peers may still be reading my q for their own store: fence before anyone advances again
   return barrier(p, st);
+}
+
+// Per-kernel CUDA-event times of `nsteps` slab steps (aggregated by kernel name, mean per launch;
+// barrier kernels appear as "barrier").  Every rank must call it.
+int cfd_dist_profile(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_params* params,
+                     int max_kernels, float* ms, const char** names, int* n_kernels) {
+  if (!p || !p->shared) return set_error_msg("not a distributed plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (auto ev : p->prof_events) cudaEventDestroy(ev);
+  p->prof_events.clear();
+  p->prof_names.clear();
+  p->profiling = true;
+  int e = cfd_dist_advance(p, stream, nsteps, params);
+  p->profiling = false;
+  if (e) return e;
+  CFD_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<const char*> uniq;
+  std::vector<double> tot;
+  std::vector<int> cnt;
+  for (size_t i = 1; i < p->prof_events.size(); ++i) {
+    const char* nm = p->prof_names[i];
+    float t = 0.f;
+    CFD_CUDA_OK(cudaEventElapsedTime(&t, p->prof_events[i - 1], p->prof_events[i]));
+    size_t k = 0;
+    for (; k < uniq.size(); ++k)
+      if (strcmp(uniq[k], nm) == 0) break;
+    if (k == uniq.size()) {
+      uniq.push_back(nm);
+      tot.push_back(0.0);
+      cnt.push_back(0);
+    }
+    tot[k] += t;
+    cnt[k] += 1;
+  }
+  const int n = (int)uniq.size();
+  if (n_kernels) *n_kernels = n < max_kernels ? n : max_kernels;
+  for (int i = 0; i < n && i < max_kernels; ++i) {
+    ms[i] = (float)(tot[i] / cnt[i]);
+    names[i] = uniq[i];
+  }
+  return 0;
 }
 
 // 0 when no barrier ever timed out

@@ -205,6 +205,73 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My, int split,
 }
 
 // ------------------------------------------------------------------------------------------
+// X, software-pipelined variant for long lines (one line per CTA, 4096 or 8192 points): persistent
+// CTAs stride over their lines; while line n is transformed (registers + exchange buffer), line
+// n+1 is already streaming into a second shared-memory buffer with cp.async (LDGSTS, no registers),
+// and the stores of line n-1 drain asynchronously -- the load phase (HBM, or NVLink peer memory on
+// several GPUs) disappears from the critical path.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int LM, bool FASTD>
+__global__ void __launch_bounds__(FftPlan<LM>::G)
+xlines_pipe_kernel(LinePeers peers, int lnloc, size_t line_begin, size_t nlines, int My, int split,
+                   const float2* __restrict__ tw, const double* __restrict__ lamx,
+                   const double* __restrict__ lamy, const float* __restrict__ lamxf,
+                   const float* __restrict__ lamyf, double cutoff, float norm) {
+  using P = FftPlan<LM>;
+  constexpr int M = P::M, G = P::G, E = P::E;
+  constexpr int RS = row_stride(M, 16);
+  extern __shared__ float2 smem[];
+  float2* s = smem;        // exchange buffer (padded)
+  float2* pre = smem + ((RS + 1) & ~1);  // prefetch buffer: M float2, 16-byte aligned
+  const int t = threadIdx.x;
+  __shared__ float2* s_peer[CFD_MAX_PEERS];
+  if (t < CFD_MAX_PEERS) s_peer[t] = peers.p[t];
+  __syncthreads();
+  const int nloc_mask = (1 << lnloc) - 1;
+  auto line_of = [&](size_t li) { return split ? line_begin + (li >> 1) : line_begin + li; };
+  auto loff_of = [&](size_t li) { return split ? li << LM : (line_begin + li) << lnloc; };
+  auto elem = [&](size_t loff, int x) -> float2* {
+    return s_peer[x >> lnloc] + loff + (x & nloc_mask);
+  };
+  auto prefetch = [&](size_t li) {
+    const size_t loff = loff_of(li);
+#pragma unroll
+    for (int c = 0; c < E / 2; ++c) {
+      const int x = 2 * (t + G * c);  // 16 bytes = 2 points, never straddles a rank boundary
+      cp_async16(pre + x, elem(loff, x));
+    }
+    cp_async_commit();
+  };
+  size_t li = blockIdx.x;
+  if (li < nlines) prefetch(li);
+  for (; li < nlines; li += gridDim.x) {
+    const size_t line = line_of(li);
+    const size_t loff = loff_of(li);
+    const int ky = (int)(line % My);
+    const int kmul = split ? 2 : 1, kadd = split ? (int)(li & 1) : 0;
+    cp_async_wait_all();
+    __syncthreads();
+    float2 v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = pre[t + G * e];
+    __syncthreads();  // everyone has drained the prefetch buffer
+    if (li + gridDim.x < nlines) prefetch(li + gridDim.x);
+    FftRun<P, -1>::run(v, t, s, tw);
+    scale_line<P, FASTD>(v, t, s, ky, My, ky == 0, kmul, kadd, lamx, lamy, lamxf, lamyf, cutoff, norm);
+    FftRun<P, +1>::run(v, t, s, tw);
+#pragma unroll
+    for (int e = 0; e < E; ++e) *elem(loff, t + G * e) = v[e];
+    __syncthreads();  // exchange buffer free for the next line
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Lines of 2^15 points (Nx = 32768) do not fit one CTA: one radix-2 decimation-in-frequency step
 //   y0[m] = x[m] + x[m + N/2],  y1[m] = (x[m] - x[m + N/2]) w_N^m              (split_lines_kernel)
 // turns a line into two half-length lines whose transforms are the even / odd frequencies; they
@@ -496,9 +563,56 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
 }
 
 template <int LM>
+int launch_xlines_pipe(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
+                       size_t nlines, int My, int split, const float2* tw, const double* lamx,
+                       const double* lamy, const float* lamxf, const float* lamyf, int fastd,
+                       double cutoff, float norm) {
+  using P = FftPlan<LM>;
+  constexpr size_t smem = ((size_t)((row_stride(P::M, 16) + 1) & ~1) + P::M) * sizeof(float2);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const unsigned grid = (unsigned)(nlines < (size_t)sms ? nlines : (size_t)sms);
+  if (fastd) {
+    auto k = xlines_pipe_kernel<LM, true>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<grid, P::G, smem, st>>>(peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
+                                lamyf, cutoff, norm);
+  } else {
+    auto k = xlines_pipe_kernel<LM, false>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<grid, P::G, smem, st>>>(peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
+                                lamyf, cutoff, norm);
+  }
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// The pipelined kernel measured no faster than the one-shot kernel on one GPU (316 vs 295 us at
+// 8192^2: the line transforms are barrier/issue bound, not load-latency bound), so it is opt-in:
+// CFD_XLINES_PIPE=1 (single GPU), CFD_XLINES_PIPE=2 (also when lines live in peer memory).
+inline int xlines_pipe_mode() {
+  static const int v = [] {
+    const char* e = getenv("CFD_XLINES_PIPE");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+template <int LM>
 int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
                     size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
+  if constexpr (LM == 12 || LM == 13) {
+    if (xlines_pipe_mode() != 0 && xlines_lemax(LM) == 4)
+      return launch_xlines_pipe<LM>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy,
+                                    lamxf, lamyf, fastd, cutoff, norm);
+  }
   if (xlines_lemax(LM) == 5)
     return launch_xlines_le<LM, 5>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
                                    lamyf, fastd, cutoff, norm);

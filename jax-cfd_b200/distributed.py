@@ -111,6 +111,15 @@ class SlabStepper:
     check(lib().cfd_dist_check(self.handle))
     return (outs, q) if want_q else outs
 
+  def profile(self, nsteps: int = 2):
+    """Mean CUDA-event time per launch of every kernel of `nsteps` steps (all ranks must call)."""
+    names = (ctypes.c_char_p * 16)()
+    ms = (ctypes.c_float * 16)()
+    nk = ctypes.c_int(0)
+    check(lib().cfd_dist_profile(self.handle, self.stream.handle, nsteps, ctypes.byref(self.params), 16,
+                                 ms, names, ctypes.byref(nk)))
+    return {names[i].decode(): float(ms[i]) for i in range(nk.value)}
+
   def sync(self):
     self.stream.sync()
 
