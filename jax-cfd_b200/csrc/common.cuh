@@ -46,6 +46,14 @@ struct LinePeers {
   float2* p[CFD_MAX_PEERS];
 };
 
+// Side streams + events used to overlap the chunks of the split 32768-point x pass.
+struct SideStreams {
+  int n = 0;
+  cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t start = nullptr;
+  cudaEvent_t done[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
 __device__ __forceinline__ int wrap_idx(int i, int n) {  // i in [-n, 2n)
   i = i < 0 ? i + n : i;
   return i >= n ? i - n : i;

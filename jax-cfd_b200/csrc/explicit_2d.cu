@@ -64,11 +64,11 @@ __device__ __forceinline__ void strow(float* p, const FC<2>& f) {
 // straight from the neighbouring ranks' buffers over NVLink (SlabSrc::prev / next, peer-mapped
 // with CUDA IPC) -- the halo exchange is fused into the stencil loads.  On one GPU prev = next =
 // own, which is the periodic wrap.
-template <int TX, int PATTERN, int C, bool LAZY>
+template <int PATTERN, int C, bool LAZY>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
                   float* __restrict__ vs, float* __restrict__ rhs, int Nx, int Ny, int row0,
-                  int nx_global, StepConsts c, int dvdt_mode) {
+                  int nx_global, StepConsts c, int dvdt_mode, int TX) {
   using Row = FC<C>;
   // Halo lanes: the divergence needs v* one column to the left of the first stored column, whose
   // own stencil reaches 2 further columns: 4 columns = 1 lane (C = 4) or 2 lanes (C = 2) on the
@@ -181,7 +181,6 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
   }
   // Row profiles of the separable term for the rows of this block, one row per lane (3 x 32 >= TX
   // + 1), broadcast by shuffle inside the loop: no scalar global loads on the critical path.
-  static_assert(TX + 1 <= 96, "row-profile table too small");
   const bool has_px = kHasSep && (px_u != nullptr || px_v != nullptr);
   float pxu_tab[3] = {1.f, 1.f, 1.f}, pxv_tab[3] = {1.f, 1.f, 1.f};
   if (has_px) {
@@ -356,7 +355,11 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
                             int nx_global, const StepConsts& c, int dvdt_mode) {
   const float* qprev = sq.own;
   if (Nx < 3) return set_error_msg("a slab needs at least 3 rows");
-  constexpr int TX = 64;
+  // rows per warp: 64 normally (5 warm-up rows = 8 % redundant work); 16 on small grids, where 64
+  // would leave most SMs without a warp (2048^2: 576 warps for 148 SMs)
+  const int cols0 = 120;
+  const long warps64 = (long)((Ny + cols0 - 1) / cols0) * ((Nx + 63) / 64) * batch;
+  const int TX = warps64 >= 148L * 12 ? 64 : 16;
   static const int forced_cols = [] {  // tuning knob: CFD_EXPLICIT_COLS=2|4 columns per lane
     const char* e = getenv("CFD_EXPLICIT_COLS");
     return (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
@@ -377,8 +380,8 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
     pattern |= code << (2 * nt++);
   }
 #define CFD_EXPL_LAUNCH(P, CC, LZ)                                                          \
-  explicit2d_kernel<TX, P, CC, LZ><<<grid, 32 * kWarpsPerCta, 0, stream>>>(                    \
-      su, sv, sq, us, vs, rhs, Nx, Ny, row0, nx_global, c, dvdt_mode)
+  explicit2d_kernel<P, CC, LZ><<<grid, 32 * kWarpsPerCta, 0, stream>>>(                        \
+      su, sv, sq, us, vs, rhs, Nx, Ny, row0, nx_global, c, dvdt_mode, TX)
 #define CFD_EXPL_CASE(P)                    \
   case P:                                   \
     if (cols == 2) {                        \

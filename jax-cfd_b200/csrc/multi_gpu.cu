@@ -30,7 +30,7 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig);
+                        const float2* wbig, const SideStreams* side);
 int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
                       const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
                       float inv_hx, float inv_hy);
@@ -235,7 +235,7 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
     if (int e = barrier(p, st)) return e;  // every rank's slab spectrum is complete
     if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
                                     lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1], p->lamf[0],
-                                    p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig))
+                                    p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig, &p->side))
       return e;
     prof_mark(p, st, "xlines_peers");
     if (int e = barrier(p, st)) return e;  // every rank has written its lines back into my slab

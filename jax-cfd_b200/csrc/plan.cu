@@ -27,7 +27,8 @@ int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int 
                      const float2* tw, const float2* rtw);
 int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
-                  int fastd, double cutoff, float norm, float2* scratch, const float2* wbig);
+                  int fastd, double cutoff, float norm, float2* scratch, const float2* wbig,
+                  const SideStreams* side);
 int launch_irfft_correct(cudaStream_t, int lm_row, const float2* T, const float* us,
                          const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
                          const float2* tw, const float2* rtw, float inv_hx, float inv_hy);
@@ -190,6 +191,16 @@ int big_line_tables(cfd_plan* p, size_t nlines) {
   int err = upload(&p->wbig, w);
   if (cudaMalloc((void**)&p->xscratch, nlines * (size_t)(2 * half) * sizeof(float2)) != cudaSuccess)
     err |= set_error_msg("scratch allocation for 32768-point lines failed");
+  if (p->side.n == 0) {
+    for (int i = 0; i < 4; ++i) {
+      if (cudaStreamCreateWithFlags(&p->side.s[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->side.done[i], cudaEventDisableTiming) != cudaSuccess)
+        return set_error_msg("side stream creation failed");
+    }
+    if (cudaEventCreateWithFlags(&p->side.start, cudaEventDisableTiming) != cudaSuccess)
+      return set_error_msg("side stream creation failed");
+    p->side.n = 4;
+  }
   return err;
 }
 
@@ -238,7 +249,8 @@ int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
   if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw)) return e;
   prof_mark(p, st, "rfft_rows");
   if (int e = launch_xlines(st, p->lm_x, p->T, p->batch, Ny / 2, p->tw_x, p->lam[0], p->lam[1],
-                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig))
+                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig,
+                            &p->side))
     return e;
   prof_mark(p, st, "xlines");
   if (int e = launch_irfft_rows(st, p->lm_row, p->T, q, p->batch, Nx, p->tw_row, p->rtw)) return e;
@@ -442,6 +454,11 @@ void cfd_plan_destroy(cfd_plan* p) {
   cudaFree(p->tw_x);
   cudaFree(p->wbig);
   cudaFree(p->xscratch);
+  for (int i = 0; i < p->side.n; ++i) {
+    cudaStreamDestroy(p->side.s[i]);
+    cudaEventDestroy(p->side.done[i]);
+  }
+  if (p->side.start) cudaEventDestroy(p->side.start);
   cudaFree(p->tw_y);
   cudaFree(p->T2);
   cudaFree(p->nut);

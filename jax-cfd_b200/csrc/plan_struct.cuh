@@ -17,6 +17,7 @@ struct cfd_plan {
   float2* tw_x = nullptr;
   float2* wbig = nullptr;      // 32768-point x lines: exp(-2 pi i m / 32768)
   float2* xscratch = nullptr;  // ... and the scratch of the split transform
+  cfd::SideStreams side;       // ... and the streams that overlap its chunks
   float2* tw_y = nullptr;   // 3-D: complex lines along axis 1
   float2* T2 = nullptr;     // 3-D: second spectrum buffer
   float* nut = nullptr;     // 3-D: Smagorinsky eddy viscosity at cell centres

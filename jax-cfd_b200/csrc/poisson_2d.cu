@@ -680,27 +680,48 @@ int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, i
 }
 // lm_x = log2(Nx)
 // `scratch` / `wbig` are only needed for lm_x == 15 (32768-point lines): scratch holds
-// nlines * 32768 float2, wbig[m] = exp(-2 pi i m / 32768), m < 16384.
+// nlines * 32768 float2, wbig[m] = exp(-2 pi i m / 32768), m < 16384.  With side streams the split
+// path runs in chunks of lines on those streams, so that the NVLink reads of one chunk (split), the
+// transforms of another (x lines, local scratch) and the NVLink writes of a third (merge) overlap.
 int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int lnloc,
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig) {
+                        const float2* wbig, const SideStreams* side) {
   if (lm_x == 15) {
     if (!scratch || !wbig) return set_error_msg("internal: 32768-point lines need the split scratch");
     const int half = 1 << 14;
-    dim3 grid(half / 256, (unsigned)nlines);
-    split_lines_kernel<<<grid, 256, 0, st>>>(peers, lnloc, line_begin, half, scratch, wbig);
-    count_launch();
-    CFD_CUDA_OK(cudaGetLastError());
-    LinePeers local;
-    for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = scratch;
-    if (int e = launch_xlines_t<14>(st, local, 14, line_begin, 2 * nlines, My, 1, tw, lamx, lamy, lamxf,
-                                    lamyf, fastd, cutoff, norm))
-      return e;
-    merge_lines_kernel<<<grid, 256, 0, st>>>(peers, lnloc, line_begin, half, scratch, wbig);
-    count_launch();
-    CFD_CUDA_OK(cudaGetLastError());
+    int nchunks = 1;
+    if (side && side->n > 0) {
+      nchunks = 8;
+      while (nchunks > 1 && (nlines % nchunks || nlines / nchunks < 32)) nchunks /= 2;
+    }
+    const size_t chunk = nlines / nchunks;
+    if (nchunks > 1) CFD_CUDA_OK(cudaEventRecord(side->start, st));
+    for (int c = 0; c < nchunks; ++c) {
+      cudaStream_t s = nchunks > 1 ? side->s[c % side->n] : st;
+      if (nchunks > 1 && c < side->n) CFD_CUDA_OK(cudaStreamWaitEvent(s, side->start, 0));
+      float2* sc = scratch + (size_t)c * chunk * (size_t)(2 * half);
+      const size_t lb = line_begin + (size_t)c * chunk;
+      dim3 grid(half / 256, (unsigned)chunk);
+      split_lines_kernel<<<grid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+      count_launch();
+      CFD_CUDA_OK(cudaGetLastError());
+      LinePeers local;
+      for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = sc;
+      if (int e = launch_xlines_t<14>(s, local, 14, lb, 2 * chunk, My, 1, tw, lamx, lamy, lamxf, lamyf,
+                                      fastd, cutoff, norm))
+        return e;
+      merge_lines_kernel<<<grid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+      count_launch();
+      CFD_CUDA_OK(cudaGetLastError());
+    }
+    if (nchunks > 1) {
+      for (int i = 0; i < side->n; ++i) {
+        CFD_CUDA_OK(cudaEventRecord(side->done[i], side->s[i]));
+        CFD_CUDA_OK(cudaStreamWaitEvent(st, side->done[i], 0));
+      }
+    }
     return 0;
   }
   CFD_DISPATCH_LM(lm_x, 4, 14,
@@ -710,11 +731,12 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
 }
 int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
-                  int fastd, double cutoff, float norm, float2* scratch, const float2* wbig) {
+                  int fastd, double cutoff, float norm, float2* scratch, const float2* wbig,
+                  const SideStreams* side) {
   LinePeers peers;
   for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
   return launch_xlines_peers(st, lm_x, peers, lm_x, 0, (size_t)batch * My, My, tw, lamx, lamy, lamxf,
-                             lamyf, fastd, cutoff, norm, scratch, wbig);
+                             lamyf, fastd, cutoff, norm, scratch, wbig, side);
 }
 int launch_irfft_correct(cudaStream_t st, int lm_row, const float2* T, const float* us,
                          const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
