@@ -29,9 +29,6 @@ int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const fl
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
                   int fastd, double cutoff, float norm, float2* scratch, const float2* wbig,
                   const SideStreams* side);
-int launch_irfft_correct(cudaStream_t, int lm_row, const float2* T, const float* us,
-                         const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
-                         const float2* tw, const float2* rtw, float inv_hx, float inv_hy);
 int launch_divergence_2d(cudaStream_t, const float* u, const float* v, float* rhs, int batch,
                          int Nx, int Ny, float inv_hx, float inv_hy);
 int launch_axpy(cudaStream_t, const float* x, int nterms, const float* const* y, const float* coef,

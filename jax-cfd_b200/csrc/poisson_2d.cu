@@ -9,9 +9,10 @@
 //   X  xlines:      for every ky: contiguous complex FFT along x, multiply by the pseudo-inverse
 //                   eigenvalue table D(kx, ky) (built in f64 from the analytic circulant
 //                   eigenvalues), inverse FFT along x, in place.  One read + one write of T.
-//   C  irfft_rows_correct: gather T[ky][x] for R+1 rows, inverse real FFT -> q rows in shared
-//                   memory, then v' = u* - forward_difference(q) (pressure.py:194-196) written
-//                   straight to the output state.
+//   Q  irfft_rows:  gather T[ky][x] for the CTA's rows, inverse real FFT, coalesced q store.
+//   C  correct2d:   v' = u* - forward_difference(q) (pressure.py:194-196); only run when a
+//                   projected state must be materialised (chained steps project lazily inside
+//                   the next explicit kernel).
 //
 // Scaling: R stores 2*X, C's pre-processing produces 2*Z, the inverse passes are unnormalised, so
 // the table D carries 1 / (2 * Nx * Ny) (a power of two: exact).
@@ -317,97 +318,6 @@ __global__ void merge_lines_kernel(LinePeers peers, int lnloc, size_t line_begin
 }
 
 // ------------------------------------------------------------------------------------------
-// C: gather RP = R + 1 rows of T, inverse real FFT -> q in smem, v' = u* - grad q.
-template <int LM, int RP>
-__global__ void __launch_bounds__(RP * FftPlan<LM>::G)
-irfft_rows_correct_kernel(const float2* __restrict__ T, const float* __restrict__ us,
-                          const float* __restrict__ vs, float* __restrict__ uo,
-                          float* __restrict__ vo, float* __restrict__ qo, int Nx,
-                          const float2* __restrict__ tw, const float2* __restrict__ rtw,
-                          float inv_hx, float inv_hy) {
-  using P = FftPlan<LM>;
-  constexpr int M = P::M, G = P::G, E = P::E;
-  constexpr int R = RP - 1;
-  constexpr int RS = row_stride(M, RP);  // skewed: the gather below walks rows fastest
-  constexpr int NT = RP * G;
-  constexpr int N = 2 * M;
-  extern __shared__ float2 smem[];
-  const int tid = threadIdx.x;
-  const int row = tid / G, t = tid % G;
-  const int x0 = blockIdx.x * R;
-  const size_t b = blockIdx.y;
-  float2* s = smem + row * RS;
-
-  // gather: rows x0 .. x0+R (the last one is the periodic neighbour needed by d/dx)
-  {
-    const float2* Tb = T + b * (size_t)M * Nx;
-    for (int idx = tid; idx < RP * M; idx += NT) {
-      const int r = idx % RP, ky = idx / RP;
-      int x = x0 + r;
-      x = x >= Nx ? x - Nx : x;
-      smem[r * RS + PAD(ky)] = __ldg(Tb + (size_t)ky * Nx + x);
-    }
-  }
-  __syncthreads();
-  // rebuild the half-size complex spectrum Z'' = 2Z from the packed real-input spectrum
-  for (int k = t; k <= M / 2; k += G) {
-    if (k == 0) {
-      const float2 x = s[0];
-      s[0] = make_float2(x.x + x.y, x.x - x.y);
-    } else if (k == M / 2) {
-      const float2 x = s[PAD(k)];
-      s[PAD(k)] = make_float2(2.f * x.x, -2.f * x.y);
-    } else {
-      const float2 xk = s[PAD(k)], xm = s[PAD(M - k)];
-      const float2 A = make_float2(xk.x + xm.x, xk.y - xm.y);
-      const float2 B = make_float2(xk.x - xm.x, xk.y + xm.y);
-      const float2 WB = cmulc(B, __ldg(rtw + k));  // conj(-i w^k) B
-      s[PAD(k)] = make_float2(A.x + WB.x, A.y + WB.y);
-      s[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
-    }
-  }
-  __syncthreads();
-  float2 v[E];
-  fft_load_regs<P>(v, t, s);
-  FftRun<P, +1>::run(v, t, s, tw);
-  __syncthreads();
-#pragma unroll
-  for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];  // (q[2m], q[2m+1]) at PAD(m)
-  __syncthreads();
-
-  // correction (pressure.py:194-196): 4 columns per thread, rows 0..R-1
-  const float* sf = reinterpret_cast<const float*>(smem);
-  constexpr int QPR = N / 4;  // float4 groups per row
-  for (int idx = tid; idx < R * QPR; idx += NT) {
-    const int r = idx / QPR, g = idx % QPR;
-    const int x = x0 + r;
-    if (x >= Nx) break;
-    const int j = 4 * g, m = 2 * g;
-    const float* q0 = sf + 2 * (size_t)(r * RS);
-    const float* q1 = sf + 2 * (size_t)((r + 1) * RS);
-    const float2 a0 = *reinterpret_cast<const float2*>(q0 + 2 * PAD(m));
-    const float2 a1 = *reinterpret_cast<const float2*>(q0 + 2 * PAD(m + 1));
-    const float a2 = q0[2 * PAD((m + 2) & (M - 1))];
-    const float2 b0 = *reinterpret_cast<const float2*>(q1 + 2 * PAD(m));
-    const float2 b1 = *reinterpret_cast<const float2*>(q1 + 2 * PAD(m + 1));
-    const size_t off = (b * Nx + x) * (size_t)N + j;
-    const float4 u4 = ldg4(us + off), v4 = ldg4(vs + off);
-    float4 ou, ov;
-    ou.x = u4.x - (b0.x - a0.x) * inv_hx;
-    ou.y = u4.y - (b0.y - a0.y) * inv_hx;
-    ou.z = u4.z - (b1.x - a1.x) * inv_hx;
-    ou.w = u4.w - (b1.y - a1.y) * inv_hx;
-    ov.x = v4.x - (a0.y - a0.x) * inv_hy;
-    ov.y = v4.y - (a1.x - a0.y) * inv_hy;
-    ov.z = v4.z - (a1.y - a1.x) * inv_hy;
-    ov.w = v4.w - (a2 - a1.y) * inv_hy;
-    stg4(uo + off, ou);
-    stg4(vo + off, ov);
-    if (qo != nullptr) stg4(qo + off, make_float4(a0.x, a0.y, a1.x, a1.y));
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Q: gather ROWS rows of T, inverse real FFT, write q rows (coalesced).  No halo row, no
 // redundant transform; the pressure-gradient correction is applied either by correct2d_kernel or
 // lazily by the next step's explicit kernel (explicit_2d.cu, LAZY mode).
@@ -621,28 +531,6 @@ int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t l
 }
 
 template <int LM>
-int launch_irfft_correct_t(cudaStream_t st, const float2* T, const float* us, const float* vs,
-                           float* uo, float* vo, float* qo, int batch, int Nx, const float2* tw,
-                           const float2* rtw, float inv_hx, float inv_hy) {
-  using P = FftPlan<LM>;
-  constexpr int ROWS_MAX = rows_for(LM);
-  constexpr int RP = ROWS_MAX < 2 ? 2 : ROWS_MAX;  // R = RP - 1 output rows per CTA
-  if constexpr (RP * P::G > 1024) {
-    return set_error_msg("last grid axis too long for the inverse row kernel (max 16384)");
-  } else {
-    constexpr size_t smem = (size_t)RP * row_stride(P::M, RP) * sizeof(float2);
-    auto k = irfft_rows_correct_kernel<LM, RP>;
-    if (int e = set_smem(k, smem)) return e;
-    constexpr int R = RP - 1;
-    k<<<dim3((Nx + R - 1) / R, batch), RP * P::G, smem, st>>>(T, us, vs, uo, vo, qo, Nx, tw, rtw,
-                                                            inv_hx, inv_hy);
-    count_launch();
-    CFD_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
-}
-
-template <int LM>
 int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, int Nx,
                         const float2* tw, const float2* rtw) {
   constexpr int ROWS_MAX = rows_for(LM);
@@ -737,14 +625,6 @@ int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const
   for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
   return launch_xlines_peers(st, lm_x, peers, lm_x, 0, (size_t)batch * My, My, tw, lamx, lamy, lamxf,
                              lamyf, fastd, cutoff, norm, scratch, wbig, side);
-}
-int launch_irfft_correct(cudaStream_t st, int lm_row, const float2* T, const float* us,
-                         const float* vs, float* uo, float* vo, float* qo, int batch, int Nx,
-                         const float2* tw, const float2* rtw, float inv_hx, float inv_hy) {
-  CFD_DISPATCH_LM(lm_row, 4, 14,
-                  return launch_irfft_correct_t<LM_>(st, T, us, vs, uo, vo, qo, batch, Nx, tw, rtw,
-                                                     inv_hx, inv_hy));
-  return 0;
 }
 int launch_divergence_2d(cudaStream_t st, const float* u, const float* v, float* rhs, int batch,
                          int Nx, int Ny, float inv_hx, float inv_hy) {
