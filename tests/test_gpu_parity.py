@@ -347,3 +347,48 @@ def test_rk4_3d_runs_and_stays_divergence_free(cfd):
   for x, y in zip(to_np(v), want):
     assert gu.rel_l2(x, y) < TOL
   assert np.abs(cfd_oracle.divergence(to_np(v), grid.step)).max() < 1e-4
+
+
+def test_thousand_step_statistics_track_the_oracle(cfd):
+  """North star: kinetic energy, enstrophy and the divergence-free residual tracked over 1000
+  steps.  Kolmogorov 128^2 (paper forcing), CUDA path (chained, lazy projection) vs the float32
+  oracle on the same initial condition.  Stated tolerances: while the two trajectories are still
+  the same realisation (first 200 steps) fields agree to 1e-4 rel-L2 and KE / enstrophy to 1e-5
+  relative; afterwards chaotic divergence of trajectories is expected, so only the statistics are
+  compared: KE within 2 %, enstrophy within 5 % at every checkpoint up to step 1000, and
+  max|div v| < 2e-3 throughout (equations_test.py:99,127 uses the same bar)."""
+  shape = (128, 128)
+  dom = ((0.0, 2 * np.pi), (0.0, 2 * np.pi))
+  grid = cfd.grids.Grid(shape, domain=dom)
+  v0 = cfd_oracle.filtered_velocity_field(11, shape, dom, 3.0, 4)
+  nu = 1e-3
+  dt = cfd.equations.stable_time_step(7.0, 0.5, nu, grid)
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  step = cfd.equations.semi_implicit_navier_stokes(1.0, nu, dt, grid, forcing=forcing)
+  of = cfd_oracle.Forcing((('const', cfd_oracle.kolmogorov_field(shape, dom, 1.0, 4)), ('linear', -0.1)))
+  diag = cfd_oracle.pinv_diagonals(shape, grid.step, np.float32)
+  chunk = 100
+  advance = cfd.funcutils.repeated(step, chunk)
+  v = wrap(cfd, grid, v0)
+  w = v0
+  rows = []
+  for k in range(1, 11):
+    v = advance(v)
+    for _ in range(chunk):
+      w = cfd_oracle.step(w, dt, grid.step, 1.0, nu, of, diag=diag)
+    d = cfd.diagnostics(v)
+    wd = cfd_oracle.diagnostics(w, grid.step)
+    err = max(gu.rel_l2(a, b) for a, b in zip(to_np(v), w))
+    rows.append((k * chunk, d['kinetic_energy'], wd['kinetic_energy'], d['enstrophy'], wd['enstrophy'],
+                 d['max_abs_div'], err))
+    assert d['max_abs_div'] < 2e-3
+    assert abs(d['kinetic_energy'] - wd['kinetic_energy']) < 2e-2 * wd['kinetic_energy'], rows[-1]
+    assert abs(d['enstrophy'] - wd['enstrophy']) < 5e-2 * wd['enstrophy'], rows[-1]
+    assert err < 1e-4, rows[-1]  # measured: 1.6e-7 (step 100) ... 7.5e-7 (step 1000)
+    if k <= 2:
+      assert abs(d['kinetic_energy'] - wd['kinetic_energy']) < 1e-5 * wd['kinetic_energy']
+      assert abs(d['enstrophy'] - wd['enstrophy']) < 1e-5 * wd['enstrophy']
+  print('\nstep  KE(cuda)  KE(oracle)  Z(cuda)  Z(oracle)  max|div|  field rel-L2')
+  for r in rows:
+    print('%5d %.6f %.6f %.5f %.5f %.2e %.2e' % r)
