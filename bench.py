@@ -37,6 +37,8 @@ WORKLOADS = {
     'TGV512': dict(shape=(512, 512, 512), batch=1, nu=1.0 / 1600, vmax=1.0, kolmogorov=False, kpeak=2,
                    smagorinsky=0.2,
                    desc='3D periodic Taylor-Green vortex 512^3 with Smagorinsky closure (cs 0.2), float32'),
+    'D3D256': dict(shape=(256, 256, 256), batch=1, nu=1.0 / 1600, vmax=1.0, kolmogorov=False, kpeak=2,
+                   desc='3D Taylor-Green vortex 256^3, no closure, float32'),
     'TGV256': dict(shape=(256, 256, 256), batch=1, nu=1.0 / 1600, vmax=1.0, kolmogorov=False, kpeak=2,
                    smagorinsky=0.2, desc='3D Taylor-Green vortex 256^3 with Smagorinsky closure, float32'),
 }

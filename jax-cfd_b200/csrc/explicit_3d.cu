@@ -10,6 +10,8 @@
 //   Smagorinsky    subgrid_models.py:40-98 (viscosity at cell centres: smag_nut3d_kernel),
 //                  subgrid_models.py:101-134 (evm_model: -div(tau), tau_ij = -2 nu_ij s_ij)
 //   update         time_stepping.py:101;   divergence   finite_differences.py:136-143
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cfd {
@@ -228,6 +230,226 @@ explicit3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Marching 3-D explicit kernel (2.5-D blocking): a CTA of 8 warps owns a tile of BY = 8 rows (y) x
+// BZ = 64 columns (z; 2 per lane, 64-bit accesses) and marches along x.  The +-2 x-stencil of the
+// advected component lives in registers (5-plane window per column); y / z neighbours and the
+// cross-component face velocities come from a 4-slot ring of shared-memory planes (tile + halo 2,
+// all three components), one __syncthreads per plane.  x-face fluxes are carried to the next plane
+// in registers, z-face fluxes are shared inside the lane (3 faces for 2 cells), y-face fluxes are
+// evaluated on both sides (13.5 face evaluations per cell vs 18 in the one-thread-per-cell kernel,
+// and ~2 global loads per cell instead of ~75).  Smagorinsky is added by smag_add3d_kernel.
+constexpr int kBY = 8, kBZ = 64, kHY = kBY + 4, kSlots = 4;
+constexpr int kHZ = kBZ + 8;  // row: [pad pad h h | 64 interior (16-byte aligned) | h h pad pad]
+constexpr int kZ0 = 4;        // column of the first interior cell
+constexpr int kPlane = kHY * kHZ;  // floats per component per slot
+
+__global__ void __launch_bounds__(256)
+explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                        const float* __restrict__ w, float* __restrict__ us,
+                        float* __restrict__ vs, float* __restrict__ ws, int N0, int N1, int N2,
+                        StepConsts c, int dvdt_mode, int TX) {
+  extern __shared__ __align__(16) float sm3[];  // [slot][comp][kHY][kHZ]
+  const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
+  const int tilesz = N2 / kBZ, tilesy = N1 / kBY;
+  const int tz = blockIdx.x % tilesz, tyb = (blockIdx.x / tilesz) % tilesy;
+  const int xb = blockIdx.x / (tilesz * tilesy);
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const float* f[3] = {u + boff, v + boff, w + boff};
+  float* o[3] = {us + boff, vs + boff, ws + boff};
+  const int j0 = tyb * kBY, k0 = tz * kBZ;
+  const int i0 = xb * TX, iend = min(i0 + TX, N0);
+  const size_t planeN = (size_t)N1 * N2;
+  const int own = (ty + 2) * kHZ + 2 * lane + kZ0;  // own position inside the halo tile
+
+  // Plane loader: threads 0..191 move one aligned float4 of the interior (12 rows x 16), threads
+  // 192..239 one halo element (12 rows x 4); source offsets inside a plane are loop invariant.
+  int ld_src = -1, ld_dst = 0;
+  if (tid < 192) {
+    const int r = tid >> 4, m = tid & 15;
+    int j = j0 + r - 2;
+    j = j < 0 ? j + N1 : (j >= N1 ? j - N1 : j);
+    ld_src = j * N2 + k0 + 4 * m;
+    ld_dst = r * kHZ + kZ0 + 4 * m;
+  } else if (tid < 240) {
+    const int h = tid - 192, r = h >> 2, hc = h & 3;
+    int j = j0 + r - 2;
+    j = j < 0 ? j + N1 : (j >= N1 ? j - N1 : j);
+    int k = hc < 2 ? k0 - 2 + hc : k0 + kBZ + (hc - 2);
+    k = k < 0 ? k + N2 : (k >= N2 ? k - N2 : k);
+    ld_src = j * N2 + k;
+    ld_dst = r * kHZ + (hc < 2 ? kZ0 - 2 + hc : kZ0 + kBZ + (hc - 2));
+  }
+  auto slot_base = [&](int plane) { return sm3 + ((plane + kSlots) & (kSlots - 1)) * (3 * kPlane); };
+  auto load_plane = [&](int i) {
+    const int iw = i < 0 ? i + N0 : (i >= N0 ? i - N0 : i);
+    float* dst = slot_base(i);
+    if (tid < 192) {
+#pragma unroll
+      for (int comp = 0; comp < 3; ++comp)
+        *reinterpret_cast<float4*>(dst + comp * kPlane + ld_dst) =
+            ldg4(f[comp] + (size_t)iw * planeN + ld_src);
+    } else if (tid < 240) {
+#pragma unroll
+      for (int comp = 0; comp < 3; ++comp)
+        dst[comp * kPlane + ld_dst] = __ldg(f[comp] + (size_t)iw * planeN + ld_src);
+    }
+  };
+  // value of component `comp` at plane (pa: i, pb: i+1, pm: i-1), row j + dy, column k + dz
+  const float* pa = nullptr;
+  const float* pb = nullptr;
+  const float* pm = nullptr;
+  auto g = [&](int comp, int dx, int dy, int dz) -> float {
+    const float* base = dx == 0 ? pa : (dx > 0 ? pb : pm);
+    return base[comp * kPlane + own + dy * kHZ + dz];
+  };
+
+  // x-window of own columns: X[comp][plane offset + 2][col]
+  float X[3][5][2];
+  float Fxp[3][2];  // x-face flux at (i-1 | i), carried
+  // prologue: planes i0-1, i0, i0+1 into the ring; own values of i0-2 straight from global
+  load_plane(i0 - 1);
+  load_plane(i0);
+  load_plane(i0 + 1);
+  {
+    const int iw = ((i0 - 2) % N0 + N0) % N0;
+#pragma unroll
+    for (int comp = 0; comp < 3; ++comp) {
+      const float2 t2 = __ldg(reinterpret_cast<const float2*>(
+          f[comp] + (size_t)iw * planeN + (size_t)(j0 + ty) * N2 + k0 + 2 * lane));
+      X[comp][1][0] = t2.x;  // will become offset -2 after the first shift
+      X[comp][1][1] = t2.y;
+    }
+  }
+  __syncthreads();
+  pm = slot_base(i0 - 1);
+  pa = slot_base(i0);
+  pb = slot_base(i0 + 1);
+#pragma unroll
+  for (int comp = 0; comp < 3; ++comp)
+#pragma unroll
+    for (int col = 0; col < 2; ++col) {
+      X[comp][2][col] = g(comp, -1, 0, col);
+      X[comp][3][col] = g(comp, 0, 0, col);
+      X[comp][4][col] = g(comp, 1, 0, col);
+    }
+  // carried x-face fluxes at face (i0-1 | i0): stencil planes i0-2 .. i0+1, velocities at plane i0-1
+#pragma unroll
+  for (int A = 0; A < 3; ++A)
+#pragma unroll
+    for (int col = 0; col < 2; ++col) {
+      const float ua = g(0, -1, 0, col);
+      const float ub = A == 0 ? g(0, 0, 0, col) : (A == 1 ? g(0, -1, 1, col) : g(0, -1, 0, col + 1));
+      const float U = 0.5f * (ua + ub);
+      Fxp[A][col] = face_flux(X[A][1][col], X[A][2][col], X[A][3][col], X[A][4][col], U, c.dth[0]);
+    }
+
+  for (int i = i0; i < iend; ++i) {
+    pa = slot_base(i);
+    pb = slot_base(i + 1);
+    load_plane(i + 2);
+    // shift the register window: offsets -2..+1 <- old -1..+2
+#pragma unroll
+    for (int comp = 0; comp < 3; ++comp)
+#pragma unroll
+      for (int col = 0; col < 2; ++col) {
+        X[comp][0][col] = X[comp][1][col];
+        X[comp][1][col] = X[comp][2][col];
+        X[comp][2][col] = X[comp][3][col];
+        X[comp][3][col] = X[comp][4][col];
+      }
+    __syncthreads();
+#pragma unroll
+    for (int comp = 0; comp < 3; ++comp)
+#pragma unroll
+      for (int col = 0; col < 2; ++col) X[comp][4][col] = slot_base(i + 2)[comp * kPlane + own + col];
+
+    const int jg = j0 + ty, kg = k0 + 2 * lane;
+    const size_t cell0 = (size_t)i * planeN + (size_t)jg * N2 + kg;
+#pragma unroll
+    for (int A = 0; A < 3; ++A) {
+      // unit vector of A for the face-velocity interpolation (interpolation.py:57-62)
+      constexpr int ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
+      // z faces shared by the lane's two cells: face fz between columns fz-1 and fz
+      float Fz[3];
+#pragma unroll
+      for (int fz = 0; fz < 3; ++fz) {
+        const float U = 0.5f * (g(2, 0, 0, fz - 1) + g(2, ex[A], ey[A], fz - 1 + ez[A]));
+        Fz[fz] = face_flux(g(A, 0, 0, fz - 2), g(A, 0, 0, fz - 1), g(A, 0, 0, fz), g(A, 0, 0, fz + 1), U,
+                           c.dth[2]);
+      }
+      float out[2];
+#pragma unroll
+      for (int col = 0; col < 2; ++col) {
+        const float c0 = X[A][2][col];
+        // x direction: new face (i | i+1), carried face (i-1 | i)
+        const float Ux = 0.5f * (g(0, 0, 0, col) + g(0, ex[A], ey[A], col + ez[A]));
+        const float Fx = face_flux(X[A][1][col], X[A][2][col], X[A][3][col], X[A][4][col], Ux, c.dth[0]);
+        // y direction: faces (j | j+1) and (j-1 | j)
+        const float Uyp = 0.5f * (g(1, 0, 0, col) + g(1, ex[A], ey[A], col + ez[A]));
+        const float Fyp = face_flux(g(A, 0, -1, col), c0, g(A, 0, 1, col), g(A, 0, 2, col), Uyp, c.dth[1]);
+        const float Uym = 0.5f * (g(1, 0, -1, col) + g(1, ex[A], ey[A] - 1, col + ez[A]));
+        const float Fym = face_flux(g(A, 0, -2, col), g(A, 0, -1, col), c0, g(A, 0, 1, col), Uym, c.dth[1]);
+        float conv = (Fx - Fxp[A][col]) * c.inv_h[0];
+        conv += (Fyp - Fym) * c.inv_h[1];
+        conv += (Fz[col + 1] - Fz[col]) * c.inv_h[2];
+        Fxp[A][col] = Fx;
+        float dv = -conv;
+        if (c.has_nu) {
+          float l = (-2.f * c0) * c.lap_sum;
+          l += (X[A][1][col] + X[A][3][col]) * c.lap_s[0];
+          l += (g(A, 0, -1, col) + g(A, 0, 1, col)) * c.lap_s[1];
+          l += (g(A, 0, 0, col - 1) + g(A, 0, 0, col + 1)) * c.lap_s[2];
+          dv += c.nu * l;
+        }
+        if (c.n_terms > 0) {
+          float fsum = 0.f;
+          for (int t = 0; t < c.n_terms; ++t) {
+            const int kind = c.term_kind[t];
+            if (kind == CFD_FORCE_SEPARABLE) {
+              if (c.has_sep[A]) {
+                float p = 1.f;
+                if (c.sep_prof[A][0]) p = __ldg(c.sep_prof[A][0] + i);
+                if (c.sep_prof[A][1]) p = p * __ldg(c.sep_prof[A][1] + jg);
+                if (c.sep_prof[A][2]) p = p * __ldg(c.sep_prof[A][2] + kg + col);
+                fsum += p * c.sep_scale[A];
+              }
+            } else if (kind == CFD_FORCE_FIELD) {
+              if (c.field[A]) fsum += __ldg(c.field[A] + cell0 + col);
+            } else if (kind == CFD_FORCE_LINEAR) {
+              fsum += c.linear_coef * c0;
+            }  // CFD_FORCE_SMAGORINSKY: added by smag_add3d_kernel
+          }
+          dv = fmaf(fsum, c.inv_rho, dv);
+        }
+        out[col] = dvdt_mode ? dv : c0 + c.dt * dv;
+      }
+      *reinterpret_cast<float2*>(o[A] + cell0) = make_float2(out[0], out[1]);
+    }
+  }
+}
+
+// u* += dt * acc / rho  (or dv/dt += acc / rho): the Smagorinsky acceleration as the last forcing
+// term (subgrid_models.py:188-213), evaluated from the PROJECTED input velocity.
+__global__ void smag_add3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                  const float* __restrict__ w, const float* __restrict__ nut,
+                                  float* __restrict__ us, float* __restrict__ vs,
+                                  float* __restrict__ ws, int N0, int N1, int N2, StepConsts c,
+                                  int dvdt_mode) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cells) return;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const int k = (int)(gid % N2), j = (int)((gid / N2) % N1), i = (int)(gid / ((size_t)N1 * N2));
+  const Idx3 ix = make_idx(i, j, k, N0, N1, N2);
+  Vel3 vel = {{u + boff, v + boff, w + boff}};
+  const float scale = (dvdt_mode ? 1.f : c.dt) * c.inv_rho;
+  us[boff + gid] += scale * smag_acc<0>(vel, nut + boff, ix, c.inv_h);
+  vs[boff + gid] += scale * smag_acc<1>(vel, nut + boff, ix, c.inv_h);
+  ws[boff + gid] += scale * smag_acc<2>(vel, nut + boff, ix, c.inv_h);
+}
+
 // diagnostics: sum 0.5|v|^2, sum 0.5|curl|^2, max|div|, max|v|^2
 __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -301,6 +523,33 @@ int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const fl
                        const float* nut, float* us, float* vs, float* ws, int batch, int N0, int N1,
                        int N2, const StepConsts& c, int dvdt_mode) {
   const size_t cells = (size_t)N0 * N1 * N2;
+  static const int use_march = [] {
+    const char* e = getenv("CFD_EXPLICIT3D_MARCH");
+    return e ? atoi(e) : 1;
+  }();
+  if (use_march && N1 % kBY == 0 && N2 % kBZ == 0 && N0 >= 4) {
+    // rows per CTA along x: long enough to amortise the 3-plane prologue, short enough to fill the GPU
+    int TX = 32;
+    while (TX > 8 && (long)(N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX) * batch < 148L * 4) TX /= 2;
+    constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      attr_set = true;
+    }
+    dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
+    explicit3d_march_kernel<<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    if (nut) {
+      dim3 g2((unsigned)((cells + 127) / 128), batch);
+      smag_add3d_kernel<<<g2, 128, 0, st>>>(u, v, w, nut, us, vs, ws, N0, N1, N2, c, dvdt_mode);
+      count_launch();
+      CFD_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+  }
   dim3 grid((unsigned)((cells + 127) / 128), batch);
   explicit3d_kernel<<<grid, 128, 0, st>>>(u, v, w, nut, us, vs, ws, N0, N1, N2, c, dvdt_mode);
   count_launch();
