@@ -450,6 +450,118 @@ __global__ void smag_add3d_kernel(const float* __restrict__ u, const float* __re
   ws[boff + gid] += scale * smag_acc<2>(vel, nut + boff, ix, c.inv_h);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Smagorinsky through strain FIELDS (what the reference itself does, subgrid_models.py:124-134):
+// three streaming kernels instead of recomputing every strain sample from velocities per cell.
+//   S[0..5] = s00, s11, s22, s01, s02, s12 at their natural offsets;  nu_t at centres;
+//   acc_i = -sum_j (tau_ij - S(tau_ij, -1, j)) / h_j  with tau_ij = -2 nu_ij s_ij.
+struct Sf {
+  const float* s[6];
+};
+struct SfOut {
+  float* s[6];
+};
+__device__ __forceinline__ int sidx(int i, int j) {  // field index of s_ij (symmetric)
+  return i == j ? i : (i + j + 2);                   // (0,1)->3 (0,2)->4 (1,2)->5
+}
+
+__global__ void smag_strain3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                     const float* __restrict__ w, SfOut out, int N0, int N1, int N2,
+                                     StepConsts c) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cells) return;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const int k = (int)(gid % N2), j = (int)((gid / N2) % N1), i = (int)(gid / ((size_t)N1 * N2));
+  const Idx3 ix = make_idx(i, j, k, N0, N1, N2);
+  Vel3 vel = {{u + boff, v + boff, w + boff}};
+  out.s[0][boff + gid] = strain<0, 0>(vel, ix, 0, 0, 0, c.inv_h);
+  out.s[1][boff + gid] = strain<1, 1>(vel, ix, 0, 0, 0, c.inv_h);
+  out.s[2][boff + gid] = strain<2, 2>(vel, ix, 0, 0, 0, c.inv_h);
+  out.s[3][boff + gid] = strain<0, 1>(vel, ix, 0, 0, 0, c.inv_h);
+  out.s[4][boff + gid] = strain<0, 2>(vel, ix, 0, 0, 0, c.inv_h);
+  out.s[5][boff + gid] = strain<1, 2>(vel, ix, 0, 0, 0, c.inv_h);
+}
+
+// s_IJ field interpolated to the cell centre (same operation order as strain_center)
+template <int I, int J>
+__device__ __forceinline__ float sfield_center(const float* __restrict__ S, const Idx3& ix) {
+  if (I == J) {
+    int d[3] = {0, 0, 0};
+    d[I] = -1;
+    return at(S, ix, d[0], d[1], d[2]);
+  }
+  constexpr int A = I < J ? I : J, B = I < J ? J : I;
+  float r[2];
+#pragma unroll
+  for (int sb = 0; sb < 2; ++sb) {
+    int d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+    d0[B] = d1[B] = sb - 1;
+    d0[A] = -1;
+    r[sb] = 0.5f * at(S, ix, d0[0], d0[1], d0[2]) + 0.5f * at(S, ix, d1[0], d1[1], d1[2]);
+  }
+  return 0.5f * r[0] + 0.5f * r[1];
+}
+
+__global__ void smag_nut_fields_kernel(Sf S, float* __restrict__ nut, int N0, int N1, int N2,
+                                       StepConsts c) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cells) return;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const int k = (int)(gid % N2), j = (int)((gid / N2) % N1), i = (int)(gid / ((size_t)N1 * N2));
+  const Idx3 ix = make_idx(i, j, k, N0, N1, N2);
+  const float s00 = sfield_center<0, 0>(S.s[0] + boff, ix), s11 = sfield_center<1, 1>(S.s[1] + boff, ix),
+              s22 = sfield_center<2, 2>(S.s[2] + boff, ix);
+  const float s01 = sfield_center<0, 1>(S.s[3] + boff, ix), s02 = sfield_center<0, 2>(S.s[4] + boff, ix),
+              s12 = sfield_center<1, 2>(S.s[5] + boff, ix);
+  const float r0 = s00 * s00 + s01 * s01 + s02 * s02;
+  const float r1 = s01 * s01 + s11 * s11 + s12 * s12;
+  const float r2 = s02 * s02 + s12 * s12 + s22 * s22;
+  nut[boff + gid] = c.smag_coef * sqrtf(2.f * ((r0 + r1) + r2));
+}
+
+template <int I, int J>
+__device__ __forceinline__ float tau_f(const Sf& S, size_t boff, const float* __restrict__ nut,
+                                       const Idx3& ix, int p0, int p1, int p2) {
+  return -2.f * nu_at<I, J>(nut, ix, p0, p1, p2) * at(S.s[I == J ? I : (I + J + 2)] + boff, ix, p0, p1, p2);
+}
+
+__global__ void smag_acc_fields_kernel(Sf S, const float* __restrict__ nut, float* __restrict__ us,
+                                       float* __restrict__ vs, float* __restrict__ ws, int N0, int N1,
+                                       int N2, StepConsts c, int dvdt_mode) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cells) return;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const int k = (int)(gid % N2), j = (int)((gid / N2) % N1), i = (int)(gid / ((size_t)N1 * N2));
+  const Idx3 ix = make_idx(i, j, k, N0, N1, N2);
+  const float* nu = nut + boff;
+  // every distinct tau sample once (tau_ij == tau_ji)
+  const float t00 = tau_f<0, 0>(S, boff, nu, ix, 0, 0, 0), t00m = tau_f<0, 0>(S, boff, nu, ix, -1, 0, 0);
+  const float t11 = tau_f<1, 1>(S, boff, nu, ix, 0, 0, 0), t11m = tau_f<1, 1>(S, boff, nu, ix, 0, -1, 0);
+  const float t22 = tau_f<2, 2>(S, boff, nu, ix, 0, 0, 0), t22m = tau_f<2, 2>(S, boff, nu, ix, 0, 0, -1);
+  const float t01 = tau_f<0, 1>(S, boff, nu, ix, 0, 0, 0), t01x = tau_f<0, 1>(S, boff, nu, ix, -1, 0, 0),
+              t01y = tau_f<0, 1>(S, boff, nu, ix, 0, -1, 0);
+  const float t02 = tau_f<0, 2>(S, boff, nu, ix, 0, 0, 0), t02x = tau_f<0, 2>(S, boff, nu, ix, -1, 0, 0),
+              t02z = tau_f<0, 2>(S, boff, nu, ix, 0, 0, -1);
+  const float t12 = tau_f<1, 2>(S, boff, nu, ix, 0, 0, 0), t12y = tau_f<1, 2>(S, boff, nu, ix, 0, -1, 0),
+              t12z = tau_f<1, 2>(S, boff, nu, ix, 0, 0, -1);
+  float d0 = (t00 - t00m) * c.inv_h[0];
+  d0 += (t01 - t01y) * c.inv_h[1];
+  d0 += (t02 - t02z) * c.inv_h[2];
+  float d1 = (t01 - t01x) * c.inv_h[0];
+  d1 += (t11 - t11m) * c.inv_h[1];
+  d1 += (t12 - t12z) * c.inv_h[2];
+  float d2 = (t02 - t02x) * c.inv_h[0];
+  d2 += (t12 - t12y) * c.inv_h[1];
+  d2 += (t22 - t22m) * c.inv_h[2];
+  const float scale = (dvdt_mode ? 1.f : c.dt) * c.inv_rho;
+  us[boff + gid] += scale * (-d0);
+  vs[boff + gid] += scale * (-d1);
+  ws[boff + gid] += scale * (-d2);
+}
+
 // diagnostics: sum 0.5|v|^2, sum 0.5|curl|^2, max|div|, max|v|^2
 __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -509,25 +621,44 @@ __global__ void diag3d_kernel(const float* __restrict__ u, const float* __restri
 
 }  // namespace
 
+// sfield != nullptr: 6 strain fields of batch * cells floats each (strain-field path)
 int launch_smag_nut_3d(cudaStream_t st, const float* u, const float* v, const float* w, float* nut,
-                       int batch, int N0, int N1, int N2, const StepConsts& c) {
+                       float* sfield, int batch, int N0, int N1, int N2, const StepConsts& c) {
   const size_t cells = (size_t)N0 * N1 * N2;
   dim3 grid((unsigned)((cells + 127) / 128), batch);
+  if (sfield) {
+    SfOut so;
+    Sf si;
+    for (int q = 0; q < 6; ++q) {
+      so.s[q] = sfield + (size_t)q * batch * cells;
+      si.s[q] = so.s[q];
+    }
+    smag_strain3d_kernel<<<grid, 128, 0, st>>>(u, v, w, so, N0, N1, N2, c);
+    count_launch();
+    smag_nut_fields_kernel<<<grid, 128, 0, st>>>(si, nut, N0, N1, N2, c);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   smag_nut3d_kernel<<<grid, 128, 0, st>>>(u, v, w, nut, N0, N1, N2, c);
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const float* w,
-                       const float* nut, float* us, float* vs, float* ws, int batch, int N0, int N1,
-                       int N2, const StepConsts& c, int dvdt_mode) {
-  const size_t cells = (size_t)N0 * N1 * N2;
+bool explicit_3d_uses_march(int N0, int N1, int N2) {
   static const int use_march = [] {
     const char* e = getenv("CFD_EXPLICIT3D_MARCH");
     return e ? atoi(e) : 1;
   }();
-  if (use_march && N1 % kBY == 0 && N2 % kBZ == 0 && N0 >= 4) {
+  return use_march && N1 % kBY == 0 && N2 % kBZ == 0 && N0 >= 4;
+}
+
+int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const float* w,
+                       const float* nut, const float* sfield, float* us, float* vs, float* ws,
+                       int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode) {
+  const size_t cells = (size_t)N0 * N1 * N2;
+  if (explicit_3d_uses_march(N0, N1, N2)) {
     // rows per CTA along x: long enough to amortise the 3-plane prologue, short enough to fill the GPU
     int TX = 32;
     while (TX > 8 && (long)(N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX) * batch < 148L * 4) TX /= 2;
@@ -542,7 +673,14 @@ int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const fl
     explicit3d_march_kernel<<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
     count_launch();
     CFD_CUDA_OK(cudaGetLastError());
-    if (nut) {
+    if (nut && sfield) {
+      dim3 g2((unsigned)((cells + 127) / 128), batch);
+      Sf si;
+      for (int q = 0; q < 6; ++q) si.s[q] = sfield + (size_t)q * batch * cells;
+      smag_acc_fields_kernel<<<g2, 128, 0, st>>>(si, nut, us, vs, ws, N0, N1, N2, c, dvdt_mode);
+      count_launch();
+      CFD_CUDA_OK(cudaGetLastError());
+    } else if (nut) {
       dim3 g2((unsigned)((cells + 127) / 128), batch);
       smag_add3d_kernel<<<g2, 128, 0, st>>>(u, v, w, nut, us, vs, ws, N0, N1, N2, c, dvdt_mode);
       count_launch();

@@ -53,10 +53,11 @@ int launch_correct_3d(cudaStream_t, const float* us, const float* vs, const floa
                       float* uo, float* vo, float* wo, int batch, int N0, int N1, int N2, float ihx,
                       float ihy, float ihz);
 int launch_smag_nut_3d(cudaStream_t, const float* u, const float* v, const float* w, float* nut,
-                       int batch, int N0, int N1, int N2, const StepConsts& c);
+                       float* sfield, int batch, int N0, int N1, int N2, const StepConsts& c);
 int launch_explicit_3d(cudaStream_t, const float* u, const float* v, const float* w, const float* nut,
-                       float* us, float* vs, float* ws, int batch, int N0, int N1, int N2,
-                       const StepConsts& c, int dvdt_mode);
+                       const float* sfield, float* us, float* vs, float* ws, int batch, int N0, int N1,
+                       int N2, const StepConsts& c, int dvdt_mode);
+bool explicit_3d_uses_march(int N0, int N1, int N2);
 int launch_diag_3d(cudaStream_t, const float* u, const float* v, const float* w, int batch, int N0,
                    int N1, int N2, float ihx, float ihy, float ihz, double* out4);
 
@@ -284,22 +285,37 @@ int solve_3d(cfd_plan* p, cudaStream_t st, float* q) {
   return 0;
 }
 
+// Smagorinsky workspace: nu_t always; the six strain fields when the marching kernel (and with it
+// the strain-field path) is used
+int smag_buffers(cfd_plan* p, const StepConsts& c, float** nut, float** sfield) {
+  *nut = nullptr;
+  *sfield = nullptr;
+  bool smag = false;
+  for (int t = 0; t < c.n_terms; ++t) smag = smag || c.term_kind[t] == CFD_FORCE_SMAGORINSKY;
+  if (!smag) return 0;
+  const size_t fbytes = (size_t)p->batch * p->cells * sizeof(float);
+  if (!p->nut) CFD_CUDA_OK(cudaMalloc((void**)&p->nut, fbytes));
+  *nut = p->nut;
+  if (explicit_3d_uses_march((int)p->shape[0], (int)p->shape[1], (int)p->shape[2])) {
+    if (!p->sfield) CFD_CUDA_OK(cudaMalloc((void**)&p->sfield, 6 * fbytes));
+    *sfield = p->sfield;
+  }
+  return 0;
+}
+
 int step_3d(cfd_plan* p, cudaStream_t st, const float* const* v_in, float* const* v_out, float* q_out,
             const StepConsts& c) {
   const int N0 = (int)p->shape[0], N1 = (int)p->shape[1], N2 = (int)p->shape[2];
   const float ih[3] = {(float)(1.0 / p->step[0]), (float)(1.0 / p->step[1]), (float)(1.0 / p->step[2])};
   float* nut = nullptr;
-  for (int t = 0; t < c.n_terms; ++t)
-    if (c.term_kind[t] == CFD_FORCE_SMAGORINSKY) {
-      if (!p->nut) CFD_CUDA_OK(cudaMalloc((void**)&p->nut, (size_t)p->batch * p->cells * sizeof(float)));
-      nut = p->nut;
-    }
+  float* sfield = nullptr;
+  if (int e = smag_buffers(p, c, &nut, &sfield)) return e;
   prof_mark(p, st, "begin");
   if (nut) {
-    if (int e = launch_smag_nut_3d(st, v_in[0], v_in[1], v_in[2], nut, p->batch, N0, N1, N2, c)) return e;
+    if (int e = launch_smag_nut_3d(st, v_in[0], v_in[1], v_in[2], nut, sfield, p->batch, N0, N1, N2, c)) return e;
     prof_mark(p, st, "smag_nut");
   }
-  if (int e = launch_explicit_3d(st, v_in[0], v_in[1], v_in[2], nut, p->us[0], p->us[1], p->us[2],
+  if (int e = launch_explicit_3d(st, v_in[0], v_in[1], v_in[2], nut, sfield, p->us[0], p->us[1], p->us[2],
                                  p->batch, N0, N1, N2, c, 0))
     return e;
   prof_mark(p, st, "explicit_3d");
@@ -459,6 +475,7 @@ void cfd_plan_destroy(cfd_plan* p) {
   cudaFree(p->tw_y);
   cudaFree(p->T2);
   cudaFree(p->nut);
+  cudaFree(p->sfield);
   cudaFree(p->rtw);
   for (int j = 0; j < CFD_MAX_DIM; ++j) {
     cudaFree(p->lam[j]);
@@ -578,15 +595,12 @@ int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
   if (p->ndim == 3) {
     const int N0 = (int)p->shape[0], N1 = (int)p->shape[1], N2 = (int)p->shape[2];
     float* nut = nullptr;
-    for (int t = 0; t < c.n_terms; ++t)
-      if (c.term_kind[t] == CFD_FORCE_SMAGORINSKY) {
-        if (!p->nut) CFD_CUDA_OK(cudaMalloc((void**)&p->nut, (size_t)p->batch * p->cells * sizeof(float)));
-        nut = p->nut;
-      }
+    float* sfield = nullptr;
+    if (int e = smag_buffers(p, c, &nut, &sfield)) return e;
     if (nut)
-      if (int e = launch_smag_nut_3d((cudaStream_t)stream, v_in[0], v_in[1], v_in[2], nut, p->batch, N0, N1, N2, c))
+      if (int e = launch_smag_nut_3d((cudaStream_t)stream, v_in[0], v_in[1], v_in[2], nut, sfield, p->batch, N0, N1, N2, c))
         return e;
-    return launch_explicit_3d((cudaStream_t)stream, v_in[0], v_in[1], v_in[2], nut, dvdt_out[0],
+    return launch_explicit_3d((cudaStream_t)stream, v_in[0], v_in[1], v_in[2], nut, sfield, dvdt_out[0],
                               dvdt_out[1], dvdt_out[2], p->batch, N0, N1, N2, c, 1);
   }
   return launch_explicit_2d((cudaStream_t)stream, v_in[0], v_in[1], nullptr, dvdt_out[0],

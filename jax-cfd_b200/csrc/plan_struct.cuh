@@ -21,6 +21,7 @@ struct cfd_plan {
   float2* tw_y = nullptr;   // 3-D: complex lines along axis 1
   float2* T2 = nullptr;     // 3-D: second spectrum buffer
   float* nut = nullptr;     // 3-D: Smagorinsky eddy viscosity at cell centres
+  float* sfield = nullptr;  // 3-D: six strain-rate fields (strain-field Smagorinsky path)
   float2* rtw = nullptr;
   double* lam[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
   float* lamf[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // float32 copies for the fast path
