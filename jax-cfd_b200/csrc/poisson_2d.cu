@@ -155,9 +155,9 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
 // rank (x >> lnloc)'s buffer at [line][x & (Nloc-1)] -- so the loads/stores below ARE the
 // all-to-all transpose of the distributed FFT, done with peer accesses over NVLink inside the
 // kernel (each rank transforms its own range of ky lines).  One GPU: a single peer, Nloc = M.
-template <int LM, int LINES, bool FASTD, int LEMAX>
+template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT>
 __global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX>::G, (LEMAX == 5 && LINES * FftPlan<LM, LEMAX>::G <= 256) ? 2 : 1)
-xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My, int split,
+xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
               const float* __restrict__ lamyf, double cutoff, float norm) {
@@ -170,6 +170,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My, int split,
   // split == 1: the "lines" are the half-length lines (y0, y1 interleaved per original line) of
   // the 32768-point transform in a local scratch; original line = line_begin + (index >> 1).
   const size_t idx0 = (size_t)blockIdx.x * LINES;
+  constexpr bool split = SPLIT;
   const size_t line0 = split ? line_begin + (idx0 >> 1) : line_begin + idx0;
   const size_t line = split ? line_begin + ((idx0 + ln) >> 1) : line0 + ln;
   const int ky = (int)(line % My);
@@ -456,17 +457,23 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
   constexpr int LINES = (P::G >= 256) ? 1 : (256 / P::G > 16 ? 16 : 256 / P::G);
   constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
   if (nlines % LINES || (!split && line_begin % LINES)) return set_error_msg("internal: line count not divisible");
-  if (fastd) {
-    auto k = xlines_kernel<LM, LINES, true, LEMAX>;
+  auto go = [&](auto k) -> int {
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, split, tw, lamx,
-                                                            lamy, lamxf, lamyf, cutoff, norm);
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx, lamy,
+                                                            lamxf, lamyf, cutoff, norm);
+    return 0;
+  };
+  int e;
+  if constexpr (LM == 14) {  // split mode exists for the half-lines of 32768-point lines only
+    if (split)
+      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, true>) : go(xlines_kernel<LM, LINES, false, LEMAX, true>);
+    else
+      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false>);
   } else {
-    auto k = xlines_kernel<LM, LINES, false, LEMAX>;
-    if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, split, tw, lamx,
-                                                            lamy, lamxf, lamyf, cutoff, norm);
+    if (split) return set_error_msg("internal: split x lines need 16384-point transforms");
+    e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false>);
   }
+  if (e) return e;
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;
