@@ -257,15 +257,18 @@ def run_gpu_slab(args, wl, name):
   outs = st.store()
   loc = outs[0].numpy()
   # e2e at N GPUs: every step copies the rank's slab host->device, steps once, copies it back
-  hu, hv = outs[0].numpy(), outs[1].numpy()
+  pin_in = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
+  pin_out = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
+  pin_in[0].array[...] = outs[0].numpy()
+  pin_in[1].array[...] = outs[1].numpy()
   e2e_steps = 3
   barrier()
   t0 = time.perf_counter()
   for _ in range(e2e_steps):
-    st.load([hu, hv])
+    st.load([p.array for p in pin_in])
     st.advance(1)
-    o = st.store()
-    hu, hv = o[0].numpy(), o[1].numpy()
+    st.store(host_out=[p.array for p in pin_out])
+    pin_in, pin_out = pin_out, pin_in
   barrier()
   e2e_s = time.perf_counter() - t0
   te = torch.tensor([e2e_s], device='cuda')
@@ -305,7 +308,7 @@ def run_gpu_slab(args, wl, name):
         'e2e': {'value': cells * e2e_steps / e2e_s / 1e9, 'unit': 'Gcell*step/s',
                 'h2d_bytes_per_step': 2 * cells * 4, 'd2h_bytes_per_step': 2 * cells * 4,
                 'steps': e2e_steps, 'ms_per_step': e2e_s / e2e_steps * 1e3,
-                'api': 'SlabStepper.load(numpy) / advance(1) / store() -> numpy on every rank'},
+                'api': 'SlabStepper.load(pinned numpy) / advance(1) / store(host_out=pinned numpy) on every rank'},
         'gpu_launches': int(launches), 'clocks': clocks,
         'diagnostics_after': {'finite': finite, 'max_abs_u_rank0': umax},
     }

@@ -337,11 +337,22 @@ irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
   const size_t b = blockIdx.y;
   float2* s = smem + row * RS;
   {
+    // all of a thread's gather loads are issued before the first one is consumed (ROWS * M / NT
+    // = E of them): the transposed reads are the latency-critical start of this kernel
     const float2* Tb = T + b * (size_t)M * Nx + x0;
-#pragma unroll 4
-    for (int idx = tid; idx < ROWS * M; idx += NT) {
+    constexpr int NG = ROWS * M / NT;
+    float2 tmp[NG];
+#pragma unroll
+    for (int n = 0; n < NG; ++n) {
+      const int idx = tid + n * NT;
       const int r = idx % ROWS, ky = idx / ROWS;
-      smem[r * RS + PAD(ky)] = __ldg(Tb + (size_t)ky * Nx + r);
+      tmp[n] = __ldg(Tb + (size_t)ky * Nx + r);
+    }
+#pragma unroll
+    for (int n = 0; n < NG; ++n) {
+      const int idx = tid + n * NT;
+      const int r = idx % ROWS, ky = idx / ROWS;
+      smem[r * RS + PAD(ky)] = tmp[n];
     }
   }
   __syncthreads();

@@ -90,25 +90,45 @@ class SlabStepper:
                                                   _engine.as_forcing(forcing))
     self.stream = _lib.Stream()
 
+  def _staging(self):
+    if getattr(self, '_stage', None) is None:
+      self._stage = [_lib.DeviceArray(self.local_shape) for _ in range(2)]
+    return self._stage
+
   def load(self, v_local):
-    """v_local: the rank's rows of (u, v): numpy or device arrays of shape local_shape."""
-    arrs = [a if _lib.is_device_array(a) else _lib.DeviceArray.from_numpy(np.ascontiguousarray(a, np.float32))
-            for a in v_local]
-    for a in arrs:
+    """v_local: the rank's rows of (u, v): numpy (ideally pinned) or device arrays of local_shape."""
+    arrs = []
+    for a, stage in zip(v_local, self._staging()):
       assert tuple(a.shape) == self.local_shape, (a.shape, self.local_shape)
+      if _lib.is_device_array(a):
+        arrs.append(a)
+      else:
+        a = np.ascontiguousarray(a, np.float32)
+        check(lib().cfd_memcpy_h2d(stage.ptr, a.ctypes.data, a.nbytes, self.stream.handle))
+        arrs.append(stage)
     check(lib().cfd_dist_load(self.handle, self.stream.handle, _lib.ptr_array(arrs)))
     self.stream.sync()
 
   def advance(self, nsteps: int):
     check(lib().cfd_dist_advance(self.handle, self.stream.handle, nsteps, ctypes.byref(self.params)))
 
-  def store(self, want_q: bool = False):
-    outs = [_lib.DeviceArray(self.local_shape) for _ in range(2)]
+  def store(self, want_q: bool = False, host_out=None):
+    """Materialises the projected local rows.  host_out: optional pair of (pinned) numpy arrays to
+    receive them; otherwise device arrays are returned."""
+    if host_out is not None:
+      outs = self._staging()
+    else:
+      outs = [_lib.DeviceArray(self.local_shape) for _ in range(2)]
     q = _lib.DeviceArray(self.local_shape) if want_q else None
     check(lib().cfd_dist_store(self.handle, self.stream.handle, _lib.ptr_array(outs),
                                None if q is None else q.ptr))
+    if host_out is not None:
+      for h, d in zip(host_out, outs):
+        check(lib().cfd_memcpy_d2h(h.ctypes.data, d.ptr, d.nbytes, self.stream.handle))
     self.stream.sync()
     check(lib().cfd_dist_check(self.handle))
+    if host_out is not None:
+      return (host_out, q) if want_q else host_out
     return (outs, q) if want_q else outs
 
   def profile(self, nsteps: int = 2):
