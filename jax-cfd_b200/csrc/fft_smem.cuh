@@ -18,8 +18,40 @@ namespace cfd {
 __host__ __device__ constexpr int PAD(int i) { return i + (i >> 4); }
 __host__ __device__ constexpr int padded_len(int m) { return m + (m >> 4); }
 
+// Optional: complex add / subtract as ONE packed FP32 instruction (FADD2 on sm_100a:
+// add.rn.f32x2 works on an aligned register pair, which is what a float2 already is; same IEEE
+// rounding as two FADDs).  Measured on B200: 13 % fewer instructions in the line kernels but the
+// FADD2 issues at half rate on the FMA pipe, and the 8192^2 step got 1 % SLOWER (1186 vs 1170 us)
+// -- the line FFTs are not issue-slot bound.  Off by default; -DCFD_PACKED_FP=1 to retry.
+#ifndef CFD_PACKED_FP
+#define CFD_PACKED_FP 0
+#endif
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pack2(float2 a) {
+  pk2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(pk2 r) {
+  float2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+#if CFD_PACKED_FP
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  pk2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+  return unpack2(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  pk2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+  return unpack2(r);
+}
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -204,8 +236,43 @@ struct FftPlan {
   __host__ __device__ static constexpr int tw_len() { return tw_off_fwd(NP); }
 };
 
+// The E - NB twiddles thread t needs in a pass (none when Ns = 1).  Kept apart from the butterfly
+// so that a caller can issue these loads BEFORE the exchange barrier of the previous pass: their
+// L1/L2 latency then overlaps the shared-memory exchange instead of following it.
+template <class P, int LR, int LNS>
+__device__ __forceinline__ void fft_pass_twiddles(float2 (&w)[P::E], int t,
+                                                  const float2* __restrict__ tw) {
+  constexpr int R = 1 << LR, NB = P::E / R, NS = 1 << LNS;
+  if (LNS > 0) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int k = (t + P::G * q) & (NS - 1);
+#pragma unroll
+      for (int r = 1; r < R; ++r) w[q + r * NB] = __ldg(&tw[(r - 1) * NS + k]);
+    }
+  }
+}
+
 // One radix pass on the E register-resident points of thread t.
 //   v[e] holds x[t + G*e] on entry; on exit v[q + r*NB] holds output r of butterfly j = t + G*q.
+template <class P, int LR, int LNS, int DIR>
+__device__ __forceinline__ void fft_pass_butterflies(float2 (&v)[P::E], const float2 (&w)[P::E]) {
+  constexpr int R = 1 << LR, NB = P::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    float2 a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = v[q + r * NB];
+    if (LNS > 0) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) a[r] = twmul<DIR>(a[r], w[q + r * NB]);
+    }
+    Dft<R, DIR>::run(a);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[q + r * NB] = a[r];
+  }
+}
+
 template <class P, int LR, int LNS, int DIR>
 __device__ __forceinline__ void fft_pass_compute(float2 (&v)[P::E], int t,
                                                  const float2* __restrict__ tw) {
@@ -268,28 +335,65 @@ struct SyncLine {
   }
 };
 
-template <class P, int DIR, class SYNC = SyncCta>
+// DB = true: two exchange buffers, `s` and `s + alt`, used alternately (exchange number X0 + pass
+// picks one).  A pass then writes a buffer nobody can still be reading -- its last readers passed
+// the previous pass's barrier -- so the "all reads done" barrier disappears: one barrier per pass,
+// and warps that finish a butterfly early store at once instead of idling.
+//
+// PRETW = true: the twiddles of pass p+1 are loaded before the exchange that follows pass p (E more
+// live registers across the exchange -- for kernels that are not capped at 64 registers).
+template <class P, int DIR, class SYNC = SyncCta, bool DB = false, int X0 = 0, bool PRETW = false>
 struct FftRun {
   template <int PASS>
+  static __device__ __forceinline__ void exchange(float2 (&v)[P::E], int t, float2* s, int line,
+                                                  int alt) {
+    constexpr int LR = P::lr_fwd(PASS);
+    constexpr int LNS = P::lns_fwd(PASS);
+    float2* buf = s;
+    if constexpr (DB) {
+      if constexpr ((X0 + PASS) & 1) buf = s + alt;
+    } else {
+      SYNC::sync(line);  // all reads of the previous layout are done
+    }
+    fft_pass_store<P, LR, LNS>(v, t, buf);
+    SYNC::sync(line);
+    fft_load_regs<P>(v, t, buf);
+  }
+  template <int PASS>
   static __device__ __forceinline__ void passes(float2 (&v)[P::E], int t, float2* s,
-                                                const float2* __restrict__ tw, int line) {
+                                                const float2* __restrict__ tw, int line, int alt) {
     if constexpr (PASS < P::NP) {
-      constexpr int LR = P::lr_fwd(PASS);
-      constexpr int LNS = P::lns_fwd(PASS);
-      constexpr int OFF = P::tw_off_fwd(PASS);
-      fft_pass_compute<P, LR, LNS, DIR>(v, t, tw + OFF);
+      fft_pass_compute<P, P::lr_fwd(PASS), P::lns_fwd(PASS), DIR>(v, t, tw + P::tw_off_fwd(PASS));
       if constexpr (PASS + 1 < P::NP) {
-        SYNC::sync(line);  // all reads of the previous layout are done
-        fft_pass_store<P, LR, LNS>(v, t, s);
-        SYNC::sync(line);
-        fft_load_regs<P>(v, t, s);
-        passes<PASS + 1>(v, t, s, tw, line);
+        exchange<PASS>(v, t, s, line, alt);
+        passes<PASS + 1>(v, t, s, tw, line, alt);
+      }
+    }
+  }
+  // w holds the twiddles of pass PASS on entry
+  template <int PASS>
+  static __device__ __forceinline__ void passes_pre(float2 (&v)[P::E], float2 (&w)[P::E], int t,
+                                                    float2* s, const float2* __restrict__ tw,
+                                                    int line, int alt) {
+    if constexpr (PASS < P::NP) {
+      fft_pass_butterflies<P, P::lr_fwd(PASS), P::lns_fwd(PASS), DIR>(v, w);
+      if constexpr (PASS + 1 < P::NP) {
+        fft_pass_twiddles<P, P::lr_fwd(PASS + 1), P::lns_fwd(PASS + 1)>(w, t,
+                                                                        tw + P::tw_off_fwd(PASS + 1));
+        exchange<PASS>(v, t, s, line, alt);
+        passes_pre<PASS + 1>(v, w, t, s, tw, line, alt);
       }
     }
   }
   static __device__ __forceinline__ void run(float2 (&v)[P::E], int t, float2* s,
-                                             const float2* __restrict__ tw, int line = 0) {
-    passes<0>(v, t, s, tw, line);
+                                             const float2* __restrict__ tw, int line = 0,
+                                             int alt = 0) {
+    if constexpr (PRETW) {
+      float2 w[P::E];  // pass 0 has Ns = 1: no twiddles
+      passes_pre<0>(v, w, t, s, tw, line, alt);
+    } else {
+      passes<0>(v, t, s, tw, line, alt);
+    }
   }
 };
 

@@ -155,8 +155,15 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
 // rank (x >> lnloc)'s buffer at [line][x & (Nloc-1)] -- so the loads/stores below ARE the
 // all-to-all transpose of the distributed FFT, done with peer accesses over NVLink inside the
 // kernel (each rank transforms its own range of ky lines).  One GPU: a single peer, Nloc = M.
-template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT>
-__global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX>::G, (LEMAX == 5 && LINES * FftPlan<LM, LEMAX>::G <= 256) ? 2 : 1)
+#ifndef CFD_XL_PRETW
+#define CFD_XL_PRETW true
+#endif
+#ifndef CFD_XL_MINB
+#define CFD_XL_MINB 1
+#endif
+template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT, bool DB>
+__global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX>::G,
+                                  (LEMAX == 5 && LINES * FftPlan<LM, LEMAX>::G <= 256) ? 2 : CFD_XL_MINB)
 xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
@@ -195,13 +202,17 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   float2 v[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) v[e] = *elem(t + G * e);
-  FftRun<P, -1>::run(v, t, s, tw);
+  // DB: second exchange buffer behind the first (see FftRun); the inverse continues the
+  // forward transform's buffer alternation
+  constexpr int ALT = LINES * RS;
+  FftRun<P, -1, SyncCta, DB, 0, CFD_XL_PRETW>::run(v, t, s, tw, 0, ALT);
 
   // only the first line(s) of a CTA can be ky = 0 (split: both halves of that line)
   const bool cta_has_packed = (line0 % My) == 0;
   scale_line<P, FASTD>(v, t, s, ky, My, cta_has_packed, kmul, kadd, lamx, lamy, lamxf, lamyf, cutoff,
                        norm);
-  FftRun<P, +1>::run(v, t, s, tw);
+  if (DB && cta_has_packed) __syncthreads();  // scale_line's reads of buffer 0 are done
+  FftRun<P, +1, SyncCta, DB, (P::NP - 1) & 1, CFD_XL_PRETW>::run(v, t, s, tw, 0, ALT);
 #pragma unroll
   for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
 }
@@ -466,7 +477,9 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
                      const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
   using P = FftPlan<LM, LEMAX>;
   constexpr int LINES = (P::G >= 256) ? 1 : (256 / P::G > 16 ? 16 : 256 / P::G);
-  constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
+  // two exchange buffers (one barrier per pass) whenever both fit beside a second CTA's
+  constexpr bool DB = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2) <= 72 * 1024;
+  constexpr size_t smem = (size_t)(DB ? 2 : 1) * LINES * row_stride(P::M, 16) * sizeof(float2);
   if (nlines % LINES || (!split && line_begin % LINES)) return set_error_msg("internal: line count not divisible");
   auto go = [&](auto k) -> int {
     if (int e = set_smem(k, smem)) return e;
@@ -477,12 +490,12 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
   int e;
   if constexpr (LM == 14) {  // split mode exists for the half-lines of 32768-point lines only
     if (split)
-      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, true>) : go(xlines_kernel<LM, LINES, false, LEMAX, true>);
+      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, true, DB>) : go(xlines_kernel<LM, LINES, false, LEMAX, true, DB>);
     else
-      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false>);
+      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB>);
   } else {
     if (split) return set_error_msg("internal: split x lines need 16384-point transforms");
-    e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false>);
+    e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB>);
   }
   if (e) return e;
   count_launch();
