@@ -10,6 +10,7 @@
 //   * ordering: a one-CTA flag barrier kernel (system-scope stores/loads on peer-mapped flags)
 //     between the phases.  No NCCL on the data path; the host side only exchanges 64-byte IPC
 //     handles once (any transport: torch.distributed in jax_cfd_b200.distributed).
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -100,6 +101,84 @@ int barrier(cfd_plan* p, cudaStream_t st) {
   return 0;
 }
 
+// CFD_DIST_STAGED=1 selects the copy-engine transpose below instead of the in-kernel one (x-line
+// kernel loading / storing peer memory), which is the default because it measured faster.
+int staged_mode() {
+  static const int v = [] {
+    const char* e = getenv("CFD_DIST_STAGED");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+// The x pass of the distributed FFT with the transposes on the COPY ENGINES.
+//
+// Rank r owns lines [r L, (r+1) L), L = My / world.  Inside every rank's T[ky][x_loc] those lines
+// are ONE contiguous block of L * Nloc points, so gathering a chunk of lines is one plain copy per
+// peer into a local buffer of the same [line][x_loc] layout, and the x-line kernel runs unchanged
+// with its peer table pointing at the local copies (its own block is read in place).  Chunks are
+// pipelined: copy-in (one stream per peer) | x-line kernel (st) | copy-out (one stream per peer),
+// so NVLink carries chunk c+1 in and chunk c-1 out while the SMs transform chunk c.
+//
+// Measured at 2 x 8192^2 (round 1), x pass per step: in-kernel transpose 0.47 ms; this path 0.59 ms
+// (4 chunks).  Two reasons, both visible in the per-chunk event times: copy-engine copies from /
+// to CUDA-IPC mapped peer memory ran at ~260 GB/s (the same copies between cudaMalloc'ed buffers
+// of one process reach 700 GB/s, scripts/ubench/p2p_ce.cu), and the x-line kernel is 30 % slower
+// through its peer table (0.37 ms) than on one contiguous line buffer (0.28 ms).  Kept as an
+// opt-in experiment (results are bit-identical); the in-kernel path stays the default.
+int xpass_staged(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int lnloc) {
+  const size_t nloc = (size_t)p->shape[0];
+  const int My = (int)p->shape[1] / 2;
+  const size_t lines = (size_t)My / p->world;
+  const size_t gl0 = (size_t)p->rank * lines;
+  int K = p->world >= 4 ? 4 : 4;
+  if (const char* e = getenv("CFD_DIST_CHUNKS")) K = atoi(e);
+  if (K > 8) K = 8;
+  while (K > 1 && (lines % K || lines / K < 64)) K /= 2;
+  const size_t chunk = lines / K;
+  auto peerT = [&](int r) { return reinterpret_cast<float2*>(fptr(p->peer_shared[r], L.off_T)); };
+  auto stage = [&](int r) { return p->xstage + (size_t)r * lines * nloc; };
+  // peer table of the kernel: local copies, addressed with the GLOBAL line number like T itself
+  LinePeers tab;
+  for (int r = 0; r < CFD_MAX_PEERS; ++r) {
+    const int q = r < p->world ? r : p->rank;
+    tab.p[r] = (q == p->rank) ? peerT(q) : stage(q) - gl0 * nloc;
+  }
+  CFD_CUDA_OK(cudaEventRecord(p->ev_ready, st));
+  for (int r = 0; r < p->world; ++r)
+    if (r != p->rank) CFD_CUDA_OK(cudaStreamWaitEvent(p->st_in[r], p->ev_ready, 0));
+  for (int c = 0; c < K; ++c) {
+    const size_t lb = (size_t)c * chunk;
+    const size_t bytes = chunk * nloc * sizeof(float2);
+    for (int k = 1; k < p->world; ++k) {
+      const int r = (p->rank + k) % p->world;  // staggered start so the peers are not hit in step
+      CFD_CUDA_OK(cudaMemcpyAsync(stage(r) + lb * nloc, peerT(r) + (gl0 + lb) * nloc, bytes,
+                                  cudaMemcpyDeviceToDevice, p->st_in[r]));
+      CFD_CUDA_OK(cudaEventRecord(p->ev_in[c][r], p->st_in[r]));
+      CFD_CUDA_OK(cudaStreamWaitEvent(st, p->ev_in[c][r], 0));
+    }
+    prof_mark(p, st, "xwait_in");
+    if (int e = launch_xlines_peers(st, p->lm_x, tab, lnloc, gl0 + lb, chunk, My, p->tw_x, p->lam[0],
+                                    p->lam[1], p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
+                                    p->xscratch, p->wbig, nullptr))
+      return e;
+    CFD_CUDA_OK(cudaEventRecord(p->ev_comp[c], st));
+    prof_mark(p, st, "xchunk");
+    for (int k = 1; k < p->world; ++k) {
+      const int r = (p->rank + k) % p->world;
+      CFD_CUDA_OK(cudaStreamWaitEvent(p->st_out[r], p->ev_comp[c], 0));
+      CFD_CUDA_OK(cudaMemcpyAsync(peerT(r) + (gl0 + lb) * nloc, stage(r) + lb * nloc, bytes,
+                                  cudaMemcpyDeviceToDevice, p->st_out[r]));
+    }
+  }
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    CFD_CUDA_OK(cudaEventRecord(p->ev_out[r], p->st_out[r]));
+    CFD_CUDA_OK(cudaStreamWaitEvent(st, p->ev_out[r], 0));
+  }
+  return 0;
+}
+
 }  // namespace
 }  // namespace cfd
 
@@ -143,6 +222,27 @@ int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const doub
   cudaMemset(p->shared, 0, L.total_bytes);
   p->shared_bytes = L.total_bytes;
   for (int r = 0; r < CFD_MAX_PEERS; ++r) p->peer_shared[r] = p->shared;
+  if (world > 1 && staged_mode()) {
+    // world blocks of (My / world) x Nloc float2 = one field's bytes (the own block stays unused)
+    bool ok = cudaMalloc(&p->xstage, L.field * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming) == cudaSuccess;
+    for (int r = 0; r < world && ok; ++r) {
+      if (r == rank) continue;
+      ok = cudaStreamCreateWithFlags(&p->st_in[r], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&p->st_out[r], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p->ev_out[r], cudaEventDisableTiming) == cudaSuccess;
+      for (int c = 0; c < 8 && ok; ++c)
+        ok = cudaEventCreateWithFlags(&p->ev_in[c][r], cudaEventDisableTiming) == cudaSuccess;
+    }
+    for (int c = 0; c < 8 && ok; ++c)
+      ok = cudaEventCreateWithFlags(&p->ev_comp[c], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      cfd_plan_destroy(p);
+      return set_error_msg("staged-transpose buffers could not be created");
+    }
+    p->workspace_bytes += L.field * sizeof(float);
+  }
   *out = p;
   return 0;
 }
@@ -233,10 +333,14 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
     if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, Tloc, 1, nloc, p->tw_row, p->rtw)) return e;
     prof_mark(p, st, "rfft_rows");
     if (int e = barrier(p, st)) return e;  // every rank's slab spectrum is complete
-    if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
-                                    lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1], p->lamf[0],
-                                    p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig, &p->side))
+    if (p->xstage) {
+      if (int e = xpass_staged(p, st, L, lnloc)) return e;
+    } else if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
+                                           lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1],
+                                           p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
+                                           p->xscratch, p->wbig, &p->side)) {
       return e;
+    }
     prof_mark(p, st, "xlines_peers");
     if (int e = barrier(p, st)) return e;  // every rank has written its lines back into my slab
     if (int e = launch_irfft_rows(st, p->lm_row, Tloc, fptr(p->shared, L.off_q[nxt]), 1, nloc,

@@ -472,6 +472,17 @@ void cfd_plan_destroy(cfd_plan* p) {
     cudaEventDestroy(p->side.done[i]);
   }
   if (p->side.start) cudaEventDestroy(p->side.start);
+  cudaFree(p->xstage);
+  if (p->ev_ready) cudaEventDestroy(p->ev_ready);
+  for (int r = 0; r < CFD_MAX_PEERS; ++r) {
+    if (p->st_in[r]) cudaStreamDestroy(p->st_in[r]);
+    if (p->st_out[r]) cudaStreamDestroy(p->st_out[r]);
+    if (p->ev_out[r]) cudaEventDestroy(p->ev_out[r]);
+    for (int c = 0; c < 8; ++c)
+      if (p->ev_in[c][r]) cudaEventDestroy(p->ev_in[c][r]);
+  }
+  for (int c = 0; c < 8; ++c)
+    if (p->ev_comp[c]) cudaEventDestroy(p->ev_comp[c]);
   cudaFree(p->tw_y);
   cudaFree(p->T2);
   cudaFree(p->nut);

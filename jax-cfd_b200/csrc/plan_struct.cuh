@@ -49,6 +49,13 @@ struct cfd_plan {
   size_t shared_bytes = 0;
   void* peer_shared[CFD_MAX_PEERS] = {nullptr};  // peers' `shared` mapped here (own entry = shared)
   unsigned long long epoch = 0;                   // barrier generation
+  // staged transpose (multi_gpu.cu): the peers' blocks of this rank's ky lines are copied into
+  // local buffers by the copy engines, chunk by chunk (one in / one out stream per peer), while
+  // the x-line kernel works on the previous chunk
+  float2* xstage = nullptr;
+  cudaStream_t st_in[CFD_MAX_PEERS] = {nullptr}, st_out[CFD_MAX_PEERS] = {nullptr};
+  cudaEvent_t ev_ready = nullptr, ev_out[CFD_MAX_PEERS] = {nullptr};
+  cudaEvent_t ev_in[8][CFD_MAX_PEERS] = {{nullptr}}, ev_comp[8] = {nullptr};
   int dist_state = 0, dist_cur = 0;               // see multi_gpu.cu
   // per-kernel timing
   bool profiling = false;

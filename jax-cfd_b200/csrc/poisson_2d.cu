@@ -205,14 +205,16 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   // DB: second exchange buffer behind the first (see FftRun); the inverse continues the
   // forward transform's buffer alternation
   constexpr int ALT = LINES * RS;
-  FftRun<P, -1, SyncCta, DB, 0, CFD_XL_PRETW>::run(v, t, s, tw, 0, ALT);
+  // twiddle loads ahead of the exchange only where the kernel is not capped at 64 registers
+  constexpr bool PRE = CFD_XL_PRETW && (LINES * G <= 512);
+  FftRun<P, -1, SyncCta, DB, 0, PRE>::run(v, t, s, tw, 0, ALT);
 
   // only the first line(s) of a CTA can be ky = 0 (split: both halves of that line)
   const bool cta_has_packed = (line0 % My) == 0;
   scale_line<P, FASTD>(v, t, s, ky, My, cta_has_packed, kmul, kadd, lamx, lamy, lamxf, lamyf, cutoff,
                        norm);
   if (DB && cta_has_packed) __syncthreads();  // scale_line's reads of buffer 0 are done
-  FftRun<P, +1, SyncCta, DB, (P::NP - 1) & 1, CFD_XL_PRETW>::run(v, t, s, tw, 0, ALT);
+  FftRun<P, +1, SyncCta, DB, (P::NP - 1) & 1, PRE>::run(v, t, s, tw, 0, ALT);
 #pragma unroll
   for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
 }
