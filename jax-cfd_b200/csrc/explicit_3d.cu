@@ -562,6 +562,239 @@ __global__ void smag_acc_fields_kernel(Sf S, const float* __restrict__ nut, floa
   ws[boff + gid] += scale * (-d2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Smagorinsky straight from the velocity planes (2.5-D blocking, same tile / plane ring as
+// explicit3d_march_kernel): two kernels, 16 + 40 B/cell of HBM traffic instead of the 116 B/cell
+// of the three strain-field kernels above, and no six-field scratch.
+//   smag_nut_march_kernel:  nu_t at cell centres            (subgrid_models.py:40-98)
+//   smag_acc_march_kernel:  u* += scale * (-div tau)        (subgrid_models.py:101-134, 188-213)
+// The arithmetic (operation order included) is that of strain<> / strain_center<> / nu_at<> above,
+// read through shared-memory planes instead of global memory.
+template <int AX, class R>
+__device__ __forceinline__ float fwd_r(const R& rd, int comp, int p0, int p1, int p2, float inv_h) {
+  int d[3] = {p0, p1, p2};
+  const float a = rd(comp, d[0], d[1], d[2]);
+  d[AX] += 1;
+  return (rd(comp, d[0], d[1], d[2]) - a) * inv_h;
+}
+template <int I, int J, class R>
+__device__ __forceinline__ float strain_r(const R& rd, int p0, int p1, int p2, const float* inv_h) {
+  return 0.5f * (fwd_r<J>(rd, I, p0, p1, p2, inv_h[J]) + fwd_r<I>(rd, J, p0, p1, p2, inv_h[I]));
+}
+template <int I, int J, class R>
+__device__ __forceinline__ float strain_center_r(const R& rd, const float* inv_h) {
+  if (I == J) {
+    int d[3] = {0, 0, 0};
+    d[I] = -1;
+    return strain_r<I, I>(rd, d[0], d[1], d[2], inv_h);
+  }
+  constexpr int A = I < J ? I : J, B = I < J ? J : I;
+  float r[2];
+#pragma unroll
+  for (int sb = 0; sb < 2; ++sb) {
+    int d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+    d0[B] = d1[B] = sb - 1;
+    d0[A] = -1;
+    const float lo = strain_r<I, J>(rd, d0[0], d0[1], d0[2], inv_h);
+    const float hi = strain_r<I, J>(rd, d1[0], d1[1], d1[2], inv_h);
+    r[sb] = 0.5f * lo + 0.5f * hi;
+  }
+  return 0.5f * r[0] + 0.5f * r[1];
+}
+template <int I, int J, class NR>
+__device__ __forceinline__ float nu_at_r(const NR& nr, int p0, int p1, int p2) {
+  if (I == J) {
+    int d[3] = {p0, p1, p2};
+    d[I] += 1;
+    return nr(d[0], d[1], d[2]);
+  }
+  constexpr int A = I < J ? I : J, B = I < J ? J : I;
+  float r[2];
+#pragma unroll
+  for (int sb = 0; sb < 2; ++sb) {
+    int d0[3] = {p0, p1, p2}, d1[3] = {p0, p1, p2};
+    d0[B] += sb;
+    d1[B] += sb;
+    d1[A] += 1;
+    r[sb] = 0.5f * nr(d0[0], d0[1], d0[2]) + 0.5f * nr(d1[0], d1[1], d1[2]);
+  }
+  return 0.5f * r[0] + 0.5f * r[1];
+}
+
+// Readers over three consecutive planes (x-1, x, x+1) of a shared-memory ring
+struct VelPlanes {
+  const float* pl[3];
+  int own;
+  __device__ __forceinline__ float operator()(int comp, int d0, int d1, int d2) const {
+    return pl[d0 + 1][comp * kPlane + own + d1 * kHZ + d2];
+  }
+};
+struct NutPlanes {
+  const float* pl[3];
+  int own;
+  __device__ __forceinline__ float operator()(int d0, int d1, int d2) const {
+    return pl[d0 + 1][own + d1 * kHZ + d2];
+  }
+};
+
+// Per-thread source / destination offsets of the plane loader (see explicit3d_march_kernel)
+__device__ __forceinline__ void plane_loader_offsets(int tid, int j0, int k0, int N1, int N2,
+                                                     int* ld_src, int* ld_dst) {
+  *ld_src = -1;
+  *ld_dst = 0;
+  if (tid < 192) {
+    const int r = tid >> 4, m = tid & 15;
+    int j = j0 + r - 2;
+    j = j < 0 ? j + N1 : (j >= N1 ? j - N1 : j);
+    *ld_src = j * N2 + k0 + 4 * m;
+    *ld_dst = r * kHZ + kZ0 + 4 * m;
+  } else if (tid < 240) {
+    const int h = tid - 192, r = h >> 2, hc = h & 3;
+    int j = j0 + r - 2;
+    j = j < 0 ? j + N1 : (j >= N1 ? j - N1 : j);
+    int k = hc < 2 ? k0 - 2 + hc : k0 + kBZ + (hc - 2);
+    k = k < 0 ? k + N2 : (k >= N2 ? k - N2 : k);
+    *ld_src = j * N2 + k;
+    *ld_dst = r * kHZ + (hc < 2 ? kZ0 - 2 + hc : kZ0 + kBZ + (hc - 2));
+  }
+}
+template <int NCOMP>
+__device__ __forceinline__ void load_plane_to(float* dst, const float* const* f, size_t plane_off,
+                                              int tid, int ld_src, int ld_dst) {
+  if (tid < 192) {
+#pragma unroll
+    for (int comp = 0; comp < NCOMP; ++comp)
+      *reinterpret_cast<float4*>(dst + comp * kPlane + ld_dst) = ldg4(f[comp] + plane_off + ld_src);
+  } else if (tid < 240) {
+#pragma unroll
+    for (int comp = 0; comp < NCOMP; ++comp)
+      dst[comp * kPlane + ld_dst] = __ldg(f[comp] + plane_off + ld_src);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+smag_nut_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                      const float* __restrict__ w, float* __restrict__ nut, int N0, int N1, int N2,
+                      StepConsts c, int TX) {
+  extern __shared__ __align__(16) float sm3[];  // [slot][comp][kHY][kHZ]
+  const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
+  const int tilesz = N2 / kBZ, tilesy = N1 / kBY;
+  const int tz = blockIdx.x % tilesz, tyb = (blockIdx.x / tilesz) % tilesy;
+  const int xb = blockIdx.x / (tilesz * tilesy);
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const float* f[3] = {u + boff, v + boff, w + boff};
+  const int j0 = tyb * kBY, k0 = tz * kBZ;
+  const int i0 = xb * TX, iend = min(i0 + TX, N0);
+  const size_t planeN = (size_t)N1 * N2;
+  const int own = (ty + 2) * kHZ + 2 * lane + kZ0;
+  int ld_src, ld_dst;
+  plane_loader_offsets(tid, j0, k0, N1, N2, &ld_src, &ld_dst);
+  auto slot = [&](int plane) { return sm3 + ((plane + kSlots) & (kSlots - 1)) * (3 * kPlane); };
+  auto load = [&](int i) {
+    const int iw = i < 0 ? i + N0 : (i >= N0 ? i - N0 : i);
+    load_plane_to<3>(slot(i), f, (size_t)iw * planeN, tid, ld_src, ld_dst);
+  };
+  load(i0 - 1);
+  load(i0);
+  load(i0 + 1);
+  for (int i = i0; i < iend; ++i) {
+    __syncthreads();  // planes <= i+1 are visible; everyone is done with plane i-2
+    load(i + 2);
+    float out[2];
+#pragma unroll
+    for (int col = 0; col < 2; ++col) {
+      const VelPlanes rd = {{slot(i - 1), slot(i), slot(i + 1)}, own + col};
+      const float s00 = strain_center_r<0, 0>(rd, c.inv_h), s11 = strain_center_r<1, 1>(rd, c.inv_h),
+                  s22 = strain_center_r<2, 2>(rd, c.inv_h);
+      const float s01 = strain_center_r<0, 1>(rd, c.inv_h), s02 = strain_center_r<0, 2>(rd, c.inv_h),
+                  s12 = strain_center_r<1, 2>(rd, c.inv_h);
+      const float r0 = s00 * s00 + s01 * s01 + s02 * s02;
+      const float r1 = s01 * s01 + s11 * s11 + s12 * s12;
+      const float r2 = s02 * s02 + s12 * s12 + s22 * s22;
+      out[col] = c.smag_coef * sqrtf(2.f * ((r0 + r1) + r2));
+    }
+    const size_t cell0 = (size_t)i * planeN + (size_t)(j0 + ty) * N2 + k0 + 2 * lane;
+    *reinterpret_cast<float2*>(nut + boff + cell0) = make_float2(out[0], out[1]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+smag_acc_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                      const float* __restrict__ w, const float* __restrict__ nut,
+                      float* __restrict__ us, float* __restrict__ vs, float* __restrict__ ws, int N0,
+                      int N1, int N2, StepConsts c, int dvdt_mode, int TX) {
+  extern __shared__ __align__(16) float sm3[];  // velocity ring [slot][3][plane], then nu_t ring
+  float* smn = sm3 + kSlots * 3 * kPlane;
+  const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
+  const int tilesz = N2 / kBZ, tilesy = N1 / kBY;
+  const int tz = blockIdx.x % tilesz, tyb = (blockIdx.x / tilesz) % tilesy;
+  const int xb = blockIdx.x / (tilesz * tilesy);
+  const size_t cells = (size_t)N0 * N1 * N2;
+  const size_t boff = (size_t)blockIdx.y * cells;
+  const float* f[3] = {u + boff, v + boff, w + boff};
+  const float* fn[1] = {nut + boff};
+  float* o[3] = {us + boff, vs + boff, ws + boff};
+  const int j0 = tyb * kBY, k0 = tz * kBZ;
+  const int i0 = xb * TX, iend = min(i0 + TX, N0);
+  const size_t planeN = (size_t)N1 * N2;
+  const int own = (ty + 2) * kHZ + 2 * lane + kZ0;
+  int ld_src, ld_dst;
+  plane_loader_offsets(tid, j0, k0, N1, N2, &ld_src, &ld_dst);
+  auto slot = [&](int plane) { return sm3 + ((plane + kSlots) & (kSlots - 1)) * (3 * kPlane); };
+  auto nslot = [&](int plane) { return smn + ((plane + kSlots) & (kSlots - 1)) * kPlane; };
+  auto load = [&](int i) {
+    const int iw = i < 0 ? i + N0 : (i >= N0 ? i - N0 : i);
+    load_plane_to<3>(slot(i), f, (size_t)iw * planeN, tid, ld_src, ld_dst);
+    load_plane_to<1>(nslot(i), fn, (size_t)iw * planeN, tid, ld_src, ld_dst);
+  };
+  load(i0 - 1);
+  load(i0);
+  load(i0 + 1);
+  const float scale = (dvdt_mode ? 1.f : c.dt) * c.inv_rho;
+  for (int i = i0; i < iend; ++i) {
+    __syncthreads();
+    load(i + 2);
+    const size_t cell0 = (size_t)i * planeN + (size_t)(j0 + ty) * N2 + k0 + 2 * lane;
+    float2 acc[3];
+#pragma unroll
+    for (int A = 0; A < 3; ++A) acc[A] = *reinterpret_cast<const float2*>(o[A] + cell0);
+    float d[3][2];
+#pragma unroll
+    for (int col = 0; col < 2; ++col) {
+      const VelPlanes rd = {{slot(i - 1), slot(i), slot(i + 1)}, own + col};
+      const NutPlanes nr = {{nslot(i - 1), nslot(i), nslot(i + 1)}, own + col};
+#define TAU(I, J, p0, p1, p2) (-2.f * nu_at_r<I, J>(nr, p0, p1, p2) * strain_r<I, J>(rd, p0, p1, p2, c.inv_h))
+      // every distinct tau sample once (tau_ij == tau_ji), same order as smag_acc_fields_kernel
+      const float t00 = TAU(0, 0, 0, 0, 0), t00m = TAU(0, 0, -1, 0, 0);
+      const float t11 = TAU(1, 1, 0, 0, 0), t11m = TAU(1, 1, 0, -1, 0);
+      const float t22 = TAU(2, 2, 0, 0, 0), t22m = TAU(2, 2, 0, 0, -1);
+      const float t01 = TAU(0, 1, 0, 0, 0), t01x = TAU(0, 1, -1, 0, 0), t01y = TAU(0, 1, 0, -1, 0);
+      const float t02 = TAU(0, 2, 0, 0, 0), t02x = TAU(0, 2, -1, 0, 0), t02z = TAU(0, 2, 0, 0, -1);
+      const float t12 = TAU(1, 2, 0, 0, 0), t12y = TAU(1, 2, 0, -1, 0), t12z = TAU(1, 2, 0, 0, -1);
+#undef TAU
+      float d0 = (t00 - t00m) * c.inv_h[0];
+      d0 += (t01 - t01y) * c.inv_h[1];
+      d0 += (t02 - t02z) * c.inv_h[2];
+      float d1 = (t01 - t01x) * c.inv_h[0];
+      d1 += (t11 - t11m) * c.inv_h[1];
+      d1 += (t12 - t12z) * c.inv_h[2];
+      float d2 = (t02 - t02x) * c.inv_h[0];
+      d2 += (t12 - t12y) * c.inv_h[1];
+      d2 += (t22 - t22m) * c.inv_h[2];
+      d[0][col] = d0;
+      d[1][col] = d1;
+      d[2][col] = d2;
+    }
+#pragma unroll
+    for (int A = 0; A < 3; ++A) {
+      acc[A].x += scale * (-d[A][0]);
+      acc[A].y += scale * (-d[A][1]);
+      *reinterpret_cast<float2*>(o[A] + cell0) = acc[A];
+    }
+  }
+}
+
 // diagnostics: sum 0.5|v|^2, sum 0.5|curl|^2, max|div|, max|v|^2
 __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -621,10 +854,44 @@ __global__ void diag3d_kernel(const float* __restrict__ u, const float* __restri
 
 }  // namespace
 
+bool explicit_3d_uses_march(int N0, int N1, int N2);
+
+// x rows per CTA of the marching kernels: long enough to amortise the 3-plane prologue, short
+// enough to fill the GPU
+static int march_tx(int batch, int N0, int N1, int N2) {
+  int TX = 32;
+  while (TX > 8 && (long)(N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX) * batch < 148L * 4) TX /= 2;
+  return TX;
+}
+
+// CFD_SMAG_TILED=0 selects the strain-field kernels instead of the plane-marching ones
+bool smag_uses_tiles(int N0, int N1, int N2) {
+  static const int v = [] {
+    const char* e = getenv("CFD_SMAG_TILED");
+    return e ? atoi(e) : 1;
+  }();
+  return v && explicit_3d_uses_march(N0, N1, N2);
+}
+
 // sfield != nullptr: 6 strain fields of batch * cells floats each (strain-field path)
 int launch_smag_nut_3d(cudaStream_t st, const float* u, const float* v, const float* w, float* nut,
                        float* sfield, int batch, int N0, int N1, int N2, const StepConsts& c) {
   const size_t cells = (size_t)N0 * N1 * N2;
+  if (!sfield && smag_uses_tiles(N0, N1, N2)) {
+    const int TX = march_tx(batch, N0, N1, N2);
+    constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CFD_CUDA_OK(cudaFuncSetAttribute(smag_nut_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      attr_set = true;
+    }
+    dim3 g((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
+    smag_nut_march_kernel<<<g, 256, smem, st>>>(u, v, w, nut, N0, N1, N2, c, TX);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((unsigned)((cells + 127) / 128), batch);
   if (sfield) {
     SfOut so;
@@ -659,9 +926,7 @@ int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const fl
                        int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode) {
   const size_t cells = (size_t)N0 * N1 * N2;
   if (explicit_3d_uses_march(N0, N1, N2)) {
-    // rows per CTA along x: long enough to amortise the 3-plane prologue, short enough to fill the GPU
-    int TX = 32;
-    while (TX > 8 && (long)(N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX) * batch < 148L * 4) TX /= 2;
+    const int TX = march_tx(batch, N0, N1, N2);
     constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -673,7 +938,19 @@ int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const fl
     explicit3d_march_kernel<<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
     count_launch();
     CFD_CUDA_OK(cudaGetLastError());
-    if (nut && sfield) {
+    if (nut && !sfield && smag_uses_tiles(N0, N1, N2)) {
+      constexpr size_t smem2 = (size_t)kSlots * 4 * kPlane * sizeof(float);
+      static bool attr2_set = false;
+      if (!attr2_set) {
+        CFD_CUDA_OK(cudaFuncSetAttribute(smag_acc_march_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        attr2_set = true;
+      }
+      smag_acc_march_kernel<<<grid, 256, smem2, st>>>(u, v, w, nut, us, vs, ws, N0, N1, N2, c, dvdt_mode,
+                                                     TX);
+      count_launch();
+      CFD_CUDA_OK(cudaGetLastError());
+    } else if (nut && sfield) {
       dim3 g2((unsigned)((cells + 127) / 128), batch);
       Sf si;
       for (int q = 0; q < 6; ++q) si.s[q] = sfield + (size_t)q * batch * cells;

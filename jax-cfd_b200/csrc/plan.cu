@@ -54,6 +54,7 @@ int launch_correct_3d(cudaStream_t, const float* us, const float* vs, const floa
                       float ihy, float ihz);
 int launch_smag_nut_3d(cudaStream_t, const float* u, const float* v, const float* w, float* nut,
                        float* sfield, int batch, int N0, int N1, int N2, const StepConsts& c);
+bool smag_uses_tiles(int N0, int N1, int N2);
 int launch_explicit_3d(cudaStream_t, const float* u, const float* v, const float* w, const float* nut,
                        const float* sfield, float* us, float* vs, float* ws, int batch, int N0, int N1,
                        int N2, const StepConsts& c, int dvdt_mode);
@@ -296,7 +297,8 @@ int smag_buffers(cfd_plan* p, const StepConsts& c, float** nut, float** sfield) 
   const size_t fbytes = (size_t)p->batch * p->cells * sizeof(float);
   if (!p->nut) CFD_CUDA_OK(cudaMalloc((void**)&p->nut, fbytes));
   *nut = p->nut;
-  if (explicit_3d_uses_march((int)p->shape[0], (int)p->shape[1], (int)p->shape[2])) {
+  if (explicit_3d_uses_march((int)p->shape[0], (int)p->shape[1], (int)p->shape[2]) &&
+      !smag_uses_tiles((int)p->shape[0], (int)p->shape[1], (int)p->shape[2])) {
     if (!p->sfield) CFD_CUDA_OK(cudaMalloc((void**)&p->sfield, 6 * fbytes));
     *sfield = p->sfield;
   }
