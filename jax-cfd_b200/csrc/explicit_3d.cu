@@ -244,7 +244,10 @@ constexpr int kHZ = kBZ + 8;  // row: [pad pad h h | 64 interior (16-byte aligne
 constexpr int kZ0 = 4;        // column of the first interior cell
 constexpr int kPlane = kHY * kHZ;  // floats per component per slot
 
-__global__ void __launch_bounds__(256)
+// HAS_FORCE = false: no forcing term other than Smagorinsky (which the smag kernels add) -- the
+// runtime walk over the term list, 6 times per plane, is compiled out.
+template <bool HAS_FORCE>
+__global__ void __launch_bounds__(256, 4)
 explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
                         const float* __restrict__ w, float* __restrict__ us,
                         float* __restrict__ vs, float* __restrict__ ws, int N0, int N1, int N2,
@@ -403,7 +406,7 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
           l += (g(A, 0, 0, col - 1) + g(A, 0, 0, col + 1)) * c.lap_s[2];
           dv += c.nu * l;
         }
-        if (c.n_terms > 0) {
+        if (HAS_FORCE) {
           float fsum = 0.f;
           for (int t = 0; t < c.n_terms; ++t) {
             const int kind = c.term_kind[t];
@@ -930,12 +933,19 @@ int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const fl
     constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-      CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+      CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
     dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
-    explicit3d_march_kernel<<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
+    bool has_force = false;  // a non-zero forcing sum (an all-Smagorinsky list adds +0 here)
+    for (int t = 0; t < c.n_terms; ++t) has_force = has_force || c.term_kind[t] != CFD_FORCE_SMAGORINSKY;
+    if (has_force)
+      explicit3d_march_kernel<true><<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
+    else
+      explicit3d_march_kernel<false><<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
     count_launch();
     CFD_CUDA_OK(cudaGetLastError());
     if (nut && !sfield && smag_uses_tiles(N0, N1, N2)) {
