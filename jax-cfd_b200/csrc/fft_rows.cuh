@@ -39,16 +39,32 @@ constexpr int lines_for(int LM) {
   return lines;
 }
 
-// points per thread (log2) of the x-line kernel: 16 by default; CFD_XLINES_LE=5 selects 32 points
-// per thread (radix-32 passes, fewer exchanges, half the threads per line).
+// points per thread (log2) of the x-line kernel.  4: 16 points, one radix-16 butterfly per pass.
+// 5: 32 points = two radix-16 butterflies per pass, half the threads per line, which lets TWO
+// independent CTAs share an SM for 4096- and 8192-point lines (their exchange / barrier phases then
+// overlap each other): 277 -> 221 us at 8192^2, 268 -> 205 us for 4096-point lines.  Shorter lines
+// already run several lines per SM and get slower; 16384-point lines stay at one CTA per SM either
+// way.  CFD_XLINES_LE=4|5 overrides.
 inline int xlines_lemax(int lm) {
   static const int forced = [] {
     const char* e = getenv("CFD_XLINES_LE");
     return e ? atoi(e) : 0;
   }();
   if (forced == 4 || forced == 5) return forced;
+  return (lm == 12 || lm == 13) ? 5 : 4;
+}
+
+// points per thread (log2) of the row kernels: 32 points per thread measured slower there (218 vs
+// 190 us, 268 vs 237 us at 8192^2 -- the rows of a CTA already drift apart on their own named
+// barriers); CFD_ROWS_LE=4|5 overrides
+inline int rows_lemax(int lm) {
+  static const int forced = [] {
+    const char* e = getenv("CFD_ROWS_LE");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 4 || forced == 5) return forced;
   (void)lm;
-  return 4;  // 32 points per thread measured no faster (register pressure); kept as an option
+  return 4;
 }
 
 static int rows_shift() {  // tuning knob: CFD_FFT_ROWS_SHIFT=k uses rows_for(LM) >> k rows per CTA

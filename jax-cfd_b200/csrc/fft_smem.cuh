@@ -203,24 +203,27 @@ struct Dft<32, DIR> {
 };
 
 // ---- radix plan -------------------------------------------------------------------------------
-// M = 2^LM points, E = min(2^LEMAX, M) points per thread (LEMAX = 4: 16 points, radix-16 passes;
-// LEMAX = 5: 32 points, radix-32 passes -- fewer exchanges and half the threads per line).
+// M = 2^LM points, E = min(2^LEMAX, M) points per thread, radix min(2^LRMAX, E) (defaults: 16
+// points, radix-16 passes; <LM, 5, 4>: 32 points = two radix-16 butterflies per thread and pass).
 // Passes use the largest radix while possible and one final smaller radix.  Forward and inverse
 // share the pass order and the twiddle table (the inverse conjugates).  Every transform starts from
 // registers v[e] = x[t + G*e] and ends with v[slot] = X[t + G*slot], so a forward transform can be
 // scaled in registers and fed straight into an inverse transform without an exchange.
-template <int LM, int LEMAX = 4>
+template <int LM, int LEMAX = 4, int LRMAX = LEMAX>
 struct FftPlan {
   static constexpr int M = 1 << LM;
   static constexpr int LE = LM < LEMAX ? LM : LEMAX;
   static constexpr int E = 1 << LE;
   static constexpr int G = M / E;  // threads per line
-  static constexpr int NP = (LM + LE - 1) / LE;  // passes
-  static constexpr int LPAD = LE < 4 ? 4 : LE;   // one padding slot per 2^LPAD points
+  // radix of the full passes: 2^LR <= E.  LR < LE: a thread runs E / 2^LR independent butterflies
+  // per pass (more instruction-level parallelism per thread, half the threads per line)
+  static constexpr int LR = LE < LRMAX ? LE : LRMAX;
+  static constexpr int NP = (LM + LR - 1) / LR;  // passes
+  static constexpr int LPAD = LR < 4 ? 4 : LR;   // one padding slot per 2^LPAD points
   __host__ __device__ static constexpr int pad(int i) { return i + (i >> LPAD); }
   // log2 radix of forward pass p
   __host__ __device__ static constexpr int lr_fwd(int p) {
-    return (p < LM / LE) ? LE : (LM - (LM / LE) * LE);
+    return (p < LM / LR) ? LR : (LM - (LM / LR) * LR);
   }
   __host__ __device__ static constexpr int lns_fwd(int p) {  // log2 Ns before pass p
     int s = 0;

@@ -212,7 +212,7 @@ int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double
   p->lam[0] = nullptr;
   p->lamf[0] = nullptr;
   p->lm_x = ilog2(Nxg);
-  int err = upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x, xlines_lemax(p->lm_x)));
+  int err = upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x));
   if (p->lm_x == 15) err |= big_line_tables(p, (size_t)(shape[1] / 2) / (p->world > 0 ? p->world : 1));
   std::vector<double> lam(Nxg);
   for (int k = 0; k < Nxg; ++k)
@@ -393,7 +393,7 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   p->lm_x = ilog2(Nx);
   int err = 0;
   err |= upload(&p->tw_row, build_twiddles(p->lm_row));
-  err |= upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x, ndim == 2 ? xlines_lemax(p->lm_x) : 4));
+  err |= upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x));
   if (p->lm_x == 15 && ndim == 2) err |= big_line_tables(p, (size_t)batch * (Ny / 2));
   if (ndim == 3) {
     p->lm_y = ilog2(shape[1]);

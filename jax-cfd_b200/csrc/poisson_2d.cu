@@ -30,11 +30,12 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 // R: rows of `rhs` (N = 2M reals each)  ->  T[b][ky][x]   (ky = 0..M-1, packed)
-template <int LM, int ROWS>
-__global__ void __launch_bounds__(ROWS * FftPlan<LM>::G)
+// LEMAX = 5: 32 points (two radix-16 butterflies per pass) per thread, half the threads per row.
+template <int LM, int ROWS, int LEMAX>
+__global__ void __launch_bounds__(ROWS * FftPlan<LM, LEMAX, 4>::G)
 rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
                  const float2* __restrict__ tw, const float2* __restrict__ rtw) {
-  using P = FftPlan<LM>;
+  using P = FftPlan<LM, LEMAX, 4>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, ROWS);
   extern __shared__ float2 smem[];
@@ -168,7 +169,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
               const float* __restrict__ lamyf, double cutoff, float norm) {
-  using P = FftPlan<LM, LEMAX>;
+  using P = FftPlan<LM, LEMAX, 4>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, 16);
   extern __shared__ float2 smem[];
@@ -206,7 +207,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   // forward transform's buffer alternation
   constexpr int ALT = LINES * RS;
   // twiddle loads ahead of the exchange only where the kernel is not capped at 64 registers
-  constexpr bool PRE = CFD_XL_PRETW && (LINES * G <= 512);
+  constexpr bool PRE = CFD_XL_PRETW && LEMAX == 4 && (LINES * G <= 512);
   FftRun<P, -1, SyncCta, DB, 0, PRE>::run(v, t, s, tw, 0, ALT);
 
   // only the first line(s) of a CTA can be ky = 0 (split: both halves of that line)
@@ -335,11 +336,11 @@ __global__ void merge_lines_kernel(LinePeers peers, int lnloc, size_t line_begin
 // Q: gather ROWS rows of T, inverse real FFT, write q rows (coalesced).  No halo row, no
 // redundant transform; the pressure-gradient correction is applied either by correct2d_kernel or
 // lazily by the next step's explicit kernel (explicit_2d.cu, LAZY mode).
-template <int LM, int ROWS>
-__global__ void __launch_bounds__(ROWS * FftPlan<LM>::G)
+template <int LM, int ROWS, int LEMAX>
+__global__ void __launch_bounds__(ROWS * FftPlan<LM, LEMAX, 4>::G)
 irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
                   const float2* __restrict__ tw, const float2* __restrict__ rtw) {
-  using P = FftPlan<LM>;
+  using P = FftPlan<LM, LEMAX, 4>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, ROWS);
   constexpr int NT = ROWS * G;
@@ -453,9 +454,16 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
   auto go = [&](auto rows_c) -> int {
     constexpr int ROWS = decltype(rows_c)::value;
     constexpr size_t smem = (size_t)ROWS * row_stride(P::M, ROWS) * sizeof(float2);
-    auto k = rfft_rows_kernel<LM, ROWS>;
-    if (int e = set_smem(k, smem)) return e;
-    k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+    if (rows_lemax(LM) == 5 && LM >= 5) {
+      using P5 = FftPlan<LM, 5, 4>;
+      auto k = rfft_rows_kernel<LM, ROWS, 5>;
+      if (int e = set_smem(k, smem)) return e;
+      k<<<dim3(Nx / ROWS, batch), ROWS * P5::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+    } else {
+      auto k = rfft_rows_kernel<LM, ROWS, 4>;
+      if (int e = set_smem(k, smem)) return e;
+      k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+    }
     count_launch();
     CFD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -477,10 +485,10 @@ template <int LM, int LEMAX>
 int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
                      size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
                      const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
-  using P = FftPlan<LM, LEMAX>;
+  using P = FftPlan<LM, LEMAX, 4>;
   constexpr int LINES = (P::G >= 256) ? 1 : (256 / P::G > 16 ? 16 : 256 / P::G);
   // two exchange buffers (one barrier per pass) whenever both fit beside a second CTA's
-  constexpr bool DB = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2) <= 72 * 1024;
+  constexpr bool DB = LEMAX == 4 && (size_t)LINES * row_stride(P::M, 16) * sizeof(float2) <= 72 * 1024;
   constexpr size_t smem = (size_t)(DB ? 2 : 1) * LINES * row_stride(P::M, 16) * sizeof(float2);
   if (nlines % LINES || (!split && line_begin % LINES)) return set_error_msg("internal: line count not divisible");
   auto go = [&](auto k) -> int {
@@ -571,9 +579,16 @@ int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, i
   auto go = [&](auto rows_c) -> int {
     constexpr int ROWS = decltype(rows_c)::value;
     constexpr size_t smem = (size_t)ROWS * row_stride(P::M, ROWS) * sizeof(float2);
-    auto k = irfft_rows_kernel<LM, ROWS>;
-    if (int e = set_smem(k, smem)) return e;
-    k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(T, q, Nx, tw, rtw);
+    if (rows_lemax(LM) == 5 && LM >= 5) {
+      using P5 = FftPlan<LM, 5, 4>;
+      auto k = irfft_rows_kernel<LM, ROWS, 5>;
+      if (int e = set_smem(k, smem)) return e;
+      k<<<dim3(Nx / ROWS, batch), ROWS * P5::G, smem, st>>>(T, q, Nx, tw, rtw);
+    } else {
+      auto k = irfft_rows_kernel<LM, ROWS, 4>;
+      if (int e = set_smem(k, smem)) return e;
+      k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(T, q, Nx, tw, rtw);
+    }
     count_launch();
     CFD_CUDA_OK(cudaGetLastError());
     return 0;
