@@ -102,6 +102,12 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
     return base + boff + (size_t)i * Ny + jg;
   };
 
+  // The face velocity U = 0.5 (a + b) (interpolation.py:57-62) is carried as 2U = a + b: the factor
+  // 0.5 is a power of two, so folding it into dt/h (Courant number) and into 1/h (flux divergence)
+  // gives bit-identical results (away from underflow) and saves one multiply per face.
+  const float dth0h = 0.5f * c.dth[0], dth1h = 0.5f * c.dth[1];
+  const float ih0h = 0.5f * c.inv_h[0], ih1h = 0.5f * c.inv_h[1];
+
   // window rows i-2 .. i+2 for the first processed row i = i0 - 1
   Row ua[5], va[5];
 #pragma unroll
@@ -137,11 +143,11 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
     const float uR1 = __shfl_down_sync(FULLMASK, ua[1].a[0], 1);
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-      const float Uu = 0.5f * (ua[1].a[k] + ua[2].a[k]);
-      f0u_prev.a[k] = face_flux(ua[0].a[k], ua[1].a[k], ua[2].a[k], ua[3].a[k], Uu, c.dth[0]);
+      const float Uu = ua[1].a[k] + ua[2].a[k];
+      f0u_prev.a[k] = face_flux(ua[0].a[k], ua[1].a[k], ua[2].a[k], ua[3].a[k], Uu, dth0h);
       const float unext = (k < C - 1) ? ua[1].a[(k + 1) % C] : uR1;
-      const float Uv = 0.5f * (ua[1].a[k] + unext);
-      f0v_prev.a[k] = face_flux(va[0].a[k], va[1].a[k], va[2].a[k], va[3].a[k], Uv, c.dth[0]);
+      const float Uv = ua[1].a[k] + unext;
+      f0v_prev.a[k] = face_flux(va[0].a[k], va[1].a[k], va[2].a[k], va[3].a[k], Uv, dth0h);
     }
   }
   Row us_prev;
@@ -238,18 +244,18 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
     float f1u[C + 1], f1v[C + 1];  // y-faces (j' | j'+1), j' = -1 .. C-1
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-      const float Uu = 0.5f * (ua[2].a[k] + ua[3].a[k]);  // interpolation.py:57-62
-      f0u.a[k] = face_flux(ua[1].a[k], ua[2].a[k], ua[3].a[k], ua[4].a[k], Uu, c.dth[0]);
-      const float Uv = 0.5f * (ue[2 + k] + ue[3 + k]);
-      f0v.a[k] = face_flux(va[1].a[k], va[2].a[k], va[3].a[k], va[4].a[k], Uv, c.dth[0]);
+      const float Uu = ua[2].a[k] + ua[3].a[k];  // 2 U, interpolation.py:57-62
+      f0u.a[k] = face_flux(ua[1].a[k], ua[2].a[k], ua[3].a[k], ua[4].a[k], Uu, dth0h);
+      const float Uv = ue[2 + k] + ue[3 + k];
+      f0v.a[k] = face_flux(va[1].a[k], va[2].a[k], va[3].a[k], va[4].a[k], Uv, dth0h);
     }
 #pragma unroll
     for (int f = 0; f < C + 1; ++f) {  // face j' = f - 1 ; stencil columns j'-1..j'+2 = ext[f .. f+3]
       const float vnext = (f == 0) ? vnL1 : va[3].a[(f + C - 1) % C];  // v[i+1][j']
-      const float Uu = 0.5f * (ve[f + 1] + vnext);
-      f1u[f] = face_flux(ue[f], ue[f + 1], ue[f + 2], ue[f + 3], Uu, c.dth[1]);
-      const float Uv = 0.5f * (ve[f + 1] + ve[f + 2]);
-      f1v[f] = face_flux(ve[f], ve[f + 1], ve[f + 2], ve[f + 3], Uv, c.dth[1]);
+      const float Uu = ve[f + 1] + vnext;
+      f1u[f] = face_flux(ue[f], ue[f + 1], ue[f + 2], ue[f + 3], Uu, dth1h);
+      const float Uv = ve[f + 1] + ve[f + 2];
+      f1v[f] = face_flux(ve[f], ve[f + 1], ve[f + 2], ve[f + 3], Uv, dth1h);
     }
 
     // ---- assemble
@@ -269,8 +275,8 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
     for (int k = 0; k < C; ++k) {
       const float u0 = ua[2].a[k], v0 = va[2].a[k];
       // -divergence(flux)   advection.py:78, finite_differences.py:136-143
-      float du = -((f0u.a[k] - f0u_prev.a[k]) * c.inv_h[0] + (f1u[k + 1] - f1u[k]) * c.inv_h[1]);
-      float dv = -((f0v.a[k] - f0v_prev.a[k]) * c.inv_h[0] + (f1v[k + 1] - f1v[k]) * c.inv_h[1]);
+      float du = -((f0u.a[k] - f0u_prev.a[k]) * ih0h + (f1u[k + 1] - f1u[k]) * ih1h);
+      float dv = -((f0v.a[k] - f0v_prev.a[k]) * ih0h + (f1v[k + 1] - f1v[k]) * ih1h);
       if (c.has_nu) {  // finite_differences.py:127-133, diffusion.py:35-37
         float lu = (-2.f * u0) * c.lap_sum;
         lu += (ua[1].a[k] + ua[3].a[k]) * c.lap_s[0];
