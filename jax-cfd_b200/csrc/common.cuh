@@ -17,6 +17,7 @@ struct StepConsts {
   float inv_h[CFD_MAX_DIM]; // 1 / h_j   (divisions by h_j become multiplications: <= 1 ulp)
   float lap_s[CFD_MAX_DIM]; // square(1 / float32(h_j))
   float lap_sum;            // float32 sum of lap_s
+  float lap_m2sum;          // -2 * lap_sum (exact): (-2 c) * sum == c * (-2 sum) bitwise
   float nu;                 // viscosity / density
   float rho;                // density (forcing / rho, equations.py:109)
   float inv_rho;            // 1 / density

@@ -209,7 +209,10 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
     if (c.field[1]) nfv = ldrow<C>(c.field[1] + (size_t)iwf * Ny + jg);
   }
 
-#pragma unroll 1
+  // two rows per trip in the lazy kernel: half of the window-rotation moves disappear (423 -> 407 us
+  // at 8192^2; the plain kernel gets slower with it, 407 -> 421 us, and keeps one row per trip)
+  constexpr int kRowUnroll = LAZY ? 2 : 1;
+#pragma unroll kRowUnroll
   for (int i = i0 - 1; i < iend; ++i) {
     // ---- column halos of row i (and v[i+1][-1]) from neighbouring lanes
     float ue[C + 4], ve[C + 4];
@@ -278,10 +281,10 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
       float du = -((f0u.a[k] - f0u_prev.a[k]) * ih0h + (f1u[k + 1] - f1u[k]) * ih1h);
       float dv = -((f0v.a[k] - f0v_prev.a[k]) * ih0h + (f1v[k + 1] - f1v[k]) * ih1h);
       if (c.has_nu) {  // finite_differences.py:127-133, diffusion.py:35-37
-        float lu = (-2.f * u0) * c.lap_sum;
+        float lu = u0 * c.lap_m2sum;  // (-2 u) * sum_j s_j
         lu += (ua[1].a[k] + ua[3].a[k]) * c.lap_s[0];
         lu += (ue[1 + k] + ue[3 + k]) * c.lap_s[1];
-        float lv = (-2.f * v0) * c.lap_sum;
+        float lv = v0 * c.lap_m2sum;
         lv += (va[1].a[k] + va[3].a[k]) * c.lap_s[0];
         lv += (ve[1 + k] + ve[3 + k]) * c.lap_s[1];
         du += c.nu * lu;

@@ -265,6 +265,10 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
   const int i0 = xb * TX, iend = min(i0 + TX, N0);
   const size_t planeN = (size_t)N1 * N2;
   const int own = (ty + 2) * kHZ + 2 * lane + kZ0;  // own position inside the halo tile
+  // face velocities are carried as 2U = a + b; the exact factor 0.5 lives in dt/h and 1/h instead
+  // (bit-identical, one multiply less per face -- see explicit_2d.cu)
+  const float dthh[3] = {0.5f * c.dth[0], 0.5f * c.dth[1], 0.5f * c.dth[2]};
+  const float ihh[3] = {0.5f * c.inv_h[0], 0.5f * c.inv_h[1], 0.5f * c.inv_h[2]};
 
   // Plane loader: threads 0..191 move one aligned float4 of the interior (12 rows x 16), threads
   // 192..239 one halo element (12 rows x 4); source offsets inside a plane are loop invariant.
@@ -344,8 +348,8 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
     for (int col = 0; col < 2; ++col) {
       const float ua = g(0, -1, 0, col);
       const float ub = A == 0 ? g(0, 0, 0, col) : (A == 1 ? g(0, -1, 1, col) : g(0, -1, 0, col + 1));
-      const float U = 0.5f * (ua + ub);
-      Fxp[A][col] = face_flux(X[A][1][col], X[A][2][col], X[A][3][col], X[A][4][col], U, c.dth[0]);
+      const float U = ua + ub;
+      Fxp[A][col] = face_flux(X[A][1][col], X[A][2][col], X[A][3][col], X[A][4][col], U, dthh[0]);
     }
 
   for (int i = i0; i < iend; ++i) {
@@ -378,29 +382,29 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
       float Fz[3];
 #pragma unroll
       for (int fz = 0; fz < 3; ++fz) {
-        const float U = 0.5f * (g(2, 0, 0, fz - 1) + g(2, ex[A], ey[A], fz - 1 + ez[A]));
+        const float U = g(2, 0, 0, fz - 1) + g(2, ex[A], ey[A], fz - 1 + ez[A]);
         Fz[fz] = face_flux(g(A, 0, 0, fz - 2), g(A, 0, 0, fz - 1), g(A, 0, 0, fz), g(A, 0, 0, fz + 1), U,
-                           c.dth[2]);
+                           dthh[2]);
       }
       float out[2];
 #pragma unroll
       for (int col = 0; col < 2; ++col) {
         const float c0 = X[A][2][col];
         // x direction: new face (i | i+1), carried face (i-1 | i)
-        const float Ux = 0.5f * (g(0, 0, 0, col) + g(0, ex[A], ey[A], col + ez[A]));
-        const float Fx = face_flux(X[A][1][col], X[A][2][col], X[A][3][col], X[A][4][col], Ux, c.dth[0]);
+        const float Ux = g(0, 0, 0, col) + g(0, ex[A], ey[A], col + ez[A]);
+        const float Fx = face_flux(X[A][1][col], X[A][2][col], X[A][3][col], X[A][4][col], Ux, dthh[0]);
         // y direction: faces (j | j+1) and (j-1 | j)
-        const float Uyp = 0.5f * (g(1, 0, 0, col) + g(1, ex[A], ey[A], col + ez[A]));
-        const float Fyp = face_flux(g(A, 0, -1, col), c0, g(A, 0, 1, col), g(A, 0, 2, col), Uyp, c.dth[1]);
-        const float Uym = 0.5f * (g(1, 0, -1, col) + g(1, ex[A], ey[A] - 1, col + ez[A]));
-        const float Fym = face_flux(g(A, 0, -2, col), g(A, 0, -1, col), c0, g(A, 0, 1, col), Uym, c.dth[1]);
-        float conv = (Fx - Fxp[A][col]) * c.inv_h[0];
-        conv += (Fyp - Fym) * c.inv_h[1];
-        conv += (Fz[col + 1] - Fz[col]) * c.inv_h[2];
+        const float Uyp = g(1, 0, 0, col) + g(1, ex[A], ey[A], col + ez[A]);
+        const float Fyp = face_flux(g(A, 0, -1, col), c0, g(A, 0, 1, col), g(A, 0, 2, col), Uyp, dthh[1]);
+        const float Uym = g(1, 0, -1, col) + g(1, ex[A], ey[A] - 1, col + ez[A]);
+        const float Fym = face_flux(g(A, 0, -2, col), g(A, 0, -1, col), c0, g(A, 0, 1, col), Uym, dthh[1]);
+        float conv = (Fx - Fxp[A][col]) * ihh[0];
+        conv += (Fyp - Fym) * ihh[1];
+        conv += (Fz[col + 1] - Fz[col]) * ihh[2];
         Fxp[A][col] = Fx;
         float dv = -conv;
         if (c.has_nu) {
-          float l = (-2.f * c0) * c.lap_sum;
+          float l = c0 * c.lap_m2sum;  // (-2 c) * sum_j s_j
           l += (X[A][1][col] + X[A][3][col]) * c.lap_s[0];
           l += (g(A, 0, -1, col) + g(A, 0, 1, col)) * c.lap_s[1];
           l += (g(A, 0, 0, col - 1) + g(A, 0, 0, col + 1)) * c.lap_s[2];

@@ -146,6 +146,7 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
   // np.sum over a float32 array of <= 3 entries: sequential float32 adds
   for (int j = 0; j < d; ++j) lap_sum = (j == 0) ? c->lap_s[0] : lap_sum + c->lap_s[j];
   c->lap_sum = lap_sum;
+  c->lap_m2sum = -2.f * lap_sum;
   c->has_nu = prm->has_viscosity ? 1 : 0;
   c->nu = (float)(prm->viscosity / prm->density);
   c->rho = (float)prm->density;

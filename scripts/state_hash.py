@@ -21,3 +21,19 @@ h = hashlib.sha256()
 for a in out:
   h.update(np.ascontiguousarray(np.asarray(a.data)).tobytes())
 print(os.environ.get('CFD_B200_LIB', 'default').split('/')[-1], h.hexdigest()[:16], float(np.abs(np.asarray(out[0].data)).max()))
+
+# 3-D case with the Smagorinsky closure (marching kernels)
+shape3 = (64, 32, 64)
+g3 = cfd.grids.Grid(shape3, domain=((0, 2 * np.pi),) * 3)
+v3 = [rs.standard_normal(shape3).astype(np.float32) for _ in range(3)]
+bc3 = cfd.boundaries.periodic_boundary_conditions(3)
+step3 = cfd.subgrid_models.explicit_smagorinsky_navier_stokes(dt=2e-3, cs=0.2, forcing=None, density=1.0, viscosity=1e-3, grid=g3)
+w = tuple(cfd.grids.GridVariable(cfd.grids.GridArray(cfd.DeviceArray.from_numpy(a), o, g3), bc3)
+          for a, o in zip(v3, g3.cell_faces))
+w = cfd.pressure.projection(w)
+for _ in range(3):
+  w = step3(w)
+h = hashlib.sha256()
+for a in w:
+  h.update(np.ascontiguousarray(np.asarray(a.data)).tobytes())
+print('3d', h.hexdigest()[:16], float(np.abs(np.asarray(w[0].data)).max()))
