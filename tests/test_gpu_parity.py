@@ -112,8 +112,13 @@ def test_projection_matches_reference_golden(cfd, name):
   assert np.abs(div).max() < 1e-3  # white-noise input of magnitude ~3/h
 
 
+# The thin shapes run every FFT kernel variant at its full-size line length (x lines of 4096 / 8192
+# points: 32 points per thread, two CTAs per SM; 16384: one 1024-thread CTA; 32768: the split
+# transform; rows of 8192 / 16384 reals) at a cell count the oracle finishes in seconds.
 @pytest.mark.parametrize('shape,nsteps', [((256, 256), 10), ((512, 1024), 3), ((1024, 64), 3),
-                                         ((16, 32), 5), ((2048, 2048), 1)])
+                                         ((16, 32), 5), ((2048, 2048), 1), ((8192, 64), 3),
+                                         ((4096, 128), 3), ((16384, 32), 2), ((32768, 32), 2),
+                                         ((64, 8192), 3), ((32, 16384), 2)])
 def test_step_matches_oracle(cfd, shape, nsteps):
   dom = ((0.0, 2 * np.pi), (0.0, 2 * np.pi))
   grid = cfd.grids.Grid(shape, domain=dom)
@@ -131,9 +136,25 @@ def test_step_matches_oracle(cfd, shape, nsteps):
     want, wq = cfd_oracle.step(want, dt, grid.step, 1.0, nu, of, return_q=True)
   for a, b in zip(to_np(got), want):
     assert gu.rel_l2(a, b) < TOL
-  assert gu.rel_l2(np.asarray(q), wq) < TOL
-  # divergence-free residual (equations_test.py:99: max|div| stays small)
-  assert np.abs(cfd_oracle.divergence(to_np(got), grid.step)).max() < 2e-3
+  if max(shape) < 64 * min(shape):
+    assert gu.rel_l2(np.asarray(q), wq) < TOL
+  else:
+    # Cells stretched 128:1 and more: q itself is ill-conditioned in float32 (the reference's own
+    # f32 run is 6e-6 away from its f64 run at 16384x32), so q is held to the float32 reference's
+    # distance from the float64 answer instead; the velocities above keep the 1e-5 bar.
+    w64 = [a.astype(np.float64) for a in v0]
+    of64 = cfd_oracle.Forcing((('const', [a.astype(np.float64) for a in
+                                          cfd_oracle.kolmogorov_field(shape, dom, 1.0, 4)]),
+                               ('linear', -0.1)))
+    for n in range(nsteps):
+      w64, q64 = cfd_oracle.step(w64, dt, grid.step, 1.0, nu, of64, return_q=True)
+    assert q64.dtype == np.float64
+    floor = gu.rel_l2(wq, q64)
+    assert gu.rel_l2(np.asarray(q), q64) < max(TOL, 3 * floor)
+  # divergence-free residual (equations_test.py:99: max|div| stays small); it is rounding noise
+  # divided by h, so on the very fine thin grids it is held to the reference's own residual
+  ref_div = np.abs(cfd_oracle.divergence(want, grid.step)).max()
+  assert np.abs(cfd_oracle.divergence(to_np(got), grid.step)).max() < max(2e-3, 3 * ref_div)
 
 
 def test_host_and_device_paths_agree_bitwise(cfd):
