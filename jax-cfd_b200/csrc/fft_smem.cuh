@@ -160,48 +160,6 @@ struct Dft<16, DIR> {
   static __device__ __forceinline__ void run(float2 (&a)[16]) { dft16<DIR>(a); }
 };
 
-template <int DIR>
-__device__ __forceinline__ void dft32(float2 (&a)[32]) {
-  float2 e[16], o[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    e[i] = a[2 * i];
-    o[i] = a[2 * i + 1];
-  }
-  dft16<DIR>(e);
-  dft16<DIR>(o);
-  // forward twiddles exp(-2 pi i k / 32), k = 1..15
-  constexpr float c1 = 0.98078528040323044913f, s1 = 0.19509032201612826785f;
-  constexpr float c2 = 0.92387953251128675613f, s2 = 0.38268343236508977173f;
-  constexpr float c3 = 0.83146961230254523708f, s3 = 0.55557023301960222474f;
-  constexpr float h = 0.70710678118654752440f;
-  o[1] = twmul<DIR>(o[1], make_float2(c1, -s1));
-  o[2] = twmul<DIR>(o[2], make_float2(c2, -s2));
-  o[3] = twmul<DIR>(o[3], make_float2(c3, -s3));
-  o[4] = twmul<DIR>(o[4], make_float2(h, -h));
-  o[5] = twmul<DIR>(o[5], make_float2(s3, -c3));
-  o[6] = twmul<DIR>(o[6], make_float2(s2, -c2));
-  o[7] = twmul<DIR>(o[7], make_float2(s1, -c1));
-  o[8] = mul_dir_i<DIR>(o[8]);
-  o[9] = twmul<DIR>(o[9], make_float2(-s1, -c1));
-  o[10] = twmul<DIR>(o[10], make_float2(-s2, -c2));
-  o[11] = twmul<DIR>(o[11], make_float2(-s3, -c3));
-  o[12] = twmul<DIR>(o[12], make_float2(-h, -h));
-  o[13] = twmul<DIR>(o[13], make_float2(-c3, -s3));
-  o[14] = twmul<DIR>(o[14], make_float2(-c2, -s2));
-  o[15] = twmul<DIR>(o[15], make_float2(-c1, -s1));
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    a[k] = cadd(e[k], o[k]);
-    a[k + 16] = csub(e[k], o[k]);
-  }
-}
-
-template <int DIR>
-struct Dft<32, DIR> {
-  static __device__ __forceinline__ void run(float2 (&a)[32]) { dft32<DIR>(a); }
-};
-
 // ---- radix plan -------------------------------------------------------------------------------
 // M = 2^LM points, E = min(2^LEMAX, M) points per thread, radix min(2^LRMAX, E) (defaults: 16
 // points, radix-16 passes; <LM, 5, 4>: 32 points = two radix-16 butterflies per thread and pass).

@@ -163,8 +163,8 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
 #define CFD_XL_MINB 1
 #endif
 template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT, bool DB>
-__global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX>::G,
-                                  (LEMAX == 5 && LINES * FftPlan<LM, LEMAX>::G <= 256) ? 2 : CFD_XL_MINB)
+__global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX, 4>::G,
+                                  (LEMAX == 5 && LINES * FftPlan<LM, LEMAX, 4>::G <= 256) ? 2 : CFD_XL_MINB)
 xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
