@@ -24,14 +24,14 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
                             float* vs, float* rhs, int batch, int Nx, int Ny, int row0,
                             int nx_global, const StepConsts& c, int dvdt_mode);
 int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
-                     const float2* tw, const float2* rtw);
+                     const float2* tw, const float2* rtw, int paired);
 int launch_irfft_rows(cudaStream_t, int lm_row, const float2* T, float* q, int batch, int Nx,
-                      const float2* tw, const float2* rtw);
+                      const float2* tw, const float2* rtw, int paired);
 int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int lnloc,
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig, const SideStreams* side);
+                        const float2* wbig, const SideStreams* side, int paired);
 int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
                       const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
                       float inv_hx, float inv_hy);
@@ -160,7 +160,7 @@ int xpass_staged(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int lnloc)
     prof_mark(p, st, "xwait_in");
     if (int e = launch_xlines_peers(st, p->lm_x, tab, lnloc, gl0 + lb, chunk, My, p->tw_x, p->lam[0],
                                     p->lam[1], p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
-                                    p->xscratch, p->wbig, nullptr))
+                                    p->xscratch, p->wbig, nullptr, p->t_paired))
       return e;
     CFD_CUDA_OK(cudaEventRecord(p->ev_comp[c], st));
     prof_mark(p, st, "xchunk");
@@ -330,7 +330,8 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
     }
     prof_mark(p, st, "explicit_2d_slab");
     float2* Tloc = reinterpret_cast<float2*>(fptr(p->shared, L.off_T));
-    if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, Tloc, 1, nloc, p->tw_row, p->rtw)) return e;
+    if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, Tloc, 1, nloc, p->tw_row, p->rtw, p->t_paired))
+      return e;
     prof_mark(p, st, "rfft_rows");
     if (int e = barrier(p, st)) return e;  // every rank's slab spectrum is complete
     if (p->xstage) {
@@ -338,13 +339,13 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
     } else if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
                                            lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1],
                                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
-                                           p->xscratch, p->wbig, &p->side)) {
+                                           p->xscratch, p->wbig, &p->side, p->t_paired)) {
       return e;
     }
     prof_mark(p, st, "xlines_peers");
     if (int e = barrier(p, st)) return e;  // every rank has written its lines back into my slab
     if (int e = launch_irfft_rows(st, p->lm_row, Tloc, fptr(p->shared, L.off_q[nxt]), 1, nloc,
-                                  p->tw_row, p->rtw))
+                                  p->tw_row, p->rtw, p->t_paired))
       return e;
     prof_mark(p, st, "irfft_rows");
     p->dist_cur = nxt;

@@ -1,6 +1,7 @@
 // Plan management + the extern "C" ABI declared in include/cfd_b200.h.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -19,16 +20,16 @@ int launch_explicit_2d(cudaStream_t, const float* u, const float* v, const float
                        float* vs, float* rhs, int batch, int Nx, int Ny, const StepConsts& c,
                        int dvdt_mode);
 int launch_irfft_rows(cudaStream_t, int lm_row, const float2* T, float* q, int batch, int Nx,
-                      const float2* tw, const float2* rtw);
+                      const float2* tw, const float2* rtw, int paired);
 int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
                       const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
                       float inv_hx, float inv_hy);
 int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
-                     const float2* tw, const float2* rtw);
+                     const float2* tw, const float2* rtw, int paired);
 int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
                   int fastd, double cutoff, float norm, float2* scratch, const float2* wbig,
-                  const SideStreams* side);
+                  const SideStreams* side, int paired);
 int launch_divergence_2d(cudaStream_t, const float* u, const float* v, float* rhs, int batch,
                          int Nx, int Ny, float inv_hx, float inv_hy);
 int launch_axpy(cudaStream_t, const float* x, int nterms, const float* const* y, const float* coef,
@@ -204,6 +205,23 @@ int big_line_tables(cfd_plan* p, size_t nlines) {
   return err;
 }
 
+// Which layout the 2-D spectrum uses (poisson_2d.cu): pairs of ky lines interleaved when the row
+// kernels hold only one or two rows per CTA (rows of >= 16384 reals: the transposed chunks would be
+// 8 / 16 bytes) and the x lines are ones the stride-2 access is built for -- 4096 / 8192 points in
+// the kernel itself, 32768 through the pair-wise split / merge.  Measured on one B200:
+//   4096 x 16384:  rfft 318 -> 218, x lines 205 -> 226, irfft 293 -> 268 us   (paired wins)
+//   8192 x 8192:   rfft 190 -> 183, x lines 223 -> 257, irfft 237 -> 214 us   (a wash: plain)
+// Several GPUs: only with the 32768-point split transform, whose peer accesses stay full 16-byte
+// pieces; a half-used sector in the x-line kernel would double the NVLink traffic.
+// CFD_T_PAIRED=0|1 overrides where the layout is supported.
+static int choose_t_paired(int ndim, int lm_row, int lm_x, int world) {
+  if (ndim != 2) return 0;
+  const bool supported = (lm_x == 12 || lm_x == 13 || lm_x == 15);
+  int want = supported && lm_row >= 13 && (world <= 1 || lm_x == 15);
+  if (const char* e = getenv("CFD_T_PAIRED")) want = supported && atoi(e) != 0 && (world <= 1 || lm_x == 15);
+  return want ? 1 : 0;
+}
+
 int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double* step) {
   const int Nxg = (int)shape[0];
   cudaFree(p->tw_x);
@@ -213,6 +231,7 @@ int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double
   p->lam[0] = nullptr;
   p->lamf[0] = nullptr;
   p->lm_x = ilog2(Nxg);
+  p->t_paired = choose_t_paired(ndim, p->lm_row, p->lm_x, p->world);
   int err = upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x));
   if (p->lm_x == 15) err |= big_line_tables(p, (size_t)(shape[1] / 2) / (p->world > 0 ? p->world : 1));
   std::vector<double> lam(Nxg);
@@ -246,14 +265,16 @@ int check_plan(const cfd_plan* p) {
 // q = pinv(rhs): rfft rows -> x lines (fwd * D * inv) -> irfft rows
 int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
   const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
-  if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw)) return e;
+  if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw, p->t_paired))
+    return e;
   prof_mark(p, st, "rfft_rows");
   if (int e = launch_xlines(st, p->lm_x, p->T, p->batch, Ny / 2, p->tw_x, p->lam[0], p->lam[1],
                             p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig,
-                            &p->side))
+                            &p->side, p->t_paired))
     return e;
   prof_mark(p, st, "xlines");
-  if (int e = launch_irfft_rows(st, p->lm_row, p->T, q, p->batch, Nx, p->tw_row, p->rtw)) return e;
+  if (int e = launch_irfft_rows(st, p->lm_row, p->T, q, p->batch, Nx, p->tw_row, p->rtw, p->t_paired))
+    return e;
   prof_mark(p, st, "irfft_rows");
   return 0;
 }
@@ -392,6 +413,7 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   const int Nx = (int)shape[0], Ny = (int)shape[ndim - 1];
   p->lm_row = ilog2(Ny / 2);
   p->lm_x = ilog2(Nx);
+  p->t_paired = choose_t_paired(ndim, p->lm_row, p->lm_x, p->world);
   int err = 0;
   err |= upload(&p->tw_row, build_twiddles(p->lm_row));
   err |= upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x));

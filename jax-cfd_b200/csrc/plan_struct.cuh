@@ -35,6 +35,7 @@ struct cfd_plan {
   float* qbuf = nullptr;   // pressure of the latest step
   float* qbuf2 = nullptr;  // pong
   float2* T = nullptr;
+  int t_paired = 0;  // 2-D spectrum layout: 1 = pairs of ky lines interleaved (poisson_2d.cu)
   size_t workspace_bytes = 0;
   // host-call staging
   float* dev_a[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};

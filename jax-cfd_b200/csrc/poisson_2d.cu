@@ -29,10 +29,18 @@ namespace cfd {
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// R: rows of `rhs` (N = 2M reals each)  ->  T[b][ky][x]   (ky = 0..M-1, packed)
+// Layouts of the packed spectrum T (M = Ny/2 lines per batch member, M even):
+//   plain:   T[b][ky][x]
+//   PAIRED:  T[b][ky >> 1][x][ky & 1]   pairs of ky lines interleaved, so that the transposed
+//            accesses of the row kernels (ROWS consecutive x for one ky) are chunks of ROWS * 16
+//            bytes instead of ROWS * 8.  An x line is then a stride-2 sequence (the partner line's
+//            CTA uses the other half of every sector).  The plan picks the layout
+//            (choose_t_paired, plan.cu, with the measurements).
+//
+// R: rows of `rhs` (N = 2M reals each)  ->  T   (ky = 0..M-1, packed)
 // LEMAX = 5: 32 points (two radix-16 butterflies per pass) per thread, half the threads per row.
-template <int LM, int ROWS, int LEMAX>
-__global__ void __launch_bounds__(ROWS * FftPlan<LM, LEMAX, 4>::G)
+template <int LM, int ROWS, int LEMAX, bool PAIRED>
+__global__ void __launch_bounds__(ROWS * FftPlan<LM, LEMAX, 4>::G, (ROWS * FftPlan<LM, LEMAX, 4>::G <= 512) ? 2 : 0)
 rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
                  const float2* __restrict__ tw, const float2* __restrict__ rtw) {
   using P = FftPlan<LM, LEMAX, 4>;
@@ -76,12 +84,20 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
   }
   __syncthreads();
   // transposed store: for each ky the ROWS values of this CTA are contiguous in T
-  float2* Tb = T + b * (size_t)M * Nx + x0;
+  float2* Tb = T + b * (size_t)M * Nx + (PAIRED ? 2 : 1) * (size_t)x0;
   constexpr int NT = ROWS * G;
+  if constexpr (PAIRED) {
 #pragma unroll 4
-  for (int idx = tid; idx < ROWS * M; idx += NT) {
-    const int r = idx % ROWS, ky = idx / ROWS;
-    Tb[(size_t)ky * Nx + r] = smem[r * RS + PAD(ky)];
+    for (int idx = tid; idx < ROWS * M; idx += NT) {
+      const int p = idx & 1, r = (idx >> 1) % ROWS, j = idx / (2 * ROWS);
+      Tb[((size_t)j * Nx + r) * 2 + p] = smem[r * RS + PAD(2 * j + p)];
+    }
+  } else {
+#pragma unroll 4
+    for (int idx = tid; idx < ROWS * M; idx += NT) {
+      const int r = idx % ROWS, ky = idx / ROWS;
+      Tb[(size_t)ky * Nx + r] = smem[r * RS + PAD(ky)];
+    }
   }
 }
 
@@ -162,7 +178,7 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
 #ifndef CFD_XL_MINB
 #define CFD_XL_MINB 1
 #endif
-template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT, bool DB>
+template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT, bool DB, bool PAIRED>
 __global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX, 4>::G,
                                   (LEMAX == 5 && LINES * FftPlan<LM, LEMAX, 4>::G <= 256) ? 2 : CFD_XL_MINB)
 xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
@@ -185,8 +201,11 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   const int kmul = split ? 2 : 1, kadd = split ? (int)((idx0 + ln) & 1) : 0;
   float2* s = smem + ln * RS;
   const int nloc_mask = (1 << lnloc) - 1;
-  // this line's offset inside every rank's buffer (split: inside the scratch)
-  const size_t loff = split ? (idx0 + ln) << LM : line << lnloc;
+  // this line's offset inside every rank's buffer (PAIRED: pair-interleaved, element stride 2);
+  // split: inside the scratch (plain contiguous half-lines)
+  const size_t loff = split ? (idx0 + ln) << LM
+                            : (PAIRED ? (((line >> 1) << lnloc) << 1) + (line & 1) : line << lnloc);
+  constexpr int XS = (!SPLIT && PAIRED) ? 2 : 1;
   // One GPU (lnloc == LM): plain contiguous line.  Several GPUs: peer table in shared memory (a
   // dynamically indexed kernel parameter would live in local memory).
   __shared__ float2* s_peer[CFD_MAX_PEERS];
@@ -197,7 +216,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   }
   float2* const Tl = peers.p[0] + loff;
   auto elem = [&](int x) -> float2* {
-    return single ? Tl + x : s_peer[x >> lnloc] + loff + (x & nloc_mask);
+    return single ? Tl + XS * x : s_peer[x >> lnloc] + loff + XS * (x & nloc_mask);
   };
 
   float2 v[E];
@@ -218,73 +237,6 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   FftRun<P, +1, SyncCta, DB, (P::NP - 1) & 1, PRE>::run(v, t, s, tw, 0, ALT);
 #pragma unroll
   for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
-}
-
-// ------------------------------------------------------------------------------------------
-// X, software-pipelined variant for long lines (one line per CTA, 4096 or 8192 points): persistent
-// CTAs stride over their lines; while line n is transformed (registers + exchange buffer), line
-// n+1 is already streaming into a second shared-memory buffer with cp.async (LDGSTS, no registers),
-// and the stores of line n-1 drain asynchronously -- the load phase (HBM, or NVLink peer memory on
-// several GPUs) disappears from the critical path.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int LM, bool FASTD>
-__global__ void __launch_bounds__(FftPlan<LM>::G)
-xlines_pipe_kernel(LinePeers peers, int lnloc, size_t line_begin, size_t nlines, int My, int split,
-                   const float2* __restrict__ tw, const double* __restrict__ lamx,
-                   const double* __restrict__ lamy, const float* __restrict__ lamxf,
-                   const float* __restrict__ lamyf, double cutoff, float norm) {
-  using P = FftPlan<LM>;
-  constexpr int M = P::M, G = P::G, E = P::E;
-  constexpr int RS = row_stride(M, 16);
-  extern __shared__ float2 smem[];
-  float2* s = smem;        // exchange buffer (padded)
-  float2* pre = smem + ((RS + 1) & ~1);  // prefetch buffer: M float2, 16-byte aligned
-  const int t = threadIdx.x;
-  __shared__ float2* s_peer[CFD_MAX_PEERS];
-  if (t < CFD_MAX_PEERS) s_peer[t] = peers.p[t];
-  __syncthreads();
-  const int nloc_mask = (1 << lnloc) - 1;
-  auto line_of = [&](size_t li) { return split ? line_begin + (li >> 1) : line_begin + li; };
-  auto loff_of = [&](size_t li) { return split ? li << LM : (line_begin + li) << lnloc; };
-  auto elem = [&](size_t loff, int x) -> float2* {
-    return s_peer[x >> lnloc] + loff + (x & nloc_mask);
-  };
-  auto prefetch = [&](size_t li) {
-    const size_t loff = loff_of(li);
-#pragma unroll
-    for (int c = 0; c < E / 2; ++c) {
-      const int x = 2 * (t + G * c);  // 16 bytes = 2 points, never straddles a rank boundary
-      cp_async16(pre + x, elem(loff, x));
-    }
-    cp_async_commit();
-  };
-  size_t li = blockIdx.x;
-  if (li < nlines) prefetch(li);
-  for (; li < nlines; li += gridDim.x) {
-    const size_t line = line_of(li);
-    const size_t loff = loff_of(li);
-    const int ky = (int)(line % My);
-    const int kmul = split ? 2 : 1, kadd = split ? (int)(li & 1) : 0;
-    cp_async_wait_all();
-    __syncthreads();
-    float2 v[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = pre[t + G * e];
-    __syncthreads();  // everyone has drained the prefetch buffer
-    if (li + gridDim.x < nlines) prefetch(li + gridDim.x);
-    FftRun<P, -1>::run(v, t, s, tw);
-    scale_line<P, FASTD>(v, t, s, ky, My, ky == 0, kmul, kadd, lamx, lamy, lamxf, lamyf, cutoff, norm);
-    FftRun<P, +1>::run(v, t, s, tw);
-#pragma unroll
-    for (int e = 0; e < E; ++e) *elem(loff, t + G * e) = v[e];
-    __syncthreads();  // exchange buffer free for the next line
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -332,12 +284,59 @@ __global__ void merge_lines_kernel(LinePeers peers, int lnloc, size_t line_begin
   s_peer[x1 >> lnloc][loff + (x1 & nloc_mask)] = make_float2(y0.x - y1.x, y0.y - y1.y);
 }
 
+// The same two steps on the PAIRED layout: a thread handles element m of BOTH lines of a pair
+// (one float4 = the two interleaved lines), so the spectrum is still read and written in full
+// 16-byte pieces; blockIdx.y counts pairs, line_begin is even.
+__global__ void split_pairs_kernel(LinePeers peers, int lnloc, size_t line_begin, int half,
+                                   float2* __restrict__ scratch, const float2* __restrict__ wbig) {
+  __shared__ float2* s_peer[CFD_MAX_PEERS];
+  if (threadIdx.x < CFD_MAX_PEERS) s_peer[threadIdx.x] = peers.p[threadIdx.x];
+  __syncthreads();
+  const size_t pi = blockIdx.y;
+  const size_t loff = (((line_begin >> 1) + pi) << lnloc) << 1;
+  const int nloc_mask = (1 << lnloc) - 1;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= half) return;
+  const int x1 = m + half;
+  const float4 a = *reinterpret_cast<const float4*>(s_peer[m >> lnloc] + loff + 2 * (m & nloc_mask));
+  const float4 b = *reinterpret_cast<const float4*>(s_peer[x1 >> lnloc] + loff + 2 * (x1 & nloc_mask));
+  const float2 w = __ldg(wbig + m);
+  float2* y = scratch + (2 * pi) * (size_t)(2 * half);  // lines 2 pi and 2 pi + 1 of this chunk
+  y[m] = make_float2(a.x + b.x, a.y + b.y);
+  y[half + m] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
+  y += 2 * half;
+  y[m] = make_float2(a.z + b.z, a.w + b.w);
+  y[half + m] = cmul(make_float2(a.z - b.z, a.w - b.w), w);
+}
+
+__global__ void merge_pairs_kernel(LinePeers peers, int lnloc, size_t line_begin, int half,
+                                   const float2* __restrict__ scratch, const float2* __restrict__ wbig) {
+  __shared__ float2* s_peer[CFD_MAX_PEERS];
+  if (threadIdx.x < CFD_MAX_PEERS) s_peer[threadIdx.x] = peers.p[threadIdx.x];
+  __syncthreads();
+  const size_t pi = blockIdx.y;
+  const size_t loff = (((line_begin >> 1) + pi) << lnloc) << 1;
+  const int nloc_mask = (1 << lnloc) - 1;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= half) return;
+  const int x1 = m + half;
+  const float2 w = __ldg(wbig + m);
+  const float2* y = scratch + (2 * pi) * (size_t)(2 * half);
+  const float2 a0 = y[m], a1 = cmulc(y[half + m], w);  // * conj(w^m)
+  y += 2 * half;
+  const float2 b0 = y[m], b1 = cmulc(y[half + m], w);
+  *reinterpret_cast<float4*>(s_peer[m >> lnloc] + loff + 2 * (m & nloc_mask)) =
+      make_float4(a0.x + a1.x, a0.y + a1.y, b0.x + b1.x, b0.y + b1.y);
+  *reinterpret_cast<float4*>(s_peer[x1 >> lnloc] + loff + 2 * (x1 & nloc_mask)) =
+      make_float4(a0.x - a1.x, a0.y - a1.y, b0.x - b1.x, b0.y - b1.y);
+}
+
 // ------------------------------------------------------------------------------------------
 // Q: gather ROWS rows of T, inverse real FFT, write q rows (coalesced).  No halo row, no
 // redundant transform; the pressure-gradient correction is applied either by correct2d_kernel or
 // lazily by the next step's explicit kernel (explicit_2d.cu, LAZY mode).
-template <int LM, int ROWS, int LEMAX>
-__global__ void __launch_bounds__(ROWS * FftPlan<LM, LEMAX, 4>::G)
+template <int LM, int ROWS, int LEMAX, bool PAIRED>
+__global__ void __launch_bounds__(ROWS * FftPlan<LM, LEMAX, 4>::G, (ROWS * FftPlan<LM, LEMAX, 4>::G <= 512) ? 2 : 0)
 irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
                   const float2* __restrict__ tw, const float2* __restrict__ rtw) {
   using P = FftPlan<LM, LEMAX, 4>;
@@ -353,20 +352,30 @@ irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
   {
     // all of a thread's gather loads are issued before the first one is consumed (ROWS * M / NT
     // = E of them): the transposed reads are the latency-critical start of this kernel
-    const float2* Tb = T + b * (size_t)M * Nx + x0;
+    const float2* Tb = T + b * (size_t)M * Nx + (PAIRED ? 2 : 1) * (size_t)x0;
     constexpr int NG = ROWS * M / NT;
     float2 tmp[NG];
 #pragma unroll
     for (int n = 0; n < NG; ++n) {
       const int idx = tid + n * NT;
-      const int r = idx % ROWS, ky = idx / ROWS;
-      tmp[n] = __ldg(Tb + (size_t)ky * Nx + r);
+      if (PAIRED) {
+        const int p = idx & 1, r = (idx >> 1) % ROWS, j = idx / (2 * ROWS);
+        tmp[n] = __ldg(Tb + ((size_t)j * Nx + r) * 2 + p);
+      } else {
+        const int r = idx % ROWS, ky = idx / ROWS;
+        tmp[n] = __ldg(Tb + (size_t)ky * Nx + r);
+      }
     }
 #pragma unroll
     for (int n = 0; n < NG; ++n) {
       const int idx = tid + n * NT;
-      const int r = idx % ROWS, ky = idx / ROWS;
-      smem[r * RS + PAD(ky)] = tmp[n];
+      if (PAIRED) {
+        const int p = idx & 1, r = (idx >> 1) % ROWS, j = idx / (2 * ROWS);
+        smem[r * RS + PAD(2 * j + p)] = tmp[n];
+      } else {
+        const int r = idx % ROWS, ky = idx / ROWS;
+        smem[r * RS + PAD(ky)] = tmp[n];
+      }
     }
   }
   __syncthreads();
@@ -447,7 +456,7 @@ __global__ void divergence2d_kernel(const float* __restrict__ u, const float* __
 
 template <int LM>
 int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, int Nx,
-                       const float2* tw, const float2* rtw) {
+                       const float2* tw, const float2* rtw, int paired) {
   constexpr int ROWS_MAX = rows_for(LM);
   using P = FftPlan<LM>;
   // ROWS must divide Nx
@@ -456,11 +465,15 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
     constexpr size_t smem = (size_t)ROWS * row_stride(P::M, ROWS) * sizeof(float2);
     if (rows_lemax(LM) == 5 && LM >= 5) {
       using P5 = FftPlan<LM, 5, 4>;
-      auto k = rfft_rows_kernel<LM, ROWS, 5>;
+      auto k = rfft_rows_kernel<LM, ROWS, 5, false>;
       if (int e = set_smem(k, smem)) return e;
       k<<<dim3(Nx / ROWS, batch), ROWS * P5::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+    } else if (paired) {
+      auto k = rfft_rows_kernel<LM, ROWS, 4, true>;
+      if (int e = set_smem(k, smem)) return e;
+      k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw);
     } else {
-      auto k = rfft_rows_kernel<LM, ROWS, 4>;
+      auto k = rfft_rows_kernel<LM, ROWS, 4, false>;
       if (int e = set_smem(k, smem)) return e;
       k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw);
     }
@@ -484,7 +497,7 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
 template <int LM, int LEMAX>
 int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
                      size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
-                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
+                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired) {
   using P = FftPlan<LM, LEMAX, 4>;
   constexpr int LINES = (P::G >= 256) ? 1 : (256 / P::G > 16 ? 16 : 256 / P::G);
   // two exchange buffers (one barrier per pass) whenever both fit beside a second CTA's
@@ -499,13 +512,22 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
   };
   int e;
   if constexpr (LM == 14) {  // split mode exists for the half-lines of 32768-point lines only
+    if (paired && !split) return set_error_msg("internal: the paired layout is not built for 16384-point lines");
     if (split)
-      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, true, DB>) : go(xlines_kernel<LM, LINES, false, LEMAX, true, DB>);
+      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, true, DB, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, true, DB, false>);
     else
-      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB>);
+      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, false>);
   } else {
     if (split) return set_error_msg("internal: split x lines need 16384-point transforms");
-    e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB>);
+    if (paired) {
+      if constexpr (LM == 12 || LM == 13) {  // the only lengths the plan selects the paired layout for
+        e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, true>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, true>);
+      } else {
+        return set_error_msg("internal: the paired layout is built for 4096/8192-point x lines only");
+      }
+    } else {
+      e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, false>);
+    }
   }
   if (e) return e;
   count_launch();
@@ -514,66 +536,19 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
 }
 
 template <int LM>
-int launch_xlines_pipe(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
-                       size_t nlines, int My, int split, const float2* tw, const double* lamx,
-                       const double* lamy, const float* lamxf, const float* lamyf, int fastd,
-                       double cutoff, float norm) {
-  using P = FftPlan<LM>;
-  constexpr size_t smem = ((size_t)((row_stride(P::M, 16) + 1) & ~1) + P::M) * sizeof(float2);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  const unsigned grid = (unsigned)(nlines < (size_t)sms ? nlines : (size_t)sms);
-  if (fastd) {
-    auto k = xlines_pipe_kernel<LM, true>;
-    if (int e = set_smem(k, smem)) return e;
-    k<<<grid, P::G, smem, st>>>(peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
-                                lamyf, cutoff, norm);
-  } else {
-    auto k = xlines_pipe_kernel<LM, false>;
-    if (int e = set_smem(k, smem)) return e;
-    k<<<grid, P::G, smem, st>>>(peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
-                                lamyf, cutoff, norm);
-  }
-  count_launch();
-  CFD_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// The pipelined kernel measured no faster than the one-shot kernel on one GPU (316 vs 295 us at
-// 8192^2: the line transforms are barrier/issue bound, not load-latency bound), so it is opt-in:
-// CFD_XLINES_PIPE=1 (single GPU), CFD_XLINES_PIPE=2 (also when lines live in peer memory).
-inline int xlines_pipe_mode() {
-  static const int v = [] {
-    const char* e = getenv("CFD_XLINES_PIPE");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
-}
-
-template <int LM>
 int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
                     size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
-                    const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm) {
-  if constexpr (LM == 12 || LM == 13) {
-    if (xlines_pipe_mode() != 0 && xlines_lemax(LM) == 4)
-      return launch_xlines_pipe<LM>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy,
-                                    lamxf, lamyf, fastd, cutoff, norm);
-  }
+                    const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired) {
   if (xlines_lemax(LM) == 5)
     return launch_xlines_le<LM, 5>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
-                                   lamyf, fastd, cutoff, norm);
+                                   lamyf, fastd, cutoff, norm, paired);
   return launch_xlines_le<LM, 4>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
-                                 lamyf, fastd, cutoff, norm);
+                                 lamyf, fastd, cutoff, norm, paired);
 }
 
 template <int LM>
 int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, int Nx,
-                        const float2* tw, const float2* rtw) {
+                        const float2* tw, const float2* rtw, int paired) {
   constexpr int ROWS_MAX = rows_for(LM);
   using P = FftPlan<LM>;
   auto go = [&](auto rows_c) -> int {
@@ -581,11 +556,15 @@ int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, i
     constexpr size_t smem = (size_t)ROWS * row_stride(P::M, ROWS) * sizeof(float2);
     if (rows_lemax(LM) == 5 && LM >= 5) {
       using P5 = FftPlan<LM, 5, 4>;
-      auto k = irfft_rows_kernel<LM, ROWS, 5>;
+      auto k = irfft_rows_kernel<LM, ROWS, 5, false>;
       if (int e = set_smem(k, smem)) return e;
       k<<<dim3(Nx / ROWS, batch), ROWS * P5::G, smem, st>>>(T, q, Nx, tw, rtw);
+    } else if (paired) {
+      auto k = irfft_rows_kernel<LM, ROWS, 4, true>;
+      if (int e = set_smem(k, smem)) return e;
+      k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(T, q, Nx, tw, rtw);
     } else {
-      auto k = irfft_rows_kernel<LM, ROWS, 4>;
+      auto k = irfft_rows_kernel<LM, ROWS, 4, false>;
       if (int e = set_smem(k, smem)) return e;
       k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(T, q, Nx, tw, rtw);
     }
@@ -610,8 +589,8 @@ int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, i
 
 // lm_row = log2(Ny / 2)
 int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, int batch, int Nx,
-                     const float2* tw, const float2* rtw) {
-  CFD_DISPATCH_LM(lm_row, 4, 14, return launch_rfft_rows_t<LM_>(st, rhs, T, batch, Nx, tw, rtw));
+                     const float2* tw, const float2* rtw, int paired) {
+  CFD_DISPATCH_LM(lm_row, 4, 14, return launch_rfft_rows_t<LM_>(st, rhs, T, batch, Nx, tw, rtw, paired));
   return 0;
 }
 // lm_x = log2(Nx)
@@ -623,7 +602,7 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig, const SideStreams* side) {
+                        const float2* wbig, const SideStreams* side, int paired) {
   if (lm_x == 15) {
     if (!scratch || !wbig) return set_error_msg("internal: 32768-point lines need the split scratch");
     const int half = 1 << 14;
@@ -640,15 +619,24 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
       float2* sc = scratch + (size_t)c * chunk * (size_t)(2 * half);
       const size_t lb = line_begin + (size_t)c * chunk;
       dim3 grid(half / 256, (unsigned)chunk);
-      split_lines_kernel<<<grid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+      dim3 pgrid(half / 256, (unsigned)(chunk / 2));
+      if (paired) {
+        if ((lb | chunk) & 1) return set_error_msg("internal: paired lines need even line ranges");
+        split_pairs_kernel<<<pgrid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+      } else {
+        split_lines_kernel<<<grid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+      }
       count_launch();
       CFD_CUDA_OK(cudaGetLastError());
       LinePeers local;
       for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = sc;
       if (int e = launch_xlines_t<14>(s, local, 14, lb, 2 * chunk, My, 1, tw, lamx, lamy, lamxf, lamyf,
-                                      fastd, cutoff, norm))
+                                      fastd, cutoff, norm, 0))
         return e;
-      merge_lines_kernel<<<grid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+      if (paired)
+        merge_pairs_kernel<<<pgrid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+      else
+        merge_lines_kernel<<<grid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
       count_launch();
       CFD_CUDA_OK(cudaGetLastError());
     }
@@ -662,17 +650,17 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
   }
   CFD_DISPATCH_LM(lm_x, 4, 14,
                   return launch_xlines_t<LM_>(st, peers, lnloc, line_begin, nlines, My, 0, tw, lamx, lamy,
-                                              lamxf, lamyf, fastd, cutoff, norm));
+                                              lamxf, lamyf, fastd, cutoff, norm, paired));
   return 0;
 }
 int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
                   int fastd, double cutoff, float norm, float2* scratch, const float2* wbig,
-                  const SideStreams* side) {
+                  const SideStreams* side, int paired) {
   LinePeers peers;
   for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
   return launch_xlines_peers(st, lm_x, peers, lm_x, 0, (size_t)batch * My, My, tw, lamx, lamy, lamxf,
-                             lamyf, fastd, cutoff, norm, scratch, wbig, side);
+                             lamyf, fastd, cutoff, norm, scratch, wbig, side, paired);
 }
 int launch_divergence_2d(cudaStream_t st, const float* u, const float* v, float* rhs, int batch,
                          int Nx, int Ny, float inv_hx, float inv_hy) {
@@ -688,8 +676,8 @@ int launch_divergence_2d(cudaStream_t st, const float* u, const float* v, float*
 
 namespace cfd {
 int launch_irfft_rows(cudaStream_t st, int lm_row, const float2* T, float* q, int batch, int Nx,
-                      const float2* tw, const float2* rtw) {
-  CFD_DISPATCH_LM(lm_row, 4, 14, return launch_irfft_rows_t<LM_>(st, T, q, batch, Nx, tw, rtw));
+                      const float2* tw, const float2* rtw, int paired) {
+  CFD_DISPATCH_LM(lm_row, 4, 14, return launch_irfft_rows_t<LM_>(st, T, q, batch, Nx, tw, rtw, paired));
   return 0;
 }
 int launch_correct_2d(cudaStream_t st, const float* us, const float* vs, const float* q,
