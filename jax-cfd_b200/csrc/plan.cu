@@ -497,6 +497,7 @@ void cfd_plan_destroy(cfd_plan* p) {
     cudaEventDestroy(p->side.done[i]);
   }
   if (p->side.start) cudaEventDestroy(p->side.start);
+  if (p->pair_graph) cudaGraphExecDestroy(p->pair_graph);
   cudaFree(p->xstage);
   if (p->ev_ready) cudaEventDestroy(p->ev_ready);
   for (int r = 0; r < CFD_MAX_PEERS; ++r) {
@@ -559,6 +560,61 @@ int cfd_step(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* co
 
 // nsteps chained steps: the projected state is materialised only at the end; in between, step
 // n+1 reads (u*, v*, q) of step n and projects while loading (LAZY explicit kernel).
+// Small grids are launch-bound (256^2: four kernels of 4-8 us each per step).  Two chained lazy
+// steps bring the ping-pong buffers back to where they started, so that pair is captured once per
+// plan (and set of constants) as a CUDA graph and replayed.  CFD_GRAPH=0 disables it.
+static bool use_pair_graph(const cfd_plan* p) {
+  static const int enabled = [] {
+    const char* e = getenv("CFD_GRAPH");
+    return e ? atoi(e) : 1;
+  }();
+  return enabled && !p->profiling && p->ndim == 2 && p->lm_x != 15 &&
+         (size_t)p->batch * p->cells <= ((size_t)1 << 21);
+}
+
+static int lazy_step(cfd_plan* p, cudaStream_t st, const StepConsts& c, float* const* us_cur,
+                     const float* q_cur, float* const* us_nxt, float* q_nxt) {
+  const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
+  if (int e = launch_explicit_2d(st, us_cur[0], us_cur[1], q_cur, us_nxt[0], us_nxt[1], p->rhs, p->batch,
+                                 Nx, Ny, c, 0))
+    return e;
+  prof_mark(p, st, "explicit_2d_lazy");
+  return solve_2d(p, st, q_nxt);
+}
+
+// Captures (us, qbuf) -> (us2, qbuf2) -> (us, qbuf) on `st`; on any failure the plan simply keeps
+// launching eagerly.
+static bool capture_pair_graph(cfd_plan* p, cudaStream_t st, const StepConsts& c) {
+  if (p->pair_graph) {
+    cudaGraphExecDestroy(p->pair_graph);
+    p->pair_graph = nullptr;
+  }
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const uint64_t before = cfd_launch_count();
+  int e = lazy_step(p, st, c, p->us, p->qbuf, p->us2, p->qbuf2);
+  if (!e) e = lazy_step(p, st, c, p->us2, p->qbuf2, p->us, p->qbuf);
+  count_launch(-(int)(cfd_launch_count() - before));  // captured, not launched
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &g);
+  if (e || ce != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    return false;
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&p->pair_graph, g, 0);
+  cudaGraphDestroy(g);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    p->pair_graph = nullptr;
+    return false;
+  }
+  p->pair_consts = c;
+  return true;
+}
+
 static int repeated_lazy(cfd_plan* p, cudaStream_t st, const float* const* v_in, float* const* v_out,
                          int nsteps, const cfd_params* params) {
   StepConsts c;
@@ -569,6 +625,37 @@ static int repeated_lazy(cfd_plan* p, cudaStream_t st, const float* const* v_in,
   float* us_nxt[2] = {p->us2[0], p->us2[1]};
   float* q_cur = p->qbuf;
   float* q_nxt = p->qbuf2;
+  if (use_pair_graph(p) && nsteps >= 6) {
+    // step 0 and one eager lazy pair first (every kernel variant has then run once outside a
+    // capture), then pairs by graph, then at most one eager step
+    if (int e = launch_explicit_2d(st, v_in[0], v_in[1], nullptr, p->us[0], p->us[1], p->rhs, p->batch, Nx,
+                                   Ny, c, 0))
+      return e;
+    if (int e = solve_2d(p, st, p->qbuf)) return e;
+    int left = nsteps - 1;
+    const bool have = p->pair_graph && memcmp(&p->pair_consts, &c, sizeof c) == 0;
+    if (!have) {
+      if (int e = lazy_step(p, st, c, p->us, p->qbuf, p->us2, p->qbuf2)) return e;
+      if (int e = lazy_step(p, st, c, p->us2, p->qbuf2, p->us, p->qbuf)) return e;
+      left -= 2;
+      capture_pair_graph(p, st, c);
+    }
+    if (p->pair_graph) {
+      for (; left >= 2; left -= 2) {
+        CFD_CUDA_OK(cudaGraphLaunch(p->pair_graph, st));
+        count_launch(8);
+      }
+    }
+    bool in_pong = false;
+    for (; left > 0; --left) {
+      if (int e = in_pong ? lazy_step(p, st, c, p->us2, p->qbuf2, p->us, p->qbuf)
+                          : lazy_step(p, st, c, p->us, p->qbuf, p->us2, p->qbuf2))
+        return e;
+      in_pong = !in_pong;
+    }
+    return in_pong ? correct_2d(p, st, p->us2[0], p->us2[1], p->qbuf2, v_out[0], v_out[1])
+                   : correct_2d(p, st, p->us[0], p->us[1], p->qbuf, v_out[0], v_out[1]);
+  }
   for (int n = 0; n < nsteps; ++n) {
     prof_mark(p, st, "begin");
     if (n == 0) {

@@ -36,6 +36,10 @@ struct cfd_plan {
   float* qbuf2 = nullptr;  // pong
   float2* T = nullptr;
   int t_paired = 0;  // 2-D spectrum layout: 1 = pairs of ky lines interleaved (poisson_2d.cu)
+  // small grids: two chained lazy steps (us -> us2 -> us) captured once as a CUDA graph and
+  // replayed, so that the 8 launches per pair cost one graph launch (plan.cu, repeated_lazy)
+  cudaGraphExec_t pair_graph = nullptr;
+  cfd::StepConsts pair_consts;  // the constants the graph was captured with
   size_t workspace_bytes = 0;
   // host-call staging
   float* dev_a[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};
