@@ -159,6 +159,25 @@ def run_reference(args, wl, name):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  # torchrun exports OMP_NUM_THREADS=1 to its workers, and both the OpenMP stencils and scipy's
+  # pocketfft pool honour it from process start: re-run this arm in a child with a clean
+  # environment so that the CPU reference really uses every host core.
+  omp = os.environ.get('OMP_NUM_THREADS')
+  if omp and omp.isdigit() and int(omp) < (os.cpu_count() or 1) and not os.environ.get('CFD_REF_CHILD'):
+    env = {k: v for k, v in os.environ.items()
+           if k not in ('OMP_NUM_THREADS', 'RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT',
+                        'GROUP_RANK', 'ROLE_RANK', 'LOCAL_WORLD_SIZE', 'ROLE_WORLD_SIZE')
+           and not k.startswith('TORCHELASTIC')}
+    env['CFD_REF_CHILD'] = '1'
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--gpus', str(args.gpus),
+           '--steps', str(args.steps), '--warmup', str(args.warmup), '--workload', name]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    sys.stdout.write(out.stdout)
+    sys.stdout.flush()
+    if out.returncode != 0:
+      sys.stderr.write(out.stderr)
+      sys.exit(out.returncode)
+    return
   rows = min(wl['shape'][0], 2048)
   cb, ms = cpu_reference(wl, args.steps, args.warmup, sample_rows=rows)
   line = {

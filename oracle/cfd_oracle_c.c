@@ -17,6 +17,19 @@
  */
 #include <math.h>
 #include <stddef.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Thread count of the stencil loops.  Launchers such as torchrun export OMP_NUM_THREADS=1 to
+ * their workers; the CPU baseline asks for all cores explicitly (cpu_baseline.CpuStep). */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 static inline float safe_div(float x, float y) { return x / (y != 0.0f ? y : 1.0f); }
 static inline float van_leer(float r) { return r > 0.0f ? safe_div(2.0f * r, 1.0f + r) : 0.0f; }

@@ -31,6 +31,8 @@ def load():
   lib.oracle_correct_2d.argtypes = [_p, _p, _p, _p, _p, _i, _i, _f, _f]
   for f in (lib.oracle_explicit_2d, lib.oracle_divergence_2d, lib.oracle_correct_2d):
     f.restype = None
+  lib.oracle_set_threads.argtypes = [_i]
+  lib.oracle_set_threads.restype = None
   return lib
 
 
@@ -44,6 +46,8 @@ class CpuStep:
         None if f is None else np.ascontiguousarray(f, np.float32) for f in const_force)
     self.linear = linear
     self.workers = workers or os.cpu_count()
+    # not OMP_NUM_THREADS: torchrun sets it to 1 for its workers
+    self.lib.oracle_set_threads(int(self.workers))
     self.diag = cfd_oracle.pinv_diagonals(shape, h, np.float32)
     nx, ny = shape
     self.us = np.empty(shape, np.float32)
