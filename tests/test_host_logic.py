@@ -1,5 +1,8 @@
 """Host-side mirror of the reference interface: grid / offset / boundary / forcing / stepper logic.
 CPU only; mirrors the reference's own KATs."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -140,3 +143,26 @@ def test_repeated_and_trajectory_semantics():
   np.testing.assert_array_equal(traj, [1, 2, 3, 4])
   final, traj = cfd.funcutils.trajectory(lambda x: x + 1, 4, start_with_input=True)(np.float32(0))
   np.testing.assert_array_equal(traj, [0, 1, 2, 3])
+
+
+def test_reference_arm_prints_contract_line_under_a_torchrun_like_environment():
+  """bench.py --impl reference: rank 0 prints ONE JSON line with the contract keys even when the
+  launcher capped OMP_NUM_THREADS (it re-runs itself with a clean environment); other ranks
+  print nothing and exit 0."""
+  import json
+  import subprocess
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  cmd = [sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+         '--workload', 'K256', '--steps', '1', '--warmup', '1']
+  env = dict(os.environ, OMP_NUM_THREADS='1', RANK='0', WORLD_SIZE='2', LOCAL_RANK='0')
+  out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0, out.stderr
+  lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['unit'] == 'Gcell*step/s'
+  assert d['value'] > 0 and d['cpu_baseline']['cores'] == os.cpu_count()
+  assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
+  env['RANK'] = '1'
+  out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith('{')]
