@@ -1,13 +1,16 @@
 // Sweep "E" (3-D): explicit terms + Euler update + divergence, and the Smagorinsky eddy viscosity.
 //
-// First 3-D implementation: one thread per cell (z fastest, coalesced), neighbours through L1/L2
-// (no register marching yet -- the 2-D kernel's design is the model for the next round).  Same
-// arithmetic as explicit_2d.cu per face (common.cuh: face_flux).
+// Two implementations with the same arithmetic per face (common.cuh: face_flux):
+//   * explicit3d_march_kernel (+ smag_nut_march_kernel / smag_acc_march_kernel): 2.5-D blocking, a
+//     CTA owns an 8 x 64 tile in (y, z) and marches along x with a ring of shared-memory planes --
+//     used whenever the tile divides the grid;
+//   * explicit3d_kernel (+ smag_nut3d_kernel / the strain-field kernels): one thread per cell,
+//     neighbours through L1/L2 -- the fallback for other shapes and the first implementation.
 //
 //   advection      advection.py:387-395 -> 81-116 -> 34-78, interpolation.py:36-303
 //   diffusion      diffusion.py:35-37, finite_differences.py:127-133
 //   forcing        forcings.py:35-129 (separable / field / linear), equations.py:108-109
-//   Smagorinsky    subgrid_models.py:40-98 (viscosity at cell centres: smag_nut3d_kernel),
+//   Smagorinsky    subgrid_models.py:40-98 (viscosity at cell centres),
 //                  subgrid_models.py:101-134 (evm_model: -div(tau), tau_ij = -2 nu_ij s_ij)
 //   update         time_stepping.py:101;   divergence   finite_differences.py:136-143
 #include <stdlib.h>
