@@ -2,7 +2,9 @@
 #pragma once
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "fft_smem.cuh"
@@ -16,11 +18,23 @@ __host__ __device__ constexpr int row_stride(int M, int rows) {
   return ((padded_len(M) + 15) & ~15) + (rows >= 16 ? 1 : 16 / rows);
 }
 
+// Opt-in to > 48 KB of dynamic shared memory, once per kernel (and per larger size): the attribute
+// call is kept off the launch path -- every later launch, including the ones recorded into a CUDA
+// graph (plan.cu), is then a plain launch.
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem)", e, __FILE__, __LINE__);
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> done[64];  // per device, keyed by kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[dev & 63][reinterpret_cast<const void*>(kernel)];
+    if (bytes > have) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem)", e, __FILE__, __LINE__);
+      have = bytes;
+    }
   }
   return 0;
 }
