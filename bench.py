@@ -124,16 +124,55 @@ def peaks():
   return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def cpu_reference(wl, steps, warmup, sample_rows=None):
-  """The oracle's OpenMP/pocketfft implementation of the same step on the host cores."""
+CPU_SAMPLE_CELLS = 1 << 26  # the CPU legs run the whole grid up to 8192^2 cells, a slab of rows beyond
+
+
+# weak scaling of the slab-decomposed path: 8192^2 cells per GPU
+# (measured: 4 GPUs 32768x8192 1.82 ms/step vs 16384x16384 1.90 ms/step)
+SLAB_SHAPES = {1: (8192, 8192), 2: (16384, 8192), 4: (32768, 8192), 8: (32768, 16384)}
+# the north-star multi-GPU configuration (BASELINE config #4): 32768^2 over the GPUs of the box
+SLAB_SHAPES_32K = {1: (32768, 32768), 2: (32768, 32768), 4: (32768, 32768), 8: (32768, 32768)}
+
+
+def is_slab(name, world):
+  return (world > 1 and name == 'K8192') or name == 'K32768'
+
+
+def workload_grid(wl, name, world):
+  """(shape, domain) of the grid the arm runs at `world` GPUs -- shared by the GPU arm and the
+  reference arm so that both describe the same configuration."""
+  if is_slab(name, world):
+    shape = (SLAB_SHAPES_32K if name == 'K32768' else SLAB_SHAPES)[world]
+    if os.environ.get('CFD_SLAB_SHAPE'):  # tuning aid, e.g. CFD_SLAB_SHAPE=32768x8192
+      shape = tuple(int(x) for x in os.environ['CFD_SLAB_SHAPE'].split('x'))
+    return shape, tuple((0.0, TWO_PI * n / 8192.0) for n in shape)  # cell size of the 8192^2 case
+  return tuple(wl['shape']), ((0.0, TWO_PI),) * len(wl['shape'])
+
+
+def gpu_config(wl, name, world):
+  """The `config` object of the JSON line (identical keys in both arms)."""
+  shape, _ = workload_grid(wl, name, world)
+  batch = wl['batch'] // world if (wl['batch'] > 1 and world > 1) else wl['batch']
+  slab = is_slab(name, world)
+  cells_per_gpu = int(np.prod(shape)) // world if slab else int(np.prod(shape)) * batch
+  desc = wl['desc'] + (f' -- weak-scaled to {shape[0]}x{shape[1]}' if slab and name == 'K8192' else '')
+  return {'workload': f'{name}-slab' if slab and name == 'K8192' else name, 'description': desc,
+          'grid': list(shape), 'batch': batch, 'cells_per_gpu': cells_per_gpu}
+
+
+def cpu_reference(wl, steps, warmup, grid=None):
+  """The oracle's OpenMP/pocketfft implementation of the same step on the host cores: the FULL
+  grid of the workload when it has at most CPU_SAMPLE_CELLS cells (K8192: all of 8192^2), else a
+  slab of its rows with the same row length and cell size."""
   sys.path.insert(0, os.path.join(ROOT, 'oracle'))
   import cfd_oracle
   import cpu_baseline
-  nx, ny = wl['shape']
-  if sample_rows is not None and sample_rows < nx:
-    nx = sample_rows
+  full, fdom = grid if grid is not None else (tuple(wl['shape']), ((0.0, TWO_PI),) * 2)
+  nx, ny = full
+  while nx * ny > CPU_SAMPLE_CELLS and nx > 16:
+    nx //= 2
   shape = (nx, ny)
-  dom = ((0.0, TWO_PI * nx / wl['shape'][0]), (0.0, TWO_PI))
+  dom = ((0.0, fdom[0][1] * nx / full[0]), fdom[1])
   h = cfd_oracle.grid_step(shape, dom)
   dt = 0.5 * min(h) / wl['vmax']
   u, v = synth_ic(shape, 1, 0, wl['vmax'], wl['kpeak'])
@@ -154,10 +193,12 @@ def cpu_reference(wl, steps, warmup, sample_rows=None):
   dt_s = time.perf_counter() - t0
   assert np.isfinite(u).all()
   value = nx * ny * steps / dt_s / 1e9
-  return dict(value=value, unit='Gcell*step/s', cores=cores, kind='port',
-              sample=f'{steps} steps of a {nx}x{ny} slab of the workload (same physics, OpenMP C '
-                     f'stencils + scipy.fft pocketfft on {cores} threads; JAX is not installed so '
-                     'the reference jitted CPU path cannot run)'), dt_s / steps * 1e3
+  what = (f'the full {nx}x{ny} grid' if shape == full else
+          f'a {nx}x{ny} slab of rows of the {full[0]}x{full[1]} grid (same row length and cell size)')
+  return dict(value=value, unit='Gcell*step/s', cores=cores, kind='port', full_grid=(shape == full),
+              sample=f'{steps} steps (+{warmup} warm-up) of {what}, same physics; OpenMP C stencils + '
+                     f'scipy.fft pocketfft on {cores} threads (JAX is not installed, so the '
+                     'reference jitted CPU path cannot run)'), dt_s / steps * 1e3
 
 
 def run_reference(args, wl, name):
@@ -183,25 +224,21 @@ def run_reference(args, wl, name):
       sys.stderr.write(out.stderr)
       sys.exit(out.returncode)
     return
-  rows = min(wl['shape'][0], 2048)
-  cb, ms = cpu_reference(wl, args.steps, args.warmup, sample_rows=rows)
+  if len(wl['shape']) != 2:
+    print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU port of the oracle is 2-D only'}), flush=True)
+    return
+  config = gpu_config(wl, name, args.gpus)
+  cb, ms = cpu_reference(wl, args.steps, args.warmup, grid=workload_grid(wl, name, args.gpus))
   line = {
       'impl': 'reference', 'metric': 'cell-updates/sec', 'value': cb['value'], 'unit': 'Gcell*step/s',
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-      'data': 'synthetic', 'config': {'workload': name, 'description': wl['desc']},
+      'data': 'synthetic', 'config': config,
       'cpu_baseline': cb,
       'e2e': {'value': cb['value'], 'unit': 'Gcell*step/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
   }
   print(json.dumps(line), flush=True)
-
-
-# weak scaling of the slab-decomposed path: 8192^2 cells per GPU
-# (measured: 4 GPUs 32768x8192 1.82 ms/step vs 16384x16384 1.90 ms/step)
-SLAB_SHAPES = {1: (8192, 8192), 2: (16384, 8192), 4: (32768, 8192), 8: (32768, 16384)}
-# the north-star multi-GPU configuration (BASELINE config #4): 32768^2 over the GPUs of the box
-SLAB_SHAPES_32K = {1: (32768, 32768), 2: (32768, 32768), 4: (32768, 32768), 8: (32768, 32768)}
 
 
 def analytic_ic(shape, rows, vmax):
@@ -222,9 +259,124 @@ def analytic_ic(shape, rows, vmax):
   return (u * scale).astype(np.float32), (v * scale).astype(np.float32)
 
 
+def slab_parity_check(cfd, _lib, dist, rank, world, local_rank):
+  """Before timing: 4 steps of a 2048x1024 Kolmogorov problem through SlabStepper on all ranks and
+  through the single-GPU path on rank 0 must agree BIT FOR BIT (same kernels, same arithmetic; the
+  single-GPU path itself is checked against the oracle by tests/).  Returns the `parity` object."""
+  shape, nsteps = (2048, 1024), 4
+  dom = ((0.0, TWO_PI), (0.0, TWO_PI))
+  grid = cfd.grids.Grid(shape, domain=dom)
+  dt = cfd.equations.stable_time_step(7.0, 0.5, 1e-3, grid)
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  st = cfd.distributed.SlabStepper(grid, dt, 1.0, 1e-3, forcing, rank=rank, world=world, device=local_rank)
+  u0, v0 = analytic_ic(shape, (0, shape[0]), 7.0)
+  rs = np.random.RandomState(0)
+  u0 = u0 + 0.1 * rs.standard_normal(shape).astype(np.float32)
+  v0 = v0 + 0.1 * rs.standard_normal(shape).astype(np.float32)
+  r0, r1 = st.rows
+  st.load([u0[r0:r1], v0[r0:r1]])
+  st.advance(nsteps // 2)
+  st.advance(nsteps - nsteps // 2)
+  outs, q = st.store(want_q=True)
+  loc = [o.numpy() for o in outs] + [q.numpy()]
+  gathered = [None] * world
+  dist.all_gather_object(gathered, loc)
+  st.close()
+  res = None
+  if rank == 0:
+    full = [np.concatenate([g[i] for g in gathered], axis=0) for i in range(3)]
+    bc = cfd.boundaries.periodic_boundary_conditions(2)
+    step = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, dt, grid, forcing=forcing)
+    v = tuple(cfd.grids.GridVariable(cfd.grids.GridArray(_lib.DeviceArray.from_numpy(a), o, grid), bc)
+              for a, o in zip((u0, v0), grid.cell_faces))
+    ref, rq = step.advance(v, nsteps, return_q=True)
+    ref = [np.asarray(x.data) for x in ref] + [np.asarray(rq)]
+    bitwise = all(np.array_equal(a, b) for a, b in zip(full, ref))
+    err = max(float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
+              for a, b in zip(full, ref))
+    res = {'bitwise': bool(bitwise), 'max_rel_l2': err, 'grid': list(shape), 'steps': nsteps,
+           'against': 'single-GPU path on rank 0 (itself checked against the oracle in tests/)'}
+  flag = [res]
+  dist.broadcast_object_list(flag, src=0)
+  if not flag[0]['bitwise']:
+    raise SystemExit(f'slab-decomposed step differs from the single-GPU step: {flag[0]}')
+  return flag[0]
+
+
+def time_slab(cfd, _lib, dist, torch, wl, shape, dom, steps, warmup, rank, world, local_rank, full=True):
+  """Times `steps` chained steps of the slab-decomposed grid (CUDA events on the launching stream,
+  barrier + device sync both sides, max over ranks)."""
+  lib = _lib.lib()
+  grid = cfd.grids.Grid(shape, domain=dom)
+  dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  st = cfd.distributed.SlabStepper(grid, dt, 1.0, wl['nu'], forcing, rank=rank, world=world,
+                                   device=local_rank)
+  u0, v0 = analytic_ic(shape, st.rows, wl['vmax'])
+  st.load([u0, v0])
+  del u0, v0
+  out = {'cells_local': int(np.prod(st.local_shape)), 'local_shape': st.local_shape}
+
+  def barrier():
+    st.sync()
+    _lib.check(lib.cfd_device_sync())
+    dist.barrier()
+
+  st.advance(warmup)
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0 and full:
+    sampler.start()
+    time.sleep(0.25)
+  e0, e1 = _lib.Event(), _lib.Event()
+  launches0 = lib.cfd_launch_count()
+  barrier()
+  e0.record(st.stream.handle)
+  st.advance(steps)
+  e1.record(st.stream.handle)
+  barrier()
+  ms_total = e0.elapsed_ms(e1)
+  out['launches'] = lib.cfd_launch_count() - launches0
+  out['clocks'] = sampler.stop() if rank == 0 and full else None
+  t = torch.tensor([ms_total], device='cuda')
+  dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  out['ms_total'] = float(t.item())
+  out['kern'] = st.profile(2)
+  outs = st.store()
+  loc = outs[0].numpy()
+  if full:
+    # e2e at N GPUs: every step copies the rank's slab host->device, steps once, copies it back
+    pin_in = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
+    pin_out = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
+    pin_in[0].array[...] = loc
+    pin_in[1].array[...] = outs[1].numpy()
+    e2e_steps = 3
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+      st.load([p.array for p in pin_in])
+      st.advance(1)
+      st.store(host_out=[p.array for p in pin_out])
+      pin_in, pin_out = pin_out, pin_in
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device='cuda')
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    out['e2e_s'], out['e2e_steps'] = float(te.item()), e2e_steps
+  finite = bool(np.isfinite(loc).all())
+  out['finite'], out['umax'] = finite, float(np.abs(loc).max())
+  t2 = torch.tensor([0.0 if finite else 1.0], device='cuda')
+  dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+  assert float(t2.item()) == 0.0, 'non-finite state after the timed steps'
+  dist.barrier()
+  st.close()
+  return out
+
+
 def run_gpu_slab(args, wl, name):
   """N > 1: one rank per GPU, slab decomposition along axis 0 (jax_cfd_b200.distributed)."""
-  import ctypes
   import torch
   import torch.distributed as dist
   import jax_cfd_b200 as cfd
@@ -240,105 +392,61 @@ def run_gpu_slab(args, wl, name):
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
   lib = _lib.lib()
   _lib.check(lib.cfd_set_device(local_rank))
-  shape = (SLAB_SHAPES_32K if name == 'K32768' else SLAB_SHAPES)[world]
-  if os.environ.get('CFD_SLAB_SHAPE'):  # tuning aid, e.g. CFD_SLAB_SHAPE=32768x8192
-    shape = tuple(int(x) for x in os.environ['CFD_SLAB_SHAPE'].split('x'))
-  grid = cfd.grids.Grid(shape, domain=((0.0, TWO_PI * shape[0] / 8192.0), (0.0, TWO_PI * shape[1] / 8192.0)))
-  dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
-  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
-                                      cfd.forcings.linear_forcing(grid, -0.1))
-  st = cfd.distributed.SlabStepper(grid, dt, 1.0, wl['nu'], forcing, rank=rank, world=world,
-                                   device=local_rank)
-  u0, v0 = analytic_ic(shape, st.rows, wl['vmax'])
-  st.load([u0, v0])
-  cells_local = int(np.prod(st.local_shape))
-
-  def barrier():
-    st.sync()
-    _lib.check(lib.cfd_device_sync())
-    dist.barrier()
-
-  st.advance(args.warmup)
-  barrier()
-  sampler = ClockSampler(local_rank)
-  if rank == 0:
-    sampler.start()
-    time.sleep(0.25)
-  e0, e1 = _lib.Event(), _lib.Event()
-  launches0 = lib.cfd_launch_count()
-  barrier()
-  e0.record(st.stream.handle)
-  st.advance(args.steps)
-  e1.record(st.stream.handle)
-  barrier()
-  ms_total = e0.elapsed_ms(e1)
-  launches = lib.cfd_launch_count() - launches0
-  clocks = sampler.stop() if rank == 0 else None
-  t = torch.tensor([ms_total], device='cuda')
-  dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms_total = float(t.item())
-  kern = st.profile(2)
-  outs = st.store()
-  loc = outs[0].numpy()
-  # e2e at N GPUs: every step copies the rank's slab host->device, steps once, copies it back
-  pin_in = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
-  pin_out = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
-  pin_in[0].array[...] = outs[0].numpy()
-  pin_in[1].array[...] = outs[1].numpy()
-  e2e_steps = 3
-  barrier()
-  t0 = time.perf_counter()
-  for _ in range(e2e_steps):
-    st.load([p.array for p in pin_in])
-    st.advance(1)
-    st.store(host_out=[p.array for p in pin_out])
-    pin_in, pin_out = pin_out, pin_in
-  barrier()
-  e2e_s = time.perf_counter() - t0
-  te = torch.tensor([e2e_s], device='cuda')
-  dist.all_reduce(te, op=dist.ReduceOp.MAX)
-  e2e_s = float(te.item())
-  finite = bool(np.isfinite(loc).all())
-  umax = float(np.abs(loc).max())
-  t2 = torch.tensor([0.0 if finite else 1.0], device='cuda')
-  dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-  assert float(t2.item()) == 0.0, 'non-finite state after the timed steps'
+  parity = slab_parity_check(cfd, _lib, dist, rank, world, local_rank) if world > 1 else None
+  shape, dom = workload_grid(wl, name, world)
+  r = time_slab(cfd, _lib, dist, torch, wl, shape, dom, args.steps, args.warmup, rank, world, local_rank)
+  # the north-star multi-GPU configuration itself (32768^2, BASELINE config #4) beside the
+  # weak-scaling family member, on the same box in the same run
+  k32 = None
+  if name == 'K8192' and world == 8 and not os.environ.get('CFD_SKIP_K32768'):
+    s32, d32 = workload_grid(WORKLOADS['K32768'], 'K32768', world)
+    n32 = max(3, min(args.steps, 10))
+    r32 = time_slab(cfd, _lib, dist, torch, WORKLOADS['K32768'], s32, d32, n32, 3, rank, world, local_rank,
+                    full=False)
+    ms32 = r32['ms_total'] / n32
+    k32 = {'grid': list(s32), 'steps': n32, 'warmup': 3, 'ms_per_step': ms32,
+           'value': float(np.prod(s32)) / (ms32 * 1e-3) / 1e9, 'unit': 'Gcell*step/s',
+           'cells_per_gpu': r32['cells_local'], 'kernel_ms_rank0': r32['kern'],
+           'roofline_step_frac': STEP_BYTES_PER_CELL * r32['cells_local'] / (ms32 * 1e-3) / 1e9 / peaks()[0]}
   if rank == 0:
     peak, peak_src = peaks()
-    ms_step = ms_total / args.steps
+    cells_local = r['cells_local']
+    ms_step = r['ms_total'] / args.steps
     cells = cells_local * world
-    value = cells * args.steps / (ms_total * 1e-3) / 1e9
+    value = cells * args.steps / (r['ms_total'] * 1e-3) / 1e9
     step_gbs = STEP_BYTES_PER_CELL * cells_local / (ms_step * 1e-3) / 1e9
-    # NVLink bytes per rank per step: x-line kernel reads and writes (world-1)/world of its lines
-    nvl = (shape[1] // 2 // world) * shape[0] * 8 * (world - 1) / world
+    # NVLink bytes per rank per step and direction: (world-1)/world of the packed spectrum
+    # (4 B/cell), once to the line owners and once back
+    nvl = 2 * cells_local * 4 * (world - 1) / world
+    config = gpu_config(wl, name, world)
+    config.update({
+        'l2_policy': 'per-GPU working set (9 fields x %.0f MB) larger than L2 (126 MB)' % (cells_local * 4 / 1e6),
+        'parallelism': f'slab decomposition along axis 0 over {world} GPUs; halo rows and the FFT '
+                       'all-to-all move over NVLink through CUDA-IPC peer mappings driven by this '
+                       'library\'s own kernels; device-side flags, no NCCL on the data path'})
     line = {
         'metric': 'cell-updates/sec', 'value': value, 'unit': 'Gcell*step/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic',
-        'config': {'workload': f'{name}-slab', 'description': wl['desc'] + f' -- weak-scaled to {shape[0]}x{shape[1]}',
-                   'grid': list(shape), 'cells_per_gpu': cells_local,
-                   'l2_policy': 'per-GPU working set (9 fields x 268 MB) larger than L2 (126 MB)',
-                   'parallelism': f'slab decomposition along axis 0 over {world} GPUs; halo rows and the FFT '
-                                  'all-to-all are peer loads/stores inside the kernels (CUDA IPC over NVLink), '
-                                  'device-side flag barriers, no NCCL on the data path'},
+        'data': 'synthetic', 'config': config,
+        'value_kind': 'chained steps (SlabStepper.advance), state resident in HBM',
         'roofline': {'bound': 'hbm', 'kernel': 'whole step (per GPU)', 'achieved': step_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': step_gbs / peak, 'traffic': None, 'peak_source': peak_src,
                      'bytes_per_cell_model': STEP_BYTES_PER_CELL},
-        'kernel_ms_rank0': kern,
+        'kernel_ms_rank0': r['kern'],
         'nvlink': {'bytes_per_gpu_per_step_each_direction': nvl,
                    'lower_bound_ms_at_770GBs': nvl / 770e9 * 1e3},
+        'parity': parity, 'k32768': k32,
         'cpu_baseline': None,
-        'e2e': {'value': cells * e2e_steps / e2e_s / 1e9, 'unit': 'Gcell*step/s',
+        'e2e': {'value': cells * r['e2e_steps'] / r['e2e_s'] / 1e9, 'unit': 'Gcell*step/s',
                 'h2d_bytes_per_step': 2 * cells * 4, 'd2h_bytes_per_step': 2 * cells * 4,
-                'steps': e2e_steps, 'ms_per_step': e2e_s / e2e_steps * 1e3,
+                'steps': r['e2e_steps'], 'ms_per_step': r['e2e_s'] / r['e2e_steps'] * 1e3,
                 'api': 'SlabStepper.load(pinned numpy) / advance(1) / store(host_out=pinned numpy) on every rank'},
-        'gpu_launches': int(launches), 'clocks': clocks,
-        'diagnostics_after': {'finite': finite, 'max_abs_u_rank0': umax},
+        'gpu_launches': int(r['launches']), 'clocks': r['clocks'],
+        'diagnostics_after': {'finite': r['finite'], 'max_abs_u_rank0': r['umax']},
     }
     print(json.dumps(line), flush=True)
   dist.barrier()
-  st.close()
   dist.destroy_process_group()
 
 
@@ -348,7 +456,7 @@ def run_gpu(args, wl, name):
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-  if (world > 1 and name == 'K8192') or name == 'K32768':
+  if is_slab(name, world):
     return run_gpu_slab(args, wl, name)
   dist = None
   if world > 1:
@@ -454,25 +562,49 @@ def run_gpu(args, wl, name):
                                     ms, names, ctypes.byref(nk)))
     kern = {names[i].decode(): float(ms[i]) for i in range(nk.value)}
     chain = {k: kern[k] for k in CHAIN_KERNELS if k in kern} or dict(kern)
-    dom = max(chain, key=chain.get)
+    kgbs = {k: KERNEL_BYTES.get(k, 0.0) * cells / (t * 1e-3) / 1e9 for k, t in kern.items()}
+    dom = max(chain, key=chain.get)       # the kernel with the largest share of the step
+    worst = min(chain, key=lambda k: kgbs[k])  # ... and the one furthest from the roofline
     dom_bytes = KERNEL_BYTES.get(dom, 0.0) * cells
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath):
-      tj = json.load(open(tpath))
+    # measured DRAM traffic per launch (ncu --set full, dram__bytes_read + write) of the commit
+    # named in the file; dropped when the file is for another workload
+    traffic = traffic_commit = None
+    tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, 'profiles')) if f.endswith('_traffic.json'))
+    if tfiles:
+      tj = json.load(open(os.path.join(ROOT, 'profiles', tfiles[-1])))
       if tj.get('workload') == name:
         traffic = tj['bytes_per_launch'].get(dom)
+        traffic_commit = tj.get('commit', 'round-1 end state (9cb5c0e)')
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_measured_at': traffic_commit,
+                'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': dom_bytes, 'kernel_ms': kern[dom],
                 'share_of_step': kern[dom] / sum(chain.values())}
-    bpc = 52.0 if ndim == 3 else (16.0 if cells * 4 * 7 <= 126e6 and batch > 1 else STEP_BYTES_PER_CELL)
+    roofline_worst = {'kernel': worst, 'achieved': kgbs[worst], 'frac': kgbs[worst] / peak,
+                      'kernel_ms': kern[worst], 'share_of_step': kern[worst] / sum(chain.values())}
+    # bytes/cell model of the whole step: 52 in 3-D, 40 in 2-D when the
+    # working set exceeds L2, 16 for batched members small enough to stay on chip (256^2)
+    member_on_chip = ndim == 2 and batch > 1 and int(np.prod(shape)) * 4 * 3 <= 1 << 20
+    bpc = 52.0 if ndim == 3 else (16.0 if member_on_chip else STEP_BYTES_PER_CELL)
     step_gbs = bpc * cells / (ms_step * 1e-3) / 1e9
     roofline_step = {'bound': 'hbm', 'bytes_per_cell_model': bpc,
                      'achieved': step_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': step_gbs / peak,
-                     'kernel_ms': kern,
-                     'kernel_gbs': {k: KERNEL_BYTES.get(k, 0.0) * cells / (t * 1e-3) / 1e9 for k, t in kern.items()}}
+                     'kernel_ms': kern, 'kernel_gbs': kgbs}
+    # the same steps issued one call at a time (cfd_step: every call also materialises the
+    # projected state, +20 B/cell) -- what a lone step_fn(v) costs
+    sc_steps = max(3, min(args.steps, 10))
+    x, y = (pa, pb) if in_a else (pb, pa)
+    _lib.check(lib.cfd_step(plan.handle, stream.handle, x, y, None, ctypes.byref(params)))
+    stream.sync()
+    e0.record(stream.handle)
+    for _ in range(sc_steps):
+      x, y = y, x
+      _lib.check(lib.cfd_step(plan.handle, stream.handle, x, y, None, ctypes.byref(params)))
+    e1.record(stream.handle)
+    sc_ms = e0.elapsed_ms(e1) / sc_steps
+    single_call = {'ms_per_step': sc_ms, 'value': cells / (sc_ms * 1e-3) / 1e9, 'unit': 'Gcell*step/s',
+                   'steps': sc_steps, 'api': 'cfd_step per step (step_fn(v) on device arrays)'}
 
     # e2e: public host-array API, pinned host buffers, H2D + D2H of the whole state every step
     hin = [_lib.PinnedArray(full) for _ in range(ndim)]
@@ -497,20 +629,25 @@ def run_gpu(args, wl, name):
            'ms_per_step': e2e_s / e2e_steps * 1e3,
            'api': 'cfd_step_host (C ABI, pinned numpy in/out) == step_fn on host arrays'}
     cb = None
-    if not args.no_cpu_baseline:
-      cb, _ = cpu_reference(wl, 3, 1, sample_rows=min(shape[0], 2048)) if ndim == 2 else (None, None)
+    if not args.no_cpu_baseline and ndim == 2:
+      # free the pinned staging first: the CPU leg needs the host memory bandwidth to itself
+      del hin, hout
+      cb, _ = cpu_reference(wl, 5, 2, grid=workload_grid(wl, name, world))
     line = {
         'metric': 'cell-updates/sec', 'value': value, 'unit': 'Gcell*step/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': name, 'description': wl['desc'], 'grid': list(shape), 'batch': batch,
-                   'cells_per_gpu': cells, 'l2_policy': 'working set (7 fields x %.0f MB) %s L2 (126 MB)' % (
-                       cells * 4 / 1e6, 'larger than' if cells * 4 * 7 > 126e6 else 'fits in'),
-                   'parallelism': 'single GPU' if world == 1 else (
-                       f'ensemble sharded over {world} GPUs ({batch} members each), no collective' if batch > 1
-                       else f'{world} independent domain replicas')},
-        'roofline': roofline, 'roofline_step': roofline_step, 'cpu_baseline': cb, 'e2e': e2e,
+        'config': dict(gpu_config(wl, name, world), **{
+            'l2_policy': 'working set (7 fields x %.0f MB) %s L2 (126 MB)' % (
+                cells * 4 / 1e6, 'larger than' if cells * 4 * 7 > 126e6 else 'fits in'),
+            'parallelism': 'single GPU' if world == 1 else (
+                f'ensemble sharded over {world} GPUs ({batch} members each), no collective' if batch > 1
+                else f'{world} independent domain replicas')}),
+        'value_kind': 'chained steps (cfd_repeated == funcutils.repeated(step_fn, n)), state resident in HBM',
+        'single_call': single_call,
+        'roofline': roofline, 'roofline_worst': roofline_worst, 'roofline_step': roofline_step,
+        'cpu_baseline': cb, 'e2e': e2e,
         'gpu_launches': int(launches), 'clocks': clocks,
         'diagnostics_after': diag,
     }

@@ -17,7 +17,9 @@
  * every data pointer is a DEVICE pointer to float32, row-major, axis 0 slowest, with an optional
  * leading batch axis: (batch, N0, N1[, N2]).  Velocity component `a` lives at offset
  * grid.cell_faces[a] (grids.py:567-572); pressure at the cell centre.  All boundaries periodic.
- * Every call is enqueue-only on the given stream unless it says it synchronises.
+ * Every call is enqueue-only on the given stream unless it says it synchronises, runs on the
+ * plan's device and restores the caller's current device before returning.  A plan owns ONE
+ * workspace: calls on the same plan must be ordered on one stream (use one plan per stream).
  * Return value: 0 on success, non-zero on error (message via cfd_last_error()).  There is no
  * CPU fallback: without a CUDA device every compute entry point fails.
  */
@@ -64,6 +66,10 @@ typedef struct cfd_params {
   int32_t has_sep[CFD_MAX_DIM];
   /* CFD_FORCE_FIELD: device arrays of the grid shape (no batch axis), NULL = zero. */
   const float* field[CFD_MAX_DIM];
+  /* dt inside the Lax-Wendroff Courant number of the convection term (equations.py:127-128 binds
+   * `convect` to the equation builder's dt; the time stepper may be given another one,
+   * time_stepping.py:59-106).  0 = same as dt. */
+  double convect_dt;
 } cfd_params;
 
 typedef struct cfd_diag {
@@ -157,6 +163,8 @@ int cfd_stream_destroy(cfd_stream s);
 int cfd_stream_sync(cfd_stream s);
 int cfd_device_sync(void);
 int cfd_set_device(int device);
+int cfd_get_device(int* device);
+int cfd_pointer_device(const void* ptr, int* device); /* device that owns a device pointer */
 /* CUDA-event timing on the launching stream (bench.py). */
 int cfd_event_create(void** ev);
 int cfd_event_destroy(void* ev);

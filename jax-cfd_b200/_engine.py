@@ -39,13 +39,26 @@ class Plan:
     self.handle = None
 
 
-def get_plan(grid: grids.Grid, batch: int = 1, device: int = 0) -> Plan:
-  key = (grid.shape, grid.step, batch, device)
+def get_plan(grid: grids.Grid, batch: int = 1, device: Optional[int] = None, stream=None) -> Plan:
+  """The plan (tables + ONE workspace) for this grid on `device` (default: the current device).
+  A plan's workspace may only be used by work ordered on one stream, so plans are cached per
+  stream: callers that enqueue on different streams get independent workspaces."""
+  if device is None:
+    device = _lib.current_device()
+  key = (grid.shape, grid.step, batch, device, stream)
   with _plans_lock:
     p = _plans.get(key)
     if p is None:
       p = _plans[key] = Plan(grid, batch, device)
     return p
+
+
+def plan_for(grid: grids.Grid, batch: int, arrays, stream=None) -> Plan:
+  """Plan on the device that owns `arrays` (the first device array; host arrays -> current)."""
+  for a in arrays:
+    if _lib.is_device_array(a):
+      return get_plan(grid, batch, _lib.device_of(a), stream)
+  return get_plan(grid, batch, None, stream)
 
 
 def clear_plans():
@@ -163,11 +176,14 @@ def as_forcing(forcing) -> Optional[ForcingFn]:
 
 
 def make_params(grid: grids.Grid, dt: float, density: float, viscosity: Optional[float],
-                forcing: Optional[ForcingFn]):
-  """Fills struct cfd_params; returns (params, keepalive)."""
+                forcing: Optional[ForcingFn], convect_dt: Optional[float] = None):
+  """Fills struct cfd_params; returns (params, keepalive).  `convect_dt`: the dt bound into the
+  convection term by the equation builder (equations.py:127-128) when it differs from the time
+  stepper's `dt`."""
   p = Params()
   keep = []
   p.dt = float(dt)
+  p.convect_dt = 0.0 if convect_dt is None else float(convect_dt)
   p.density = float(density)
   p.has_viscosity = 0 if viscosity is None else 1
   p.viscosity = 0.0 if viscosity is None else float(viscosity)
@@ -235,6 +251,14 @@ def validate_velocity(v, grid: Optional[grids.Grid] = None) -> Tuple[grids.Grid,
     dt = np.dtype(str(u.data.dtype).replace('torch.', ''))
     if dt != np.float32:
       raise TypeError(f'the B200 path computes in float32; got {u.data.dtype}')
+  if all(dev):
+    # the kernels read raw base pointers: strided views (slices, transposes) would be misread
+    for u in v:
+      if not _lib.is_c_contiguous(u.data):
+        raise ValueError('device arrays must be C-contiguous (got a strided view; make it '
+                         'contiguous first)')
+    if len({_lib.device_of(u.data) for u in v}) != 1:
+      raise ValueError('velocity components live on different CUDA devices')
   return g, batch, lead, all(dev)
 
 
@@ -246,16 +270,27 @@ def rewrap(v, datas):
 class NativeStep:
   """step_fn of semi_implicit_navier_stokes with forward Euler (equations.py:120-151)."""
 
-  def __init__(self, grid, dt, density, viscosity, forcing: Optional[ForcingFn]):
+  def __init__(self, grid, dt, density, viscosity, forcing: Optional[ForcingFn],
+               convect_dt: Optional[float] = None):
     self.grid, self.dt, self.density, self.viscosity, self.forcing = grid, dt, density, viscosity, forcing
+    self.convect_dt = convect_dt
     self._params = None
     self._keep = None
     self.last_q = None
 
+  def with_time_step(self, time_step: float) -> 'NativeStep':
+    """The same equation advanced with another stepper dt; the convection term keeps the dt it was
+    built with (time_stepping.py:59-106 vs equations.py:127-128)."""
+    if time_step == self.dt and self.convect_dt is None:
+      return self
+    base = self.dt if self.convect_dt is None else self.convect_dt
+    return NativeStep(self.grid, time_step, self.density, self.viscosity, self.forcing,
+                      convect_dt=None if base == time_step else base)
+
   def params(self):
     if self._params is None:
       self._params, self._keep = make_params(self.grid, self.dt, self.density, self.viscosity,
-                                             self.forcing)
+                                             self.forcing, self.convect_dt)
     return self._params
 
   def __call__(self, v):
@@ -266,7 +301,8 @@ class NativeStep:
     grid, batch, lead, on_dev = validate_velocity(v, self.grid)
     if nsteps == 0:
       return tuple(v)
-    plan = get_plan(grid, batch)
+    stream = _lib.stream_of(v[0].data) if on_dev else None
+    plan = plan_for(grid, batch, [u.data for u in v], stream)
     params = self.params()
     if not on_dev:
       ins = [np.ascontiguousarray(u.data, dtype=np.float32) for u in v]
@@ -278,7 +314,6 @@ class NativeStep:
                                 ctypes.byref(params)))
       res = rewrap(v, outs)
       return (res, q) if return_q else res
-    stream = _lib.stream_of(v[0].data)
     a = [u.data for u in v]
     b = [_lib.empty_like(u.data) for u in v]
     q = _lib.empty_like(v[0].data) if return_q else None
@@ -322,10 +357,10 @@ class NativeExplicitTerms:
 
   def __call__(self, v):
     grid, batch, lead, on_dev = validate_velocity(v, self.grid)
-    plan = get_plan(grid, batch)
     ins = _to_device_tuple(v)
     outs = [_lib.empty_like(x) for x in ins]
     stream = _lib.stream_of(ins[0])
+    plan = plan_for(grid, batch, ins, stream)
     check(lib().cfd_explicit_terms(plan.handle, stream, _lib.ptr_array(ins), _lib.ptr_array(outs),
                                    ctypes.byref(self._step.params())))
     if not on_dev:
@@ -341,11 +376,11 @@ class NativeProjection:
 
   def __call__(self, v, return_q=False):
     grid, batch, lead, on_dev = validate_velocity(v, self.grid)
-    plan = get_plan(grid, batch)
     ins = _to_device_tuple(v)
     outs = [_lib.empty_like(x) for x in ins]
     q = _lib.empty_like(ins[0]) if return_q else None
     stream = _lib.stream_of(ins[0])
+    plan = plan_for(grid, batch, ins, stream)
     check(lib().cfd_project(plan.handle, stream, _lib.ptr_array(ins), _lib.ptr_array(outs),
                             None if q is None else _lib.device_ptr(q)))
     if not on_dev:
@@ -360,11 +395,11 @@ class NativeProjection:
 def axpy(v, ks, coefs):
   """u0 + sum_j coef_j k_j on the device (stage combination of navier_stokes_rk)."""
   grid, batch, lead, on_dev = validate_velocity(v)
-  plan = get_plan(grid, batch)
   x = _to_device_tuple(v)
   ys = [_to_device_tuple(k) for k in ks]
   outs = [_lib.empty_like(a) for a in x]
   stream = _lib.stream_of(x[0])
+  plan = plan_for(grid, batch, x, stream)
   n = len(ys)
   ypp = (ctypes.POINTER(ctypes.c_void_p) * max(n, 1))()
   keep = []
@@ -381,9 +416,10 @@ def axpy(v, ks, coefs):
 
 def diagnostics(v):
   grid, batch, lead, on_dev = validate_velocity(v)
-  plan = get_plan(grid, batch)
   x = _to_device_tuple(v)
   d = _lib.Diag()
-  check(lib().cfd_diagnostics(plan.handle, _lib.stream_of(x[0]), _lib.ptr_array(x), ctypes.byref(d)))
+  stream = _lib.stream_of(x[0])
+  plan = plan_for(grid, batch, x, stream)
+  check(lib().cfd_diagnostics(plan.handle, stream, _lib.ptr_array(x), ctypes.byref(d)))
   return dict(kinetic_energy=d.kinetic_energy, enstrophy=d.enstrophy, max_abs_div=d.max_abs_div,
               max_speed_sq=d.max_speed_sq)

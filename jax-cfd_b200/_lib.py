@@ -42,6 +42,7 @@ class Params(ctypes.Structure):
       ('sep_scale', ctypes.c_float * MAX_DIM),
       ('has_sep', ctypes.c_int32 * MAX_DIM),
       ('field', ctypes.c_void_p * MAX_DIM),
+      ('convect_dt', ctypes.c_double),
   ]
 
 
@@ -116,6 +117,8 @@ _SIGS = {
     'cfd_stream_sync': (ctypes.c_int, [ctypes.c_void_p]),
     'cfd_device_sync': (ctypes.c_int, []),
     'cfd_set_device': (ctypes.c_int, [ctypes.c_int]),
+    'cfd_get_device': (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    'cfd_pointer_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
     'cfd_event_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
     'cfd_event_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'cfd_event_record': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -159,20 +162,29 @@ class DeviceArray:
   """float32 array in device memory obtained through the C ABI (cfd_malloc)."""
 
   def __init__(self, shape: Sequence[int], dtype=np.float32, ptr: Optional[int] = None,
-               owner=None):
+               owner=None, device: Optional[int] = None):
     self.shape = tuple(int(s) for s in shape)
     self.dtype = np.dtype(dtype)
     self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
     self._owner = owner
     if ptr is None:
       require_device()
-      p = ctypes.c_void_p()
-      check(lib().cfd_malloc(ctypes.byref(p), max(self.nbytes, 16)))
+      prev = current_device()
+      self.device = prev if device is None else int(device)
+      if self.device != prev:
+        check(lib().cfd_set_device(self.device))
+      try:
+        p = ctypes.c_void_p()
+        check(lib().cfd_malloc(ctypes.byref(p), max(self.nbytes, 16)))
+      finally:
+        if self.device != prev:
+          check(lib().cfd_set_device(prev))
       self.ptr = p.value
       self._owned = True
     else:
       self.ptr = int(ptr)
       self._owned = False
+      self.device = device
 
   @property
   def ndim(self):
@@ -232,6 +244,43 @@ def is_device_array(x) -> bool:
                                         not isinstance(x, np.ndarray))
 
 
+def is_c_contiguous(x) -> bool:
+  """True when a device array is dense and row-major (the kernels read raw base pointers)."""
+  if isinstance(x, DeviceArray):
+    return True
+  if hasattr(x, 'is_contiguous'):  # torch
+    return bool(x.is_contiguous())
+  cai = x.__cuda_array_interface__
+  strides = cai.get('strides')
+  if strides is None:
+    return True
+  itemsize = np.dtype(cai['typestr']).itemsize
+  expect = itemsize
+  for n, st in zip(reversed(cai['shape']), reversed(strides)):
+    if n != 1 and st != expect:
+      return False
+    expect *= n
+  return True
+
+
+def device_of(x) -> int:
+  """Index of the CUDA device that owns a device array's memory."""
+  dev = getattr(x, 'device', None)
+  if isinstance(dev, int):  # DeviceArray
+    return dev
+  if dev is not None and getattr(dev, 'type', None) == 'cuda' and dev.index is not None:  # torch
+    return int(dev.index)
+  d = ctypes.c_int(0)
+  check(lib().cfd_pointer_device(device_ptr(x), ctypes.byref(d)))
+  return int(d.value)
+
+
+def current_device() -> int:
+  d = ctypes.c_int(0)
+  check(lib().cfd_get_device(ctypes.byref(d)))
+  return int(d.value)
+
+
 def device_ptr(x) -> int:
   if isinstance(x, DeviceArray):
     return x.ptr
@@ -253,7 +302,7 @@ def empty_like(x):
   """Device output buffer of the same kind as `x` (torch tensor -> torch tensor)."""
   if hasattr(x, 'data_ptr') and hasattr(x, 'new_empty'):
     return x.new_empty(tuple(x.shape))
-  return DeviceArray(tuple(x.shape), np.float32)
+  return DeviceArray(tuple(x.shape), np.float32, device=device_of(x))
 
 
 def stream_of(x) -> Optional[int]:

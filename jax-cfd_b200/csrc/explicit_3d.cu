@@ -810,8 +810,9 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ float nanmax_f(float a, float b) { return (a > b || a != a) ? a : b; }  // jnp.max
 __device__ __forceinline__ float warp_max_f(float v) {
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = nanmax_f(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ void atomic_max_d(double* addr, double val) {
@@ -819,7 +820,8 @@ __device__ __forceinline__ void atomic_max_d(double* addr, double val) {
   unsigned long long old = *a, assumed;
   do {
     assumed = old;
-    if (__longlong_as_double(assumed) >= val) break;
+    const double cur = __longlong_as_double(assumed);
+    if (cur != cur || (cur >= val && val == val)) break;  // NaN sticks
     old = atomicCAS(a, assumed, __double_as_longlong(val));
   } while (assumed != old);
 }
@@ -847,8 +849,8 @@ __global__ void diag3d_kernel(const float* __restrict__ u, const float* __restri
     const float sp = u0 * u0 + v0 * v0 + w0 * w0;
     ke += 0.5 * (double)sp;
     ens += 0.5 * ((double)cx * cx + (double)cy * cy + (double)cz * cz);
-    mdiv = fmaxf(mdiv, fabsf(div));
-    msp = fmaxf(msp, sp);
+    mdiv = nanmax_f(fabsf(div), mdiv);
+    msp = nanmax_f(sp, msp);
   }
   ke = warp_sum_d(ke);
   ens = warp_sum_d(ens);

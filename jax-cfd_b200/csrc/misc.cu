@@ -38,8 +38,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// NaN-propagating max (jnp.max semantics, equations.py:68: a blown-up state must not yield a
+// finite time step); fmaxf would drop the NaN
+__device__ __forceinline__ float nanmax(float a, float b) { return (a > b || a != a) ? a : b; }
 __device__ __forceinline__ float warp_max(float v) {
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ void atomic_max_double(double* addr, double val) {
@@ -47,7 +50,8 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double val) {
   unsigned long long old = *a, assumed;
   do {
     assumed = old;
-    if (__longlong_as_double(assumed) >= val) break;
+    const double cur = __longlong_as_double(assumed);
+    if (cur != cur || (cur >= val && val == val)) break;  // NaN sticks
     old = atomicCAS(a, assumed, __double_as_longlong(val));
   } while (assumed != old);
 }
@@ -75,8 +79,8 @@ __global__ void diag2d_kernel(const float* __restrict__ u, const float* __restri
     const float sp = u0 * u0 + v0 * v0;
     ke += 0.5 * (double)sp;
     ens += 0.5 * (double)w * (double)w;
-    mdiv = fmaxf(mdiv, fabsf(div));
-    msp = fmaxf(msp, sp);
+    mdiv = nanmax(fabsf(div), mdiv);
+    msp = nanmax(sp, msp);
   }
   ke = warp_sum(ke);
   ens = warp_sum(ens);

@@ -137,8 +137,11 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
   const int d = p->ndim;
   c->dt = (float)prm->dt;
   float lap_sum = 0.f;
+  // the dt of the Lax-Wendroff Courant number (equations.py:127-128 closes `convect` over the
+  // builder's dt) may differ from the dt of the time stepper (time_stepping.py:101)
+  const double cdt = prm->convect_dt > 0 ? prm->convect_dt : prm->dt;
   for (int j = 0; j < d; ++j) {
-    c->dth[j] = (float)(prm->dt / p->step[j]);
+    c->dth[j] = (float)(cdt / p->step[j]);
     c->inv_h[j] = (float)(1.0 / p->step[j]);
     const float hf = (float)p->step[j];
     const float inv = 1.0f / hf;
@@ -261,6 +264,15 @@ int check_plan(const cfd_plan* p) {
   CFD_CUDA_OK(cudaSetDevice(p->device));
   return 0;
 }
+
+// Every entry point runs on the plan's device and leaves the caller's current device untouched.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { cudaGetDevice(&prev); }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 // q = pinv(rhs): rfft rows -> x lines (fwd * D * inv) -> irfft rows
 int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
@@ -398,7 +410,8 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
     return set_error_msg("last axis longer than 32768 is not supported yet");
   for (int j = 1; j + 1 < ndim; ++j)
     if (shape[j] > (1 << 14)) return set_error_msg("middle axis longer than 16384 is not supported yet");
-  if (cfd_device_count() <= device) return set_error_msg("no such CUDA device (no CPU fallback)");
+  if (device < 0 || cfd_device_count() <= device) return set_error_msg("no such CUDA device (no CPU fallback)");
+  DeviceGuard guard_;
   CFD_CUDA_OK(cudaSetDevice(device));
   cfd_plan* p = new cfd_plan();
   p->ndim = ndim;
@@ -481,6 +494,7 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
 
 void cfd_plan_destroy(cfd_plan* p) {
   if (p == nullptr) return;
+  DeviceGuard guard_;
   cudaSetDevice(p->device);
   cudaFree(p->tw_row);
   if (p->shared) {
@@ -537,6 +551,7 @@ size_t cfd_plan_workspace_bytes(const cfd_plan* p) { return p ? p->workspace_byt
 
 int cfd_step(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
              float* q_out, const cfd_params* params) {
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (!v_in || !v_out || !params) return set_error_msg("null argument");
   for (int a = 0; a < p->ndim; ++a) {
@@ -685,6 +700,7 @@ static int repeated_lazy(cfd_plan* p, cudaStream_t st, const float* const* v_in,
 
 int cfd_repeated(cfd_plan* p, cfd_stream stream, float* const* v_a, float* const* v_b, int nsteps,
                  const cfd_params* params, int* result_in_b) {
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (!v_a || !v_b || !params) return set_error_msg("null argument");
   if (nsteps < 0) return set_error_msg("nsteps must be >= 0");
@@ -709,6 +725,7 @@ int cfd_repeated(cfd_plan* p, cfd_stream stream, float* const* v_a, float* const
 
 int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
                        float* const* dvdt_out, const cfd_params* params) {
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (!v_in || !dvdt_out || !params) return set_error_msg("null argument");
   StepConsts c;
@@ -732,6 +749,7 @@ int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
 
 int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
                 float* q_out) {
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (!v_in || !v_out) return set_error_msg("null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -756,6 +774,7 @@ int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float*
 
 int cfd_axpy(cfd_plan* p, cfd_stream stream, const float* const* x, int nterms,
              const float* const* const* y, const double* coef, float* const* out) {
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (nterms < 0 || nterms > 4) return set_error_msg("cfd_axpy: 0 <= nterms <= 4");
   const size_t n = (size_t)p->batch * p->cells;
@@ -772,6 +791,7 @@ int cfd_axpy(cfd_plan* p, cfd_stream stream, const float* const* x, int nterms,
 }
 
 int cfd_diagnostics(cfd_plan* p, cfd_stream stream, const float* const* v, cfd_diag* out) {
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (!v || !out) return set_error_msg("null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -796,6 +816,7 @@ int cfd_diagnostics(cfd_plan* p, cfd_stream stream, const float* const* v, cfd_d
 
 int cfd_step_host(cfd_plan* p, const float* const* v_in_host, float* const* v_out_host,
                   float* q_out_host, int nsteps, const cfd_params* params) {
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (!v_in_host || !v_out_host || !params) return set_error_msg("null argument");
   if (nsteps < 1) return set_error_msg("nsteps must be >= 1");
@@ -840,6 +861,7 @@ int cfd_step_profile(cfd_plan* p, cfd_stream stream, const float* const* v_in, f
   // Times every kernel of a 3-step chain (first step, lazy steps, final materialisation) with
   // CUDA events on the launching stream; reports the mean per launch, aggregated by kernel name
   // in first-seen order.
+  DeviceGuard guard_;
   if (int e = check_plan(p)) return e;
   if (reps < 1) reps = 1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -935,6 +957,18 @@ int cfd_device_sync(void) {
 }
 int cfd_set_device(int device) {
   CFD_CUDA_OK(cudaSetDevice(device));
+  return 0;
+}
+int cfd_get_device(int* device) {
+  CFD_CUDA_OK(cudaGetDevice(device));
+  return 0;
+}
+int cfd_pointer_device(const void* ptr, int* device) {
+  cudaPointerAttributes a;
+  CFD_CUDA_OK(cudaPointerGetAttributes(&a, ptr));
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+    return set_error_msg("not a device pointer");
+  *device = a.device;
   return 0;
 }
 int cfd_event_create(void** ev) {

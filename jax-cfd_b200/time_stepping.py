@@ -59,7 +59,9 @@ def navier_stokes_rk(tableau: ButcherTableau, equation: ExplicitNavierStokesODE,
   num_steps = len(b)
   native = _is_native(equation)
   if native and num_steps == 1 and b[0] == 1:
-    return equation.fused_step
+    # one fused call per step; a stepper dt that differs from the builder's dt (which stays
+    # bound inside the convection term) gets its own parameter block
+    return equation.fused_step.with_time_step(dt)
 
   def combine(u0, ks, coefs):
     pairs = [(c, k) for c, k in zip(coefs, ks) if c]

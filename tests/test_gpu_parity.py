@@ -77,7 +77,7 @@ def test_step_matches_reference_golden(cfd, name):
     vn = cfd.funcutils.repeated(step, n)(v)
     for i, a in enumerate(to_np(vn)):
       err = gu.rel_l2(a, rec[f'f32_v{n}_{i}'])
-      assert err < TOL * max(1, n / 2), (name, n, i, err)
+      assert err < TOL, (name, n, i, err)  # measured: <= 2e-7 at n = 20
 
 
 @pytest.mark.parametrize('name', ['rk4_2d_32', 'rk2_2d_32'])
@@ -413,3 +413,25 @@ def test_thousand_step_statistics_track_the_oracle(cfd):
   print('\nstep  KE(cuda)  KE(oracle)  Z(cuda)  Z(oracle)  max|div|  field rel-L2')
   for r in rows:
     print('%5d %.6f %.6f %.5f %.5f %.2e %.2e' % r)
+
+
+def test_stepper_time_step_separate_from_convection_dt(cfd):
+  """time_stepper=lambda ode, dt: forward_euler(ode, dt / 2): the Courant number inside
+  Lax-Wendroff keeps the builder's dt (equations.py:127-128), the update uses dt / 2."""
+  rec = gu.load('k2d_64x32')
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  dt = rec['dt']
+  step = cfd.equations.semi_implicit_navier_stokes(
+      rec['density'], rec['viscosity'], dt, grid, forcing=make_forcing(cfd, grid, rec),
+      time_stepper=lambda ode, t: cfd.time_stepping.forward_euler(ode, t / 2))
+  arrays = tuple(rec[f'v0_{i}'] for i in range(2))
+  got = to_np(step(wrap(cfd, grid, arrays)))
+  k0 = cfd_oracle.explicit_terms(arrays, dt, rec['h'], rec['viscosity'] / rec['density'],
+                                 gu.oracle_forcing(rec), rec['density'])
+  ustar = tuple(u + np.float32(dt / 2) * k for u, k in zip(arrays, k0))
+  want, _ = cfd_oracle.projection(ustar, rec['h'])
+  for a, b in zip(got, want):
+    assert gu.rel_l2(a, b) < TOL
+  plain = to_np(cfd.equations.semi_implicit_navier_stokes(
+      rec['density'], rec['viscosity'], dt, grid, forcing=make_forcing(cfd, grid, rec))(wrap(cfd, grid, arrays)))
+  assert gu.rel_l2(got[0], plain[0]) > 1e-4  # and it really is a different step

@@ -166,3 +166,39 @@ def test_reference_arm_prints_contract_line_under_a_torchrun_like_environment():
   env['RANK'] = '1'
   out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
   assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith('{')]
+
+
+def test_strided_device_views_are_rejected():
+  """the kernels read raw base pointers, so a device array that reports non-dense
+  strides (a slice / transpose) must be refused instead of being misread."""
+  import jax_cfd_b200 as cfd
+  from jax_cfd_b200 import _engine, _lib
+
+  class FakeCai:
+    def __init__(self, shape, strides):
+      self.shape, self.dtype = shape, np.dtype(np.float32)
+      self.__cuda_array_interface__ = {'shape': shape, 'typestr': '<f4', 'data': (4096, False),
+                                       'version': 3, 'strides': strides}
+  assert _lib.is_c_contiguous(FakeCai((8, 16), None))
+  assert _lib.is_c_contiguous(FakeCai((8, 16), (64, 4)))
+  assert _lib.is_c_contiguous(FakeCai((1, 8, 16), (999, 64, 4)))
+  assert not _lib.is_c_contiguous(FakeCai((8, 16), (128, 4)))   # every other row
+  assert not _lib.is_c_contiguous(FakeCai((8, 16), (4, 32)))    # transposed
+  grid = cfd.grids.Grid((8, 16), domain=((0, 1), (0, 1)))
+  bc = cfd.boundaries.periodic_boundary_conditions(2)
+  v = tuple(cfd.grids.GridVariable(cfd.grids.GridArray(FakeCai((8, 16), (128, 4)), o, grid), bc)
+            for o in grid.cell_faces)
+  with pytest.raises(ValueError, match='C-contiguous'):
+    _engine.validate_velocity(v, grid)
+
+
+def test_forward_euler_with_a_different_time_step_keeps_the_convection_dt():
+  """navier_stokes_rk's `time_step` and the dt bound into convect by the equation
+  builder are separate in the reference (time_stepping.py:59-106 vs equations.py:127-128)."""
+  import jax_cfd_b200 as cfd
+  grid = cfd.grids.Grid((32, 32), domain=((0, 1), (0, 1)))
+  step = cfd.equations.semi_implicit_navier_stokes(
+      1.0, 1e-3, 0.01, grid, time_stepper=lambda ode, dt: cfd.time_stepping.forward_euler(ode, dt / 2))
+  assert step.dt == 0.005 and step.convect_dt == 0.01
+  same = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, grid)
+  assert same.dt == 0.01 and same.convect_dt is None
