@@ -68,6 +68,20 @@ inline int xlines_lemax(int lm) {
   return (lm == 12 || lm == 13) ? 5 : 4;
 }
 
+// Balanced radix schedule with one radix-32 pass (FftPlan<LM, 5, 5, true>: 8192 points = 32 x 16 x
+// 16, three passes and two exchanges per direction instead of 16 x 16 x 16 x 2 with three) for
+// the 8192-point x lines, whose kernel is bound by the shared-memory / L1 data pipe (63 % of its
+// peak in round 1, two thirds of it exchange traffic).  CFD_XLINES_BAL=0|1 overrides.
+inline bool xlines_balanced(int lm) {
+  static const int forced = [] {
+    const char* e = getenv("CFD_XLINES_BAL");
+    return e ? atoi(e) : -1;
+  }();
+  if (xlines_lemax(lm) != 5) return false;
+  if (forced == 0 || forced == 1) return forced == 1 && lm == 13;
+  return lm == 13;
+}
+
 // points per thread (log2) of the row kernels: 32 points per thread measured slower there (218 vs
 // 190 us, 268 vs 237 us at 8192^2 -- the rows of a CTA already drift apart on their own named
 // barriers); CFD_ROWS_LE=4|5 overrides

@@ -12,6 +12,9 @@
 // per pass as tw[(r-1) * Ns + k] = exp(-2 pi i r k / (Ns R)) so that a warp reads consecutive k.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
+
+#include <vector>
 
 namespace cfd {
 
@@ -141,6 +144,44 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
   }
 }
 
+// 32 points: two 16-point transforms of the even / odd inputs + one twiddle level
+template <int DIR>
+__device__ __forceinline__ void dft32(float2 (&a)[32]) {
+  float2 e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    e[i] = a[2 * i];
+    o[i] = a[2 * i + 1];
+  }
+  dft16<DIR>(e);
+  dft16<DIR>(o);
+  // forward twiddles exp(-2 pi i k / 32), k = 1..15 (k = 8 is -i)
+  constexpr float C1 = 0.98078528040323044913f, S1 = 0.19509032201612826785f;
+  constexpr float C2 = 0.92387953251128675613f, S2 = 0.38268343236508977173f;
+  constexpr float C3 = 0.83146961230254523708f, S3 = 0.55557023301960222474f;
+  constexpr float H = 0.70710678118654752440f;
+  o[1] = twmul<DIR>(o[1], make_float2(C1, -S1));
+  o[2] = twmul<DIR>(o[2], make_float2(C2, -S2));
+  o[3] = twmul<DIR>(o[3], make_float2(C3, -S3));
+  o[4] = twmul<DIR>(o[4], make_float2(H, -H));
+  o[5] = twmul<DIR>(o[5], make_float2(S3, -C3));
+  o[6] = twmul<DIR>(o[6], make_float2(S2, -C2));
+  o[7] = twmul<DIR>(o[7], make_float2(S1, -C1));
+  o[8] = mul_dir_i<DIR>(o[8]);
+  o[9] = twmul<DIR>(o[9], make_float2(-S1, -C1));
+  o[10] = twmul<DIR>(o[10], make_float2(-S2, -C2));
+  o[11] = twmul<DIR>(o[11], make_float2(-S3, -C3));
+  o[12] = twmul<DIR>(o[12], make_float2(-H, -H));
+  o[13] = twmul<DIR>(o[13], make_float2(-C3, -S3));
+  o[14] = twmul<DIR>(o[14], make_float2(-C2, -S2));
+  o[15] = twmul<DIR>(o[15], make_float2(-C1, -S1));
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    a[k] = cadd(e[k], o[k]);
+    a[k + 16] = csub(e[k], o[k]);
+  }
+}
+
 template <int R, int DIR>
 struct Dft;
 template <int DIR>
@@ -159,6 +200,10 @@ template <int DIR>
 struct Dft<16, DIR> {
   static __device__ __forceinline__ void run(float2 (&a)[16]) { dft16<DIR>(a); }
 };
+template <int DIR>
+struct Dft<32, DIR> {
+  static __device__ __forceinline__ void run(float2 (&a)[32]) { dft32<DIR>(a); }
+};
 
 // ---- radix plan -------------------------------------------------------------------------------
 // M = 2^LM points, E = min(2^LEMAX, M) points per thread, radix min(2^LRMAX, E) (defaults: 16
@@ -167,7 +212,39 @@ struct Dft<16, DIR> {
 // share the pass order and the twiddle table (the inverse conjugates).  Every transform starts from
 // registers v[e] = x[t + G*e] and ends with v[slot] = X[t + G*slot], so a forward transform can be
 // scaled in registers and fed straight into an inverse transform without an exchange.
-template <int LM, int LEMAX = 4, int LRMAX = LEMAX>
+// Pass schedule of a 2^lm-point transform with radices up to 2^lr (shared by the kernels and by the
+// host code that lays out the twiddle table, plan.cu).
+//   bal = false: full-radix passes first, one final smaller radix        (13, 4) -> 16 16 16 2
+//   bal = true:  the fewest passes, radices as even as possible, larger first (13, 5) -> 32 16 16
+__host__ __device__ constexpr int fft_sched_np(int lm, int lr) { return (lm + lr - 1) / lr; }
+__host__ __device__ constexpr int fft_sched_lr(int lm, int lr, bool bal, int p) {
+  if (!bal) return (p < lm / lr) ? lr : (lm - (lm / lr) * lr);
+  const int np = fft_sched_np(lm, lr);
+  return lm / np + (p < lm % np ? 1 : 0);
+}
+
+// Host side: twiddle table of a 2^lm-point transform with the schedule of FftPlan<lm, ., lrmax, bal>:
+// pass p owns (R - 1) * Ns entries, tw[(r - 1) * Ns + k] = exp(-2 pi i r k / (Ns R)), computed in
+// double precision and rounded once.
+inline std::vector<float2> fft_build_twiddles(int lm, int lrmax = 4, bool bal = false) {
+  const int lr = lm < lrmax ? lm : lrmax;
+  const int np = fft_sched_np(lm, lr);
+  std::vector<float2> tw;
+  int lns = 0;
+  for (int p = 0; p < np; ++p) {
+    const int lrp = fft_sched_lr(lm, lr, bal, p);
+    const int R = 1 << lrp, Ns = 1 << lns;
+    for (int r = 1; r < R; ++r)
+      for (int k = 0; k < Ns; ++k) {
+        const double ang = -2.0 * 3.14159265358979323846 * (double)r * (double)k / ((double)Ns * (double)R);
+        tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+      }
+    lns += lrp;
+  }
+  return tw;
+}
+
+template <int LM, int LEMAX = 4, int LRMAX = LEMAX, bool BAL = false>
 struct FftPlan {
   static constexpr int M = 1 << LM;
   static constexpr int LE = LM < LEMAX ? LM : LEMAX;
@@ -176,13 +253,11 @@ struct FftPlan {
   // radix of the full passes: 2^LR <= E.  LR < LE: a thread runs E / 2^LR independent butterflies
   // per pass (more instruction-level parallelism per thread, half the threads per line)
   static constexpr int LR = LE < LRMAX ? LE : LRMAX;
-  static constexpr int NP = (LM + LR - 1) / LR;  // passes
+  static constexpr int NP = fft_sched_np(LM, LR);  // passes
   static constexpr int LPAD = LR < 4 ? 4 : LR;   // one padding slot per 2^LPAD points
   __host__ __device__ static constexpr int pad(int i) { return i + (i >> LPAD); }
   // log2 radix of forward pass p
-  __host__ __device__ static constexpr int lr_fwd(int p) {
-    return (p < LM / LR) ? LR : (LM - (LM / LR) * LR);
-  }
+  __host__ __device__ static constexpr int lr_fwd(int p) { return fft_sched_lr(LM, LR, BAL, p); }
   __host__ __device__ static constexpr int lns_fwd(int p) {  // log2 Ns before pass p
     int s = 0;
     for (int q = 0; q < p; ++q) s += lr_fwd(q);
@@ -234,6 +309,56 @@ __device__ __forceinline__ void fft_pass_butterflies(float2 (&v)[P::E], const fl
   }
 }
 
+// Twiddles of one butterfly applied from FEW table entries: only w^(2^b k) (b = 0..LR-1) are loaded;
+// input r is multiplied by the entry of each set bit of r except that the low three bits use
+// products formed once (w^3, w^5, w^6, w^7).  A radix-16 butterfly then issues 4 loads instead of
+// 15 (the line kernels are bound by the L1 / shared-memory data pipe, and twiddle loads were a
+// quarter of its wavefronts) at the price of 11 more complex multiplies; rounding: at most three
+// float32 multiplies on a twiddle path instead of one table entry rounded once.
+#ifndef CFD_TW_POW
+#define CFD_TW_POW 1
+#endif
+template <int R, int DIR>
+__device__ __forceinline__ void apply_twiddles_pow(float2 (&a)[R], const float2* __restrict__ tw,
+                                                   int NS, int k) {
+  if constexpr (R == 2) {
+    a[1] = twmul<DIR>(a[1], __ldg(&tw[k]));
+  } else {
+    const float2 w1 = __ldg(&tw[k]), w2 = __ldg(&tw[NS + k]);
+    if constexpr (R == 4) {
+      a[1] = twmul<DIR>(a[1], w1);
+      a[2] = twmul<DIR>(a[2], w2);
+      a[3] = twmul<DIR>(a[3], cmul(w1, w2));
+    } else {
+      const float2 w4 = __ldg(&tw[3 * NS + k]);
+      float2 w[8];
+      w[1] = w1;
+      w[2] = w2;
+      w[3] = cmul(w1, w2);
+      w[4] = w4;
+      w[5] = cmul(w4, w1);
+      w[6] = cmul(w4, w2);
+      w[7] = cmul(w4, w[3]);
+#pragma unroll
+      for (int hi = 0; hi < R; hi += 8) {
+#pragma unroll
+        for (int lo = 1; lo < 8; ++lo) a[hi + lo] = twmul<DIR>(a[hi + lo], w[lo]);
+      }
+      if constexpr (R >= 16) {
+        const float2 w8 = __ldg(&tw[7 * NS + k]);
+#pragma unroll
+        for (int r = 8; r < R; ++r)
+          if (r & 8) a[r] = twmul<DIR>(a[r], w8);
+      }
+      if constexpr (R >= 32) {
+        const float2 w16 = __ldg(&tw[15 * NS + k]);
+#pragma unroll
+        for (int r = 16; r < R; ++r) a[r] = twmul<DIR>(a[r], w16);
+      }
+    }
+  }
+}
+
 template <class P, int LR, int LNS, int DIR>
 __device__ __forceinline__ void fft_pass_compute(float2 (&v)[P::E], int t,
                                                  const float2* __restrict__ tw) {
@@ -245,8 +370,12 @@ __device__ __forceinline__ void fft_pass_compute(float2 (&v)[P::E], int t,
     for (int r = 0; r < R; ++r) a[r] = v[q + r * NB];
     if (LNS > 0) {
       const int k = (t + P::G * q) & (NS - 1);
+#if CFD_TW_POW
+      apply_twiddles_pow<R, DIR>(a, tw, NS, k);
+#else
 #pragma unroll
       for (int r = 1; r < R; ++r) a[r] = twmul<DIR>(a[r], __ldg(&tw[(r - 1) * NS + k]));
+#endif
     }
     Dft<R, DIR>::run(a);
 #pragma unroll

@@ -86,23 +86,14 @@ static int ilog2(int64_t n) {
 }
 static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 
-// Twiddle table for a 2^lm-point transform, same pass structure as FftPlan<LM>.
-static std::vector<float2> build_twiddles(int lm, int lemax = 4) {
-  const int le = lm < lemax ? lm : lemax;
-  const int np = (lm + le - 1) / le;
-  std::vector<float2> tw;
-  int lns = 0;
-  for (int p = 0; p < np; ++p) {
-    const int lr = (p < lm / le) ? le : (lm - (lm / le) * le);
-    const int R = 1 << lr, Ns = 1 << lns;
-    for (int r = 1; r < R; ++r)
-      for (int k = 0; k < Ns; ++k) {
-        const double ang = -2.0 * M_PI * (double)r * (double)k / ((double)Ns * (double)R);
-        tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
-      }
-    lns += lr;
-  }
-  return tw;
+static std::vector<float2> build_twiddles(int lm, int lrmax = 4, bool bal = false) {
+  return fft_build_twiddles(lm, lrmax, bal);
+}
+// ... for the x lines of a 2-D plan: the x-line kernel picks its own schedule per length
+static std::vector<float2> build_xline_twiddles(int lm_x) {
+  const int lm = lm_x == 15 ? 14 : lm_x;  // 32768-point lines are two 16384-point transforms
+  const bool bal = xlines_balanced(lm);
+  return build_twiddles(lm, bal ? 5 : 4, bal);
 }
 
 }  // namespace cfd
@@ -235,7 +226,7 @@ int plan_tables_create(cfd_plan* p, int ndim, const int64_t* shape, const double
   p->lamf[0] = nullptr;
   p->lm_x = ilog2(Nxg);
   p->t_paired = choose_t_paired(ndim, p->lm_row, p->lm_x, p->world);
-  int err = upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x));
+  int err = upload(&p->tw_x, ndim == 2 ? build_xline_twiddles(p->lm_x) : build_twiddles(p->lm_x));
   if (p->lm_x == 15) err |= big_line_tables(p, (size_t)(shape[1] / 2) / (p->world > 0 ? p->world : 1));
   std::vector<double> lam(Nxg);
   for (int k = 0; k < Nxg; ++k)
@@ -429,7 +420,7 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   p->t_paired = choose_t_paired(ndim, p->lm_row, p->lm_x, p->world);
   int err = 0;
   err |= upload(&p->tw_row, build_twiddles(p->lm_row));
-  err |= upload(&p->tw_x, build_twiddles(p->lm_x == 15 ? 14 : p->lm_x));
+  err |= upload(&p->tw_x, ndim == 2 ? build_xline_twiddles(p->lm_x) : build_twiddles(p->lm_x));
   if (p->lm_x == 15 && ndim == 2) err |= big_line_tables(p, (size_t)batch * (Ny / 2));
   if (ndim == 3) {
     p->lm_y = ilog2(shape[1]);

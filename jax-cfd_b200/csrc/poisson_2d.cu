@@ -64,39 +64,38 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
   LSYNC::sync(row);
 #pragma unroll
   for (int e = 0; e < E; ++e) s[PAD(t + G * e)] = v[e];
-  LSYNC::sync(row);
-  // split the half-size complex transform into the real-input spectrum (in place, pairs k, M-k)
-  for (int k = t; k <= M / 2; k += G) {
-    if (k == 0) {
-      const float2 z = s[0];
-      s[0] = make_float2(2.f * (z.x + z.y), 2.f * (z.x - z.y));
-    } else if (k == M / 2) {
-      const float2 z = s[PAD(k)];
-      s[PAD(k)] = make_float2(2.f * z.x, -2.f * z.y);
+  __syncthreads();
+  // Split of the half-size complex transform into the real-input spectrum (pairs k, M - k), merged
+  // with the transposed store: every pair is read from the line buffers once and goes straight to
+  // T (no in-place split pass: two shared-memory traversals fewer).  For each ky the ROWS values of
+  // this CTA are contiguous in T.
+  float2* Tb = T + b * (size_t)M * Nx + (PAIRED ? 2 : 1) * (size_t)x0;
+  auto tptr = [&](int ky, int r) -> float2* {
+    return PAIRED ? Tb + ((size_t)(ky >> 1) * Nx + r) * 2 + (ky & 1) : Tb + (size_t)ky * Nx + r;
+  };
+  constexpr int NT = ROWS * G;
+#pragma unroll 4
+  for (int idx = tid; idx < ROWS * (M / 2); idx += NT) {
+    int r, k;
+    if constexpr (PAIRED) {
+      r = (idx >> 1) % ROWS;
+      k = 2 * (idx / (2 * ROWS)) + (idx & 1);
     } else {
-      const float2 zk = s[PAD(k)], zm = s[PAD(M - k)];
+      r = idx % ROWS;
+      k = idx / ROWS;
+    }
+    const float2* sr = smem + r * RS;
+    if (k == 0) {
+      const float2 z = sr[0], zh = sr[PAD(M / 2)];
+      *tptr(0, r) = make_float2(2.f * (z.x + z.y), 2.f * (z.x - z.y));
+      *tptr(M / 2, r) = make_float2(2.f * zh.x, -2.f * zh.y);
+    } else {
+      const float2 zk = sr[PAD(k)], zm = sr[PAD(M - k)];
       const float2 A = make_float2(zk.x + zm.x, zk.y - zm.y);  // Zk + conj(Zm)
       const float2 B = make_float2(zk.x - zm.x, zk.y + zm.y);  // Zk - conj(Zm)
       const float2 WB = cmul(__ldg(rtw + k), B);               // (-i w^k) B
-      s[PAD(k)] = make_float2(A.x + WB.x, A.y + WB.y);
-      s[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
-    }
-  }
-  __syncthreads();
-  // transposed store: for each ky the ROWS values of this CTA are contiguous in T
-  float2* Tb = T + b * (size_t)M * Nx + (PAIRED ? 2 : 1) * (size_t)x0;
-  constexpr int NT = ROWS * G;
-  if constexpr (PAIRED) {
-#pragma unroll 4
-    for (int idx = tid; idx < ROWS * M; idx += NT) {
-      const int p = idx & 1, r = (idx >> 1) % ROWS, j = idx / (2 * ROWS);
-      Tb[((size_t)j * Nx + r) * 2 + p] = smem[r * RS + PAD(2 * j + p)];
-    }
-  } else {
-#pragma unroll 4
-    for (int idx = tid; idx < ROWS * M; idx += NT) {
-      const int r = idx % ROWS, ky = idx / ROWS;
-      Tb[(size_t)ky * Nx + r] = smem[r * RS + PAD(ky)];
+      *tptr(k, r) = make_float2(A.x + WB.x, A.y + WB.y);
+      *tptr(M - k, r) = make_float2(A.x - WB.x, -(A.y - WB.y));
     }
   }
 }
@@ -178,14 +177,15 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
 #ifndef CFD_XL_MINB
 #define CFD_XL_MINB 1
 #endif
-template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT, bool DB, bool PAIRED>
+// BAL: balanced radix schedule with radix-32 passes (fft_rows.cuh, xlines_balanced)
+template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT, bool DB, bool PAIRED, bool BAL = false>
 __global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX, 4>::G,
                                   (LEMAX == 5 && LINES * FftPlan<LM, LEMAX, 4>::G <= 256) ? 2 : CFD_XL_MINB)
 xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
               const float* __restrict__ lamyf, double cutoff, float norm) {
-  using P = FftPlan<LM, LEMAX, 4>;
+  using P = FftPlan<LM, LEMAX, BAL ? 5 : 4, BAL>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, 16);
   extern __shared__ float2 smem[];
@@ -350,53 +350,59 @@ irfft_rows_kernel(const float2* __restrict__ T, float* __restrict__ q, int Nx,
   const size_t b = blockIdx.y;
   float2* s = smem + row * RS;
   {
-    // all of a thread's gather loads are issued before the first one is consumed (ROWS * M / NT
-    // = E of them): the transposed reads are the latency-critical start of this kernel
+    // Gather merged with the pre-processing of the inverse real transform: a thread loads the pairs
+    // (k, M - k) of one row straight from T, forms Z[k] and Z[M - k] in registers and stores them
+    // to the line buffers (no separate in-place pass: two shared-memory traversals fewer).  All of
+    // a thread's gather loads are issued before the first one is consumed: the transposed reads
+    // are the latency-critical start of this kernel.
     const float2* Tb = T + b * (size_t)M * Nx + (PAIRED ? 2 : 1) * (size_t)x0;
-    constexpr int NG = ROWS * M / NT;
-    float2 tmp[NG];
+    auto tptr = [&](int ky, int r) -> const float2* {
+      return PAIRED ? Tb + ((size_t)(ky >> 1) * Nx + r) * 2 + (ky & 1) : Tb + (size_t)ky * Nx + r;
+    };
+    auto pair_of = [&](int idx, int& r, int& k) {
+      if constexpr (PAIRED) {
+        r = (idx >> 1) % ROWS;
+        k = 2 * (idx / (2 * ROWS)) + (idx & 1);
+      } else {
+        r = idx % ROWS;
+        k = idx / ROWS;
+      }
+    };
+    constexpr int NG = (ROWS * (M / 2) + NT - 1) / NT;  // pairs per thread
+    float2 xa[NG], xb[NG];
 #pragma unroll
     for (int n = 0; n < NG; ++n) {
       const int idx = tid + n * NT;
-      if (PAIRED) {
-        const int p = idx & 1, r = (idx >> 1) % ROWS, j = idx / (2 * ROWS);
-        tmp[n] = __ldg(Tb + ((size_t)j * Nx + r) * 2 + p);
-      } else {
-        const int r = idx % ROWS, ky = idx / ROWS;
-        tmp[n] = __ldg(Tb + (size_t)ky * Nx + r);
+      int r, k;
+      pair_of(idx, r, k);
+      if (idx < ROWS * (M / 2)) {
+        xa[n] = __ldg(tptr(k, r));
+        xb[n] = __ldg(tptr(k == 0 ? M / 2 : M - k, r));
       }
     }
 #pragma unroll
     for (int n = 0; n < NG; ++n) {
       const int idx = tid + n * NT;
-      if (PAIRED) {
-        const int p = idx & 1, r = (idx >> 1) % ROWS, j = idx / (2 * ROWS);
-        smem[r * RS + PAD(2 * j + p)] = tmp[n];
-      } else {
-        const int r = idx % ROWS, ky = idx / ROWS;
-        smem[r * RS + PAD(ky)] = tmp[n];
+      int r, k;
+      pair_of(idx, r, k);
+      if (idx < ROWS * (M / 2)) {
+        float2* sr = smem + r * RS;
+        if (k == 0) {
+          sr[0] = make_float2(xa[n].x + xa[n].y, xa[n].x - xa[n].y);
+          sr[PAD(M / 2)] = make_float2(2.f * xb[n].x, -2.f * xb[n].y);
+        } else {
+          const float2 xk = xa[n], xm = xb[n];
+          const float2 A = make_float2(xk.x + xm.x, xk.y - xm.y);
+          const float2 B = make_float2(xk.x - xm.x, xk.y + xm.y);
+          const float2 WB = cmulc(B, __ldg(rtw + k));
+          sr[PAD(k)] = make_float2(A.x + WB.x, A.y + WB.y);
+          sr[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
+        }
       }
     }
   }
   __syncthreads();
-  for (int k = t; k <= M / 2; k += G) {
-    if (k == 0) {
-      const float2 x = s[0];
-      s[0] = make_float2(x.x + x.y, x.x - x.y);
-    } else if (k == M / 2) {
-      const float2 x = s[PAD(k)];
-      s[PAD(k)] = make_float2(2.f * x.x, -2.f * x.y);
-    } else {
-      const float2 xk = s[PAD(k)], xm = s[PAD(M - k)];
-      const float2 A = make_float2(xk.x + xm.x, xk.y - xm.y);
-      const float2 B = make_float2(xk.x - xm.x, xk.y + xm.y);
-      const float2 WB = cmulc(B, __ldg(rtw + k));
-      s[PAD(k)] = make_float2(A.x + WB.x, A.y + WB.y);
-      s[PAD(M - k)] = make_float2(A.x - WB.x, -(A.y - WB.y));
-    }
-  }
   using LSYNC = std::conditional_t<(ROWS <= 15), SyncLine<G>, SyncCta>;
-  LSYNC::sync(row);
   float2 v[E];
   fft_load_regs<P>(v, t, s);
   FftRun<P, +1, LSYNC>::run(v, t, s, tw, row);
@@ -519,13 +525,35 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
       e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, false>);
   } else {
     if (split) return set_error_msg("internal: split x lines need 16384-point transforms");
+    bool bal = false;
+    if constexpr (LM == 13 && LEMAX == 5) bal = xlines_balanced(LM);
     if (paired) {
       if constexpr (LM == 12 || LM == 13) {  // the only lengths the plan selects the paired layout for
+        if constexpr (LM == 13 && LEMAX == 5) {
+          if (bal) {
+            e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, true, true>)
+                      : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, true, true>);
+            if (e) return e;
+            count_launch();
+            CFD_CUDA_OK(cudaGetLastError());
+            return 0;
+          }
+        }
         e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, true>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, true>);
       } else {
         return set_error_msg("internal: the paired layout is built for 4096/8192-point x lines only");
       }
     } else {
+      if constexpr (LM == 13 && LEMAX == 5) {
+        if (bal) {
+          e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, false, true>)
+                    : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, false, true>);
+          if (e) return e;
+          count_launch();
+          CFD_CUDA_OK(cudaGetLastError());
+          return 0;
+        }
+      }
       e = fastd ? go(xlines_kernel<LM, LINES, true, LEMAX, false, DB, false>) : go(xlines_kernel<LM, LINES, false, LEMAX, false, DB, false>);
     }
   }

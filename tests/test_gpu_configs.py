@@ -65,15 +65,22 @@ def multiscale_field(shape, seed, vmax):
 
 
 def test_k8192_step_matches_cpu_oracle(cfd):
-  """BASELINE headline size: one 8192^2 step with the K8192 physics (bench.py) against the
-  OpenMP-C + pocketfft port of the oracle (tests/test_oracle_c.py pins it to the golden vectors)."""
+  """BASELINE headline size: 8192^2 steps with the K8192 physics (bench.py) against the OpenMP-C +
+  pocketfft port of the oracle (tests/test_oracle_c.py pins it to the golden vectors).
+
+  The initial condition is made divergence free first, like every initial condition of the
+  reference (initial_conditions.py:112-121) and like bench.py's.  (On a field with O(1) divergence
+  a float32 solve at h = 7.7e-4 leaves eps * |q| / h ~ 1e-5 of rounding noise in the velocity --
+  the reference's own float32 run is that far from its float64 run; measured 2.7e-6 at 2048^2.)
+  `q` of a divergence-free flow is dt * pressure ~ 1e-4 and is itself dominated by the rounding of
+  div(u*): it is held to 3x the oracle's own sensitivity to a half-ulp perturbation of the input."""
   import cpu_baseline
   shape = (8192, 8192)
   dom = ((0.0, TWO_PI), (0.0, TWO_PI))
   grid = cfd.grids.Grid(shape, domain=dom)
   nu, vmax = 1e-4, 7.0
   dt = cfd.equations.stable_time_step(vmax, 0.5, nu, grid)
-  u0, v0 = multiscale_field(shape, 0, vmax)
+  u0, v0 = to_np(cfd.pressure.projection(wrap(cfd, grid, multiscale_field(shape, 0, vmax))))
   forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
                                       cfd.forcings.linear_forcing(grid, -0.1))
   step = cfd.equations.semi_implicit_navier_stokes(1.0, nu, dt, grid, forcing=forcing)
@@ -82,16 +89,24 @@ def test_k8192_step_matches_cpu_oracle(cfd):
   q = np.asarray(q)
   cs = cpu_baseline.CpuStep(shape, grid.step, dt, 1.0, nu,
                             cfd_oracle.kolmogorov_field(shape, dom, 1.0, 4), -0.1)
-  wu, wv = cs.step(u0, v0)
-  assert gu.rel_l2(got[0], wu) < TOL
-  assert gu.rel_l2(got[1], wv) < TOL
-  assert gu.rel_l2(q, cs.q) < TOL
+  wu, wv = (a.copy() for a in cs.step(u0, v0))
+  wq = cs.q.copy()
+  eu, ev, eq = gu.rel_l2(got[0], wu), gu.rel_l2(got[1], wv), gu.rel_l2(q, wq)
+  # conditioning of q: the oracle's q for an input perturbed by half an ulp
+  rs = np.random.RandomState(1)
+  pert = [(a * (1 + np.float32(6e-8) * rs.choice(np.float32([-1, 1]), size=shape))).astype(np.float32)
+          for a in (u0, v0)]
+  cs.step(pert[0], pert[1])
+  floor_q = gu.rel_l2(cs.q, wq)
+  del pert
+  print(f'\nK8192 one step: rel-L2 u {eu:.2e} v {ev:.2e} q {eq:.2e} (q floor {floor_q:.2e})')
+  assert eu < TOL and ev < TOL
+  assert eq < max(TOL, 3 * floor_q)
   # the chained (lazy-projection) path must agree with single steps at this size too
   two = to_np(cfd.funcutils.repeated(step, 2)(wrap(cfd, grid, [u0, v0])))
   wu2, wv2 = cs.step(wu, wv)
   assert gu.rel_l2(two[0], wu2) < TOL
   assert gu.rel_l2(two[1], wv2) < TOL
-  del cs
   # divergence-free residual: rounding noise / h (h = 7.7e-4), held to the oracle's own residual
   ref_div = np.abs(cfd_oracle.divergence([wu2, wv2], grid.step)).max()
   assert np.abs(cfd_oracle.divergence(two, grid.step)).max() < max(2e-3, 3 * ref_div)
