@@ -87,10 +87,24 @@ int cfd_device_count(void);           /* 0 when no CUDA device is usable */
 /* ---- plan: grid metadata + eigenvalue / twiddle tables + workspace ------------------------
  * Replaces the trace-time work of pressure.solve_fast_diag (pressure.py:115-157),
  * array_utils.laplacian_matrix (array_utils.py:168-173; built analytically here) and
- * fast_diagonalization.pseudoinverse (fast_diagonalization.py:228-266).
- * shape[j] must be a power of two >= 16 (>= 32 on the last axis).  `step[j]` = grid.step[j]. */
+ * fast_diagonalization.pseudoinverse (fast_diagonalization.py:228-266).  `step[j]` = grid.step[j].
+ *
+ * Implementation of the fast-diagonalisation transform (fast_diagonalization.py:90-125):
+ *   CFD_IMPL_RFFT    shared-memory line FFTs ('rfft'; 'fft' computes the same transform for real
+ *                    input and maps here too); needs every axis a power of two >= 16 (>= 32 on the
+ *                    last axis)
+ *   CFD_IMPL_MATMUL  eigenvector products along each axis on the FP64 tensor cores ('matmul',
+ *                    fast_diagonalization.py:129-165); any shape with axes of up to 4096 cells
+ *   CFD_IMPL_AUTO    rfft when the shape allows it, else matmul -- the reference's own fallback
+ *                    for odd last axes (fast_diagonalization.py:107-108), extended to every shape
+ *                    the radix-2 line kernels do not take
+ * cfd_plan_create == cfd_plan_create_impl(..., CFD_IMPL_AUTO). */
+enum cfd_implementation { CFD_IMPL_AUTO = 0, CFD_IMPL_RFFT = 1, CFD_IMPL_MATMUL = 2 };
 int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double* step,
                     int batch, int device);
+int cfd_plan_create_impl(cfd_plan** out, int ndim, const int64_t* shape, const double* step,
+                         int batch, int device, int implementation);
+int cfd_plan_implementation(const cfd_plan* plan); /* CFD_IMPL_RFFT or CFD_IMPL_MATMUL */
 void cfd_plan_destroy(cfd_plan* plan);
 size_t cfd_plan_workspace_bytes(const cfd_plan* plan);
 
@@ -115,6 +129,27 @@ int cfd_explicit_terms(cfd_plan* plan, cfd_stream stream, const float* const* v_
  * v_out may alias v_in. */
 int cfd_project(cfd_plan* plan, cfd_stream stream, const float* const* v_in,
                 float* const* v_out, float* q_out);
+
+/* fast_diagonalization.transform (fast_diagonalization.py:28-126) on one real field of the plan's
+ * grid (batched like everything else):  out = X diag X^-1 in.
+ *   rfft plans:   circulant symmetric operators.  diag_lines = func(eigenvalue sums) in rfftn layout
+ *                 (N0, [N1,] N_last/2 + 1), TRANSPOSED to line layout (N_last/2 + 1, [N1,] N0), device
+ *                 float32 (the reference narrows `diagonals` to complex64, fast_diagonalization.py:214).
+ *                 Used by diffusion.solve_fast_diag (diffusion.py:166-212) and by the spectral filter of
+ *                 initial_conditions.filtered_velocity_field (filter_utils.py:32-42).  in may alias out.
+ *   matmul plans: any hermitian operators.  eigvecs[j] / eigvecs_t[j] = device float64 N_j x N_j
+ *                 row-major eigenvector matrix of axis j (columns = eigenvectors, np.linalg.eigh) and its
+ *                 transpose; diag = device float64 table of the grid shape in that eigenbasis. */
+int cfd_transform_rfft(cfd_plan* plan, cfd_stream stream, const float* in, float* out,
+                       const float* diag_lines);
+int cfd_transform_matmul(cfd_plan* plan, cfd_stream stream, const float* in, float* out,
+                         const double* const* eigvecs, const double* const* eigvecs_t,
+                         const double* diag);
+
+/* out = numer * x / denom per component, in float32 in that order (the normalisation step of
+ * initial_conditions.filtered_velocity_field, initial_conditions.py:118-121).  out may alias x. */
+int cfd_scale(cfd_plan* plan, cfd_stream stream, const float* const* x, double numer, double denom,
+              float* const* out);
 
 /* out = x + sum_k coef[k] * y[k]  per component (the stage combinations of navier_stokes_rk,
  * time_stepping.py:96-101).  y is an array of nterms pointers-to-component-arrays. */

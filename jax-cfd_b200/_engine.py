@@ -20,14 +20,16 @@ _plans_lock = threading.Lock()
 class Plan:
   """Owns one cfd_plan (tables + workspace) for a (grid, batch, device)."""
 
-  def __init__(self, grid: grids.Grid, batch: int, device: int = 0):
+  def __init__(self, grid: grids.Grid, batch: int, device: int = 0, implementation: int = _lib.IMPL_AUTO):
     _lib.require_device()
     self.grid, self.batch, self.device = grid, batch, device
     shape = (ctypes.c_int64 * grid.ndim)(*grid.shape)
     step = (ctypes.c_double * grid.ndim)(*grid.step)
     handle = ctypes.c_void_p()
-    check(lib().cfd_plan_create(ctypes.byref(handle), grid.ndim, shape, step, batch, device))
+    check(lib().cfd_plan_create_impl(ctypes.byref(handle), grid.ndim, shape, step, batch, device,
+                                     implementation))
     self.handle = handle
+    self.implementation = lib().cfd_plan_implementation(handle)  # IMPL_RFFT or IMPL_MATMUL
 
   def __del__(self):
     h = getattr(self, 'handle', None)
@@ -39,26 +41,49 @@ class Plan:
     self.handle = None
 
 
-def get_plan(grid: grids.Grid, batch: int = 1, device: Optional[int] = None, stream=None) -> Plan:
+def get_plan(grid: grids.Grid, batch: int = 1, device: Optional[int] = None, stream=None,
+             implementation: int = _lib.IMPL_AUTO) -> Plan:
   """The plan (tables + ONE workspace) for this grid on `device` (default: the current device).
   A plan's workspace may only be used by work ordered on one stream, so plans are cached per
   stream: callers that enqueue on different streams get independent workspaces."""
   if device is None:
     device = _lib.current_device()
-  key = (grid.shape, grid.step, batch, device, stream)
+  key = (grid.shape, grid.step, batch, device, stream, implementation)
   with _plans_lock:
     p = _plans.get(key)
     if p is None:
-      p = _plans[key] = Plan(grid, batch, device)
+      p = _plans[key] = Plan(grid, batch, device, implementation)
     return p
 
 
-def plan_for(grid: grids.Grid, batch: int, arrays, stream=None) -> Plan:
+def plan_for(grid: grids.Grid, batch: int, arrays, stream=None, implementation: int = _lib.IMPL_AUTO) -> Plan:
   """Plan on the device that owns `arrays` (the first device array; host arrays -> current)."""
   for a in arrays:
     if _lib.is_device_array(a):
-      return get_plan(grid, batch, _lib.device_of(a), stream)
-  return get_plan(grid, batch, None, stream)
+      return get_plan(grid, batch, _lib.device_of(a), stream, implementation)
+  return get_plan(grid, batch, None, stream, implementation)
+
+
+def fft_shape_ok(shape) -> bool:
+  """The shapes the radix-2 line-FFT kernels take (cfd_plan_create_impl, CFD_IMPL_RFFT)."""
+  shape = tuple(shape)
+  pow2 = all(n >= 16 and n & (n - 1) == 0 for n in shape)
+  mid_ok = all(n <= 1 << 14 for n in shape[1:-1])
+  return (pow2 and shape[-1] >= 32 and shape[-1] <= 1 << 15 and mid_ok and
+          shape[0] <= (1 << 15 if len(shape) == 2 else 1 << 14))
+
+
+def check_implementation(grid: grids.Grid, implementation) -> int:
+  """Build-time validation of (grid, implementation): the errors cfd_plan_create_impl would raise at
+  the first call, raised when the step function is built."""
+  code = _lib.implementation_code(implementation)
+  if code == _lib.IMPL_RFFT and not fft_shape_ok(grid.shape):
+    raise NotImplementedError(
+        f'implementation={implementation!r} needs every axis a power of two >= 16 (>= 32 on the last '
+        f'axis); got {grid.shape}.  Use implementation=None or "matmul".')
+  if (code == _lib.IMPL_MATMUL or not fft_shape_ok(grid.shape)) and any(n > 4096 for n in grid.shape):
+    raise NotImplementedError('the matmul implementation takes axes of up to 4096 cells')
+  return code
 
 
 def clear_plans():
@@ -271,9 +296,11 @@ class NativeStep:
   """step_fn of semi_implicit_navier_stokes with forward Euler (equations.py:120-151)."""
 
   def __init__(self, grid, dt, density, viscosity, forcing: Optional[ForcingFn],
-               convect_dt: Optional[float] = None):
+               convect_dt: Optional[float] = None, implementation=None):
     self.grid, self.dt, self.density, self.viscosity, self.forcing = grid, dt, density, viscosity, forcing
     self.convect_dt = convect_dt
+    self.implementation = implementation
+    self.impl_code = check_implementation(grid, implementation)
     self._params = None
     self._keep = None
     self.last_q = None
@@ -285,7 +312,7 @@ class NativeStep:
       return self
     base = self.dt if self.convect_dt is None else self.convect_dt
     return NativeStep(self.grid, time_step, self.density, self.viscosity, self.forcing,
-                      convect_dt=None if base == time_step else base)
+                      convect_dt=None if base == time_step else base, implementation=self.implementation)
 
   def params(self):
     if self._params is None:
@@ -302,7 +329,7 @@ class NativeStep:
     if nsteps == 0:
       return tuple(v)
     stream = _lib.stream_of(v[0].data) if on_dev else None
-    plan = plan_for(grid, batch, [u.data for u in v], stream)
+    plan = plan_for(grid, batch, [u.data for u in v], stream, self.impl_code)
     params = self.params()
     if not on_dev:
       ins = [np.ascontiguousarray(u.data, dtype=np.float32) for u in v]
@@ -351,16 +378,16 @@ def _from_device(datas, like_host: bool):
 class NativeExplicitTerms:
   """explicit_terms of navier_stokes_explicit_terms (equations.py:77-116) on the device."""
 
-  def __init__(self, grid, dt, density, viscosity, forcing):
+  def __init__(self, grid, dt, density, viscosity, forcing, implementation=None):
     self.grid = grid
-    self._step = NativeStep(grid, dt, density, viscosity, forcing)
+    self._step = NativeStep(grid, dt, density, viscosity, forcing, implementation=implementation)
 
   def __call__(self, v):
     grid, batch, lead, on_dev = validate_velocity(v, self.grid)
     ins = _to_device_tuple(v)
     outs = [_lib.empty_like(x) for x in ins]
     stream = _lib.stream_of(ins[0])
-    plan = plan_for(grid, batch, ins, stream)
+    plan = plan_for(grid, batch, ins, stream, self._step.impl_code)
     check(lib().cfd_explicit_terms(plan.handle, stream, _lib.ptr_array(ins), _lib.ptr_array(outs),
                                    ctypes.byref(self._step.params())))
     if not on_dev:
@@ -371,16 +398,21 @@ class NativeExplicitTerms:
 class NativeProjection:
   """pressure.projection with solve_fast_diag (pressure.py:181-198)."""
 
-  def __init__(self, grid=None):
+  def __init__(self, grid=None, implementation=None):
     self.grid = grid
+    self.implementation = implementation
+    self.impl_code = (_lib.implementation_code(implementation) if grid is None
+                      else check_implementation(grid, implementation))
 
   def __call__(self, v, return_q=False):
     grid, batch, lead, on_dev = validate_velocity(v, self.grid)
+    if self.grid is None:
+      check_implementation(grid, self.implementation)
     ins = _to_device_tuple(v)
     outs = [_lib.empty_like(x) for x in ins]
     q = _lib.empty_like(ins[0]) if return_q else None
     stream = _lib.stream_of(ins[0])
-    plan = plan_for(grid, batch, ins, stream)
+    plan = plan_for(grid, batch, ins, stream, self.impl_code)
     check(lib().cfd_project(plan.handle, stream, _lib.ptr_array(ins), _lib.ptr_array(outs),
                             None if q is None else _lib.device_ptr(q)))
     if not on_dev:
@@ -423,3 +455,85 @@ def diagnostics(v):
   check(lib().cfd_diagnostics(plan.handle, stream, _lib.ptr_array(x), ctypes.byref(d)))
   return dict(kinetic_energy=d.kinetic_energy, enstrophy=d.enstrophy, max_abs_div=d.max_abs_div,
               max_speed_sq=d.max_speed_sq)
+
+
+def scale(v, numer: float, denom: float):
+  """numer * u / denom per component on the device, float32, in that order
+  (initial_conditions.py:118-121)."""
+  grid, batch, lead, on_dev = validate_velocity(v)
+  x = _to_device_tuple(v)
+  outs = [_lib.empty_like(a) for a in x]
+  stream = _lib.stream_of(x[0])
+  plan = plan_for(grid, batch, x, stream)
+  check(lib().cfd_scale(plan.handle, stream, _lib.ptr_array(x), float(numer), float(denom), _lib.ptr_array(outs)))
+  if not on_dev:
+    check(lib().cfd_stream_sync(stream))
+  return rewrap(v, _from_device(outs, not on_dev))
+
+
+class NativeTransform:
+  """`fast_diagonalization.transform` on one real float32 field of a periodic grid: out = X diag X^-1 in.
+
+  rfft: `diag` = func(eigenvalue sums) in rfftn layout (N0, [N1,] N_last/2+1), real.
+  matmul: `eigvecs[j]` (N_j, N_j) float64 with eigenvectors in columns, `diag` of the grid shape."""
+
+  def __init__(self, grid: grids.Grid, diag: np.ndarray, eigvecs=None):
+    self.grid = grid
+    self.eigvecs = None if eigvecs is None else [np.ascontiguousarray(v, np.float64) for v in eigvecs]
+    if eigvecs is None:
+      nlast = grid.shape[-1] // 2 + 1
+      if tuple(diag.shape) != grid.shape[:-1] + (nlast,):
+        raise ValueError(f'diagonal shape {diag.shape} does not match the rfftn layout of {grid.shape}')
+      # line layout: (N_last/2+1, [N1,] N0) -- the layout the x-line kernels read
+      self.diag = np.ascontiguousarray(np.transpose(np.asarray(diag, np.float32)))
+      self.impl = _lib.IMPL_RFFT
+    else:
+      if tuple(diag.shape) != grid.shape:
+        raise ValueError(f'diagonal shape {diag.shape} does not match the grid shape {grid.shape}')
+      # the reference narrows `diagonals` to the data dtype (fast_diagonalization.py:143)
+      self.diag = np.ascontiguousarray(np.asarray(diag, np.float32).astype(np.float64))
+      self.impl = _lib.IMPL_MATMUL
+    self._dev = {}
+
+  def _tables(self, device):
+    t = self._dev.get(device)
+    if t is None:
+      prev = _lib.current_device()
+      check(lib().cfd_set_device(device))
+      try:
+        d = DeviceArray.from_numpy(self.diag)
+        vs = vts = None
+        if self.eigvecs is not None:
+          vs = [DeviceArray.from_numpy(v) for v in self.eigvecs]
+          vts = [DeviceArray.from_numpy(np.ascontiguousarray(v.T)) for v in self.eigvecs]
+      finally:
+        check(lib().cfd_set_device(prev))
+      t = self._dev[device] = (d, vs, vts)
+    return t
+
+  def __call__(self, rhs):
+    """rhs: array of shape (..., *grid.shape), float32, numpy or device.  Returns the same kind."""
+    on_dev = _lib.is_device_array(rhs)
+    shape = tuple(rhs.shape)
+    nd = self.grid.ndim
+    if shape[len(shape) - nd:] != self.grid.shape:
+      raise ValueError(f'rhs.shape={shape} does not match shape={self.grid.shape}')
+    if np.dtype(str(rhs.dtype).replace('torch.', '')) != np.float32:
+      raise ValueError(f'rhs.dtype={rhs.dtype} does not match dtype=float32')
+    if on_dev and not _lib.is_c_contiguous(rhs):
+      raise ValueError('device arrays must be C-contiguous')
+    batch = int(np.prod(shape[:len(shape) - nd], dtype=np.int64)) if len(shape) > nd else 1
+    x = rhs if on_dev else DeviceArray.from_numpy(np.ascontiguousarray(rhs, np.float32))
+    out = _lib.empty_like(x)
+    stream = _lib.stream_of(x)
+    plan = plan_for(self.grid, batch, [x], stream, self.impl)
+    d, vs, vts = self._tables(plan.device)
+    if self.impl == _lib.IMPL_RFFT:
+      check(lib().cfd_transform_rfft(plan.handle, stream, _lib.device_ptr(x), _lib.device_ptr(out), d.ptr))
+    else:
+      check(lib().cfd_transform_matmul(plan.handle, stream, _lib.device_ptr(x), _lib.device_ptr(out),
+                                       _lib.ptr_array(vs), _lib.ptr_array(vts), d.ptr))
+    if not on_dev:
+      check(lib().cfd_stream_sync(stream))
+      return out.numpy()
+    return out

@@ -15,6 +15,16 @@ import numpy as np
 MAX_DIM = 3
 MAX_TERMS = 4
 FORCE_SEPARABLE, FORCE_FIELD, FORCE_LINEAR, FORCE_SMAGORINSKY = 1, 2, 3, 4
+IMPL_AUTO, IMPL_RFFT, IMPL_MATMUL = 0, 1, 2
+# fast_diagonalization.transform's `implementation` strings (fast_diagonalization.py:90-125); 'fft'
+# and 'rfft' compute the same transform of real data and share the line-FFT kernels
+IMPLEMENTATIONS = {None: IMPL_AUTO, 'rfft': IMPL_RFFT, 'fft': IMPL_RFFT, 'matmul': IMPL_MATMUL}
+
+
+def implementation_code(implementation) -> int:
+  if implementation not in IMPLEMENTATIONS:
+    raise ValueError(f'invalid implementation: {implementation}')
+  return IMPLEMENTATIONS[implementation]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('CFD_B200_LIB', os.path.join(_HERE, 'lib', 'libcfd_b200.so'))
@@ -62,6 +72,10 @@ _SIGS = {
     'cfd_plan_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double),
                                        ctypes.c_int, ctypes.c_int]),
+    'cfd_plan_create_impl': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double),
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    'cfd_plan_implementation': (ctypes.c_int, [ctypes.c_void_p]),
     'cfd_plan_destroy': (None, [ctypes.c_void_p]),
     'cfd_plan_workspace_bytes': (ctypes.c_size_t, [ctypes.c_void_p]),
     'cfd_step': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
@@ -75,6 +89,13 @@ _SIGS = {
                                           ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(Params)]),
     'cfd_project': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                    ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    'cfd_transform_rfft': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]),
+    'cfd_transform_matmul': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                            ctypes.c_void_p]),
+    'cfd_scale': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                 ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p)]),
     'cfd_axpy': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                 ctypes.c_int, ctypes.POINTER(ctypes.POINTER(ctypes.c_void_p)),
                                 ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_void_p)]),

@@ -382,6 +382,7 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
   int pattern = 0, nt = 0;
   for (int t = 0; t < c.n_terms; ++t) {
     const int kind = c.term_kind[t];
+    if (kind == CFD_FORCE_SMAGORINSKY) continue;  // added by smag_add2d_kernel (smagorinsky_2d.cu)
     int code = kind == CFD_FORCE_SEPARABLE ? 1 : kind == CFD_FORCE_FIELD ? 2 : kind == CFD_FORCE_LINEAR ? 3 : -1;
     if (code < 0 || nt >= 3) return set_error_msg("unsupported forcing term for the 2-D kernel");
     for (int q = 0; q < nt; ++q)

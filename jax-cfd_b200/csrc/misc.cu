@@ -12,9 +12,15 @@ struct AxpyArgs {
 
 // out = x + sum_k coef[k] * y[k]   (time_stepping.py:96-101: u0 + dt * sum(a_ij k_j))
 __global__ void axpy_kernel(const float* __restrict__ x, int nterms, AxpyArgs a,
-                            float* __restrict__ out, size_t n4) {
+                            float* __restrict__ out, size_t n4, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (i < n - 4 * n4) {  // tail of a field whose size is not a multiple of 4
+    const size_t e = 4 * n4 + i;
+    float acc = 0.f;
+    for (int k = 0; k < nterms; ++k) acc = k == 0 ? a.coef[0] * a.y[0][e] : acc + a.coef[k] * a.y[k][e];
+    out[e] = x[e] + acc;
+  }
   for (; i < n4; i += stride) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = 0; k < nterms; ++k) {
@@ -32,6 +38,15 @@ __global__ void axpy_kernel(const float* __restrict__ x, int nterms, AxpyArgs a,
     const float4 xv = ldg4(x + 4 * i);
     stg4(out + 4 * i, make_float4(xv.x + acc.x, xv.y + acc.y, xv.z + acc.z, xv.w + acc.w));
   }
+}
+
+// out = numer * x / denom, evaluated in that order in float32 (initial_conditions.py:118-121:
+// `maximum_velocity * u / max_speed`)
+__global__ void scale_kernel(const float* __restrict__ x, float numer, float denom, float* __restrict__ out,
+                             size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __fdiv_rn(numer * x[i], denom);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -106,7 +121,17 @@ int launch_axpy(cudaStream_t st, const float* x, int nterms, const float* const*
   const size_t n4 = n / 4;
   const int threads = 256;
   const int blocks = (int)((n4 + threads - 1) / threads < 148 * 16 ? (n4 + threads - 1) / threads : 148 * 16);
-  axpy_kernel<<<blocks, threads, 0, st>>>(x, nterms, a, out, n4);
+  axpy_kernel<<<blocks > 0 ? blocks : 1, threads, 0, st>>>(x, nterms, a, out, n4, n);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_scale(cudaStream_t st, const float* x, float numer, float denom, float* out, size_t n) {
+  const int threads = 256;
+  size_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  scale_kernel<<<(int)blocks, threads, 0, st>>>(x, numer, denom, out, n);
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;

@@ -31,7 +31,7 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig, const SideStreams* side, int paired);
+                        const float2* wbig, const SideStreams* side, int paired, const float* dtab);
 int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
                       const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
                       float inv_hx, float inv_hy);
@@ -160,7 +160,7 @@ int xpass_staged(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int lnloc)
     prof_mark(p, st, "xwait_in");
     if (int e = launch_xlines_peers(st, p->lm_x, tab, lnloc, gl0 + lb, chunk, My, p->tw_x, p->lam[0],
                                     p->lam[1], p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
-                                    p->xscratch, p->wbig, nullptr, p->t_paired))
+                                    p->xscratch, p->wbig, nullptr, p->t_paired, nullptr))
       return e;
     CFD_CUDA_OK(cudaEventRecord(p->ev_comp[c], st));
     prof_mark(p, st, "xchunk");
@@ -296,9 +296,12 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
   cudaStream_t st = (cudaStream_t)stream;
   StepConsts c;
   if (int e = make_consts(p, params, &c)) return e;
-  for (int t = 0; t < c.n_terms; ++t)
+  for (int t = 0; t < c.n_terms; ++t) {
     if (c.term_kind[t] == CFD_FORCE_FIELD && p->world > 1)
       return set_error_msg("field forcing is not supported on slab-decomposed grids");
+    if (c.term_kind[t] == CFD_FORCE_SMAGORINSKY)
+      return set_error_msg("the Smagorinsky closure is not supported on slab-decomposed 2-D grids");
+  }
   const int nloc = (int)p->shape[0], Ny = (int)p->shape[1], My = Ny / 2;
   const SharedLayout L = shared_layout((size_t)nloc, (size_t)Ny);
   const int prev = (p->rank + p->world - 1) % p->world, next = (p->rank + 1) % p->world;
@@ -339,7 +342,7 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
     } else if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
                                            lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1],
                                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
-                                           p->xscratch, p->wbig, &p->side, p->t_paired)) {
+                                           p->xscratch, p->wbig, &p->side, p->t_paired, nullptr)) {
       return e;
     }
     prof_mark(p, st, "xlines_peers");

@@ -29,13 +29,24 @@ int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int 
 int launch_xlines(cudaStream_t, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
                   int fastd, double cutoff, float norm, float2* scratch, const float2* wbig,
-                  const SideStreams* side, int paired);
+                  const SideStreams* side, int paired, const float* dtab);
 int launch_divergence_2d(cudaStream_t, const float* u, const float* v, float* rhs, int batch,
                          int Nx, int Ny, float inv_hx, float inv_hy);
 int launch_axpy(cudaStream_t, const float* x, int nterms, const float* const* y, const float* coef,
                 float* out, size_t n);
 int launch_diag_2d(cudaStream_t, const float* u, const float* v, int batch, int Nx, int Ny,
                    float inv_hx, float inv_hy, double* out4);
+int launch_scale(cudaStream_t, const float* x, float numer, float denom, float* out, size_t n);
+int launch_explicit_2d_generic(cudaStream_t, const float* u, const float* v, float* us, float* vs, int batch,
+                               int N0, int N1, const StepConsts& c, int dvdt_mode);
+void periodic_laplacian_eigenbasis(int N, double h, std::vector<double>* V, std::vector<double>* lam);
+int matmul_transform(cudaStream_t st, int ndim, const int64_t* shape, int batch, const float* in, float* out,
+                     const double* const* V, const double* const* Vt, const double* diag, double* w1,
+                     double* w2);
+int launch_smag_nut_2d(cudaStream_t, const float* u, const float* v, float* nut, int batch, int N0,
+                       int N1, const StepConsts& c);
+int launch_smag_add_2d(cudaStream_t, const float* u, const float* v, const float* nut, float* us,
+                       float* vs, int batch, int N0, int N1, const StepConsts& c, int dvdt_mode);
 
 int launch_rfft_rows3(cudaStream_t, int lm, const float* rhs, float2* T, int batch, int NR,
                       const float2* tw, const float2* rtw);
@@ -47,7 +58,7 @@ int launch_lines_gather(cudaStream_t, int lm, const float2* B, float2* A, int pl
                         const float2* tw);
 int launch_xlines3(cudaStream_t, int lm, float2* T, size_t nlines, int N1, int NZP, const float2* tw,
                    const double* const* lam, const float* const* lamf, int fastd, double cutoff,
-                   float norm);
+                   float norm, const float* dtab);
 int launch_divergence_3d(cudaStream_t, const float* u, const float* v, const float* w, float* rhs,
                          int batch, int N0, int N1, int N2, float ihx, float ihy, float ihz);
 int launch_correct_3d(cudaStream_t, const float* us, const float* vs, const float* ws, const float* q,
@@ -126,6 +137,8 @@ void prof_mark(cfd_plan* p, cudaStream_t st, const char* name) {
 int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
   memset(c, 0, sizeof *c);
   const int d = p->ndim;
+  for (int j = 0; j < d; ++j)  // periodic stencils of reach 2 (transform-only plans may be smaller)
+    if (p->shape[j] < 2) return set_error_msg("the time step needs at least 2 cells along every axis");
   c->dt = (float)prm->dt;
   float lap_sum = 0.f;
   // the dt of the Lax-Wendroff Courant number (equations.py:127-128 closes `convect` over the
@@ -153,8 +166,6 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c) {
     const int k = prm->term_kind[t];
     if (k < CFD_FORCE_SEPARABLE || k > CFD_FORCE_SMAGORINSKY)
       return set_error_msg("cfd_params.term_kind: unknown forcing kind");
-    if (k == CFD_FORCE_SMAGORINSKY && d == 2)
-      return set_error_msg("the Smagorinsky closure is implemented for 3-D grids only");
     c->term_kind[t] = k;
   }
   c->linear_coef = (float)prm->linear_coef;
@@ -266,20 +277,34 @@ struct DeviceGuard {
 };
 
 // q = pinv(rhs): rfft rows -> x lines (fwd * D * inv) -> irfft rows
-int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
+int solve_matmul(cfd_plan* p, cudaStream_t st, const float* rhs, float* q, const double* diag) {
+  if (int e = matmul_transform(st, p->ndim, p->shape, p->batch, rhs, q, p->mm_V, p->mm_Vt, diag, p->mm_w1,
+                               p->mm_w2))
+    return e;
+  prof_mark(p, st, "matmul_transform");
+  return 0;
+}
+
+// out = irfftn(D * rfftn(in)) with D the pseudo-inverse of the Laplacian (dtab == nullptr) or a
+// caller-supplied real diagonal in line layout (cfd_transform_rfft)
+int transform_2d(cfd_plan* p, cudaStream_t st, const float* in, float* q, const float* dtab) {
   const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
-  if (int e = launch_rfft_rows(st, p->lm_row, p->rhs, p->T, p->batch, Nx, p->tw_row, p->rtw, p->t_paired))
+  if (int e = launch_rfft_rows(st, p->lm_row, in, p->T, p->batch, Nx, p->tw_row, p->rtw, p->t_paired))
     return e;
   prof_mark(p, st, "rfft_rows");
   if (int e = launch_xlines(st, p->lm_x, p->T, p->batch, Ny / 2, p->tw_x, p->lam[0], p->lam[1],
                             p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch, p->wbig,
-                            &p->side, p->t_paired))
+                            &p->side, p->t_paired, dtab))
     return e;
   prof_mark(p, st, "xlines");
   if (int e = launch_irfft_rows(st, p->lm_row, p->T, q, p->batch, Nx, p->tw_row, p->rtw, p->t_paired))
     return e;
   prof_mark(p, st, "irfft_rows");
   return 0;
+}
+int solve_2d(cfd_plan* p, cudaStream_t st, float* q) {
+  if (p->impl == 1) return solve_matmul(p, st, p->rhs, q, p->mm_diag);
+  return transform_2d(p, st, p->rhs, q, nullptr);
 }
 
 int correct_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, const float* q,
@@ -292,16 +317,16 @@ int correct_2d(cfd_plan* p, cudaStream_t st, const float* us, const float* vs, c
 }
 
 // 3-D: q = pinv(rhs) in five sweeps (poisson_3d.cu)
-int solve_3d(cfd_plan* p, cudaStream_t st, float* q) {
+int transform_3d(cfd_plan* p, cudaStream_t st, const float* in, float* q, const float* dtab) {
   const int N0 = (int)p->shape[0], N1 = (int)p->shape[1], N2 = (int)p->shape[2];
   const int NZP = N2 / 2 + 1;
-  if (int e = launch_rfft_rows3(st, p->lm_row, p->rhs, p->T, p->batch, N0 * N1, p->tw_row, p->rtw)) return e;
+  if (int e = launch_rfft_rows3(st, p->lm_row, in, p->T, p->batch, N0 * N1, p->tw_row, p->rtw)) return e;
   prof_mark(p, st, "rfft_z");
   if (int e = launch_lines_scatter(st, p->lm_y, p->T, p->T2, p->batch * NZP, N0, p->tw_y)) return e;
   prof_mark(p, st, "fft_y");
   const float norm = (float)(1.0 / (2.0 * (double)p->cells));
   if (int e = launch_xlines3(st, p->lm_x, p->T2, (size_t)p->batch * NZP * N1, N1, NZP, p->tw_x, p->lam,
-                             p->lamf, p->fastd, p->cutoff, norm))
+                             p->lamf, p->fastd, p->cutoff, norm, dtab))
     return e;
   prof_mark(p, st, "xlines3");
   if (int e = launch_lines_gather(st, p->lm_y, p->T2, p->T, p->batch * NZP, N0, p->tw_y)) return e;
@@ -309,6 +334,10 @@ int solve_3d(cfd_plan* p, cudaStream_t st, float* q) {
   if (int e = launch_irfft_rows3(st, p->lm_row, p->T, q, p->batch, N0 * N1, p->tw_row, p->rtw)) return e;
   prof_mark(p, st, "irfft_z");
   return 0;
+}
+int solve_3d(cfd_plan* p, cudaStream_t st, float* q) {
+  if (p->impl == 1) return solve_matmul(p, st, p->rhs, q, p->mm_diag);
+  return transform_3d(p, st, p->rhs, q, nullptr);
 }
 
 // Smagorinsky workspace: nu_t always; the six strain fields when the marching kernel (and with it
@@ -359,6 +388,51 @@ int step_3d(cfd_plan* p, cudaStream_t st, const float* const* v_in, float* const
   return 0;
 }
 
+// the warp-marching stencil kernel (explicit_2d.cu) and the vectorised elementwise kernels take
+// rows that are a multiple of 4 columns long and at least 3 rows
+bool tuned_2d(const cfd_plan* p) { return p->shape[1] % 4 == 0 && p->shape[0] >= 3; }
+// chained steps with lazy projection: the tuned 2-D kernels with the line-FFT solve
+bool lazy_capable(const cfd_plan* p) { return p->ndim == 2 && p->impl == 0 && tuned_2d(p); }
+
+bool has_smag(const StepConsts& c) {
+  for (int t = 0; t < c.n_terms; ++t)
+    if (c.term_kind[t] == CFD_FORCE_SMAGORINSKY) return true;
+  return false;
+}
+
+// 2-D explicit terms: u* (or dv/dt) and, when `rhs` is given, div(u*).  With the Smagorinsky closure
+// (subgrid_models.py:188-213: the last forcing term, evaluated from the projected input) the
+// stencil kernel leaves the divergence to a separate sweep after the closure has been added.
+int explicit_2d_full(cfd_plan* p, cudaStream_t st, const float* u, const float* v, float* us, float* vs,
+                     float* rhs, const StepConsts& c, int dvdt_mode) {
+  const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
+  const bool tuned = tuned_2d(p);  // else: one-thread-per-cell kernels (generic.cu)
+  if (tuned && !has_smag(c)) {
+    if (int e = launch_explicit_2d(st, u, v, nullptr, us, vs, rhs, p->batch, Nx, Ny, c, dvdt_mode)) return e;
+    prof_mark(p, st, "explicit_2d");
+    return 0;
+  }
+  if (tuned) {
+    if (int e = launch_explicit_2d(st, u, v, nullptr, us, vs, nullptr, p->batch, Nx, Ny, c, dvdt_mode)) return e;
+  } else if (int e = launch_explicit_2d_generic(st, u, v, us, vs, p->batch, Nx, Ny, c, dvdt_mode)) {
+    return e;
+  }
+  prof_mark(p, st, "explicit_2d");
+  if (has_smag(c)) {
+    const size_t fbytes = (size_t)p->batch * p->cells * sizeof(float);
+    if (!p->nut) CFD_CUDA_OK(cudaMalloc((void**)&p->nut, fbytes));
+    if (int e = launch_smag_nut_2d(st, u, v, p->nut, p->batch, Nx, Ny, c)) return e;
+    prof_mark(p, st, "smag_nut_2d");
+    if (int e = launch_smag_add_2d(st, u, v, p->nut, us, vs, p->batch, Nx, Ny, c, dvdt_mode)) return e;
+    prof_mark(p, st, "smag_add_2d");
+  }
+  if (rhs) {
+    if (int e = launch_divergence_2d(st, us, vs, rhs, p->batch, Nx, Ny, c.inv_h[0], c.inv_h[1])) return e;
+    prof_mark(p, st, "divergence_2d");
+  }
+  return 0;
+}
+
 int ensure_lazy_buffers(cfd_plan* p) {
   const size_t fbytes = (size_t)p->batch * p->cells * sizeof(float);
   for (int a = 0; a < p->ndim; ++a)
@@ -383,37 +457,25 @@ int cfd_device_count(void) {
 }
 uint64_t cfd_launch_count(void) { return g_launches.load(); }
 
-int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double* step, int batch,
-                    int device) {
-  if (out == nullptr || shape == nullptr || step == nullptr) return set_error_msg("null argument");
-  *out = nullptr;
-  if (ndim != 2 && ndim != 3) return set_error_msg("cfd_plan_create: ndim must be 2 or 3");
-  if (batch < 1) return set_error_msg("batch must be >= 1");
-  for (int j = 0; j < ndim; ++j) {
-    if (!is_pow2(shape[j]) || shape[j] < 16)
-      return set_error_msg("every grid axis must be a power of two >= 16");
-    if (!(step[j] > 0)) return set_error_msg("grid step must be positive");
-  }
-  if (shape[ndim - 1] < 32) return set_error_msg("last grid axis must be >= 32");
+// Can the radix-2 line-FFT kernels take this grid?  (every axis a power of two within the lengths
+// the kernels are built for)
+static const char* fft_shape_problem(int ndim, const int64_t* shape) {
+  for (int j = 0; j < ndim; ++j)
+    if (!is_pow2(shape[j]) || shape[j] < 16) return "every grid axis must be a power of two >= 16";
+  if (shape[ndim - 1] < 32) return "last grid axis must be >= 32";
   if (shape[0] > (ndim == 2 ? (1 << 15) : (1 << 14)))
-    return set_error_msg("axis 0 longer than 32768 (2-D) / 16384 (3-D) is not supported");
-  if (shape[ndim - 1] > (1 << 15))
-    return set_error_msg("last axis longer than 32768 is not supported yet");
+    return "axis 0 longer than 32768 (2-D) / 16384 (3-D) is not supported";
+  if (shape[ndim - 1] > (1 << 15)) return "last axis longer than 32768 is not supported yet";
   for (int j = 1; j + 1 < ndim; ++j)
-    if (shape[j] > (1 << 14)) return set_error_msg("middle axis longer than 16384 is not supported yet");
-  if (device < 0 || cfd_device_count() <= device) return set_error_msg("no such CUDA device (no CPU fallback)");
-  DeviceGuard guard_;
-  CFD_CUDA_OK(cudaSetDevice(device));
-  cfd_plan* p = new cfd_plan();
-  p->ndim = ndim;
-  p->batch = batch;
-  p->device = device;
-  p->cells = 1;
-  for (int j = 0; j < ndim; ++j) {
-    p->shape[j] = shape[j];
-    p->step[j] = step[j];
-    p->cells *= (size_t)shape[j];
-  }
+    if (shape[j] > (1 << 14)) return "middle axis longer than 16384 is not supported yet";
+  return nullptr;
+}
+
+// tables of the line-FFT implementation
+static int create_fft_tables(cfd_plan* p) {
+  const int ndim = p->ndim, batch = p->batch;
+  const int64_t* shape = p->shape;
+  const double* step = p->step;
   const int Nx = (int)shape[0], Ny = (int)shape[ndim - 1];
   p->lm_row = ilog2(Ny / 2);
   p->lm_x = ilog2(Nx);
@@ -448,7 +510,6 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
     std::vector<float> lamf(lam.begin(), lam.end());
     err |= upload(&p->lamf[j], lamf);
   }
-  p->cutoff = 10.0 * 1.1920928955078125e-07;  // 10 * finfo(float32).eps, fast_diagonalization.py:257-258
   {
     // Every eigenvalue sum except the mean mode has |L| >= min_j |lam_j[1]| (all lam <= 0).  If
     // that exceeds the cutoff with a safety margin, only L(0,...,0) = 0 is discarded and the
@@ -462,18 +523,92 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   }
   p->norm = (float)(1.0 / (2.0 * (double)p->cells));
   const size_t fbytes = (size_t)batch * p->cells * sizeof(float);
-  for (int a = 0; a < ndim && !err; ++a) {
-    if (cudaMalloc((void**)&p->us[a], fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
-  }
-  if (!err && cudaMalloc((void**)&p->rhs, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
-  if (!err && cudaMalloc((void**)&p->qbuf, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   // spectrum: packed Ny/2 columns in 2-D, unpacked N2/2 + 1 planes (two buffers) in 3-D
   const size_t tbytes = ndim == 2 ? fbytes
                                   : (size_t)batch * (shape[2] / 2 + 1) * shape[0] * shape[1] * sizeof(float2);
   if (!err && cudaMalloc((void**)&p->T, tbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   if (!err && ndim == 3 && cudaMalloc((void**)&p->T2, tbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  p->workspace_bytes += tbytes * (ndim == 3 ? 2 : 1);
+  return err;
+}
+
+// tables of the matmul implementation: analytic real eigenbasis of the periodic Laplacian along
+// each axis (what np.linalg.eigh returns up to the choice of basis inside the two-dimensional
+// eigenspaces, which the product X f(L) X^T does not depend on) and the pseudo-inverse diagonal,
+// formed in float64 and narrowed to float32 like the reference's (fast_diagonalization.py:143-144)
+static int create_matmul_tables(cfd_plan* p) {
+  const int ndim = p->ndim;
+  std::vector<double> lam[CFD_MAX_DIM];
+  int err = 0;
+  for (int j = 0; j < ndim; ++j) {
+    const int n = (int)p->shape[j];
+    std::vector<double> V, Vt((size_t)n * n);
+    periodic_laplacian_eigenbasis(n, p->step[j], &V, &lam[j]);
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < n; ++c) Vt[(size_t)c * n + i] = V[(size_t)i * n + c];
+    err |= upload(&p->mm_V[j], V);
+    err |= upload(&p->mm_Vt[j], Vt);
+    p->workspace_bytes += 2 * V.size() * sizeof(double);
+  }
+  std::vector<double> diag(p->cells);
+  const int N1 = (int)p->shape[1], N2 = ndim == 3 ? (int)p->shape[2] : 1;
+  for (size_t idx = 0; idx < p->cells; ++idx) {
+    const int k2 = (int)(idx % N2), k1 = (int)((idx / N2) % N1), k0 = (int)(idx / ((size_t)N1 * N2));
+    const double L = lam[0][k0] + lam[1][k1] + (ndim == 3 ? lam[2][k2] : 0.0);
+    diag[idx] = fabs(L) > p->cutoff ? (double)(float)(1.0 / L) : 0.0;  // fast_diagonalization.py:259-262
+  }
+  err |= upload(&p->mm_diag, diag);
+  const size_t wbytes = (size_t)p->batch * p->cells * sizeof(double);
+  if (!err && cudaMalloc((void**)&p->mm_w1, wbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  if (!err && cudaMalloc((void**)&p->mm_w2, wbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  p->workspace_bytes += 2 * wbytes + p->cells * sizeof(double);
+  return err;
+}
+
+int cfd_plan_create_impl(cfd_plan** out, int ndim, const int64_t* shape, const double* step, int batch,
+                         int device, int implementation) {
+  if (out == nullptr || shape == nullptr || step == nullptr) return set_error_msg("null argument");
+  *out = nullptr;
+  if (ndim != 2 && ndim != 3) return set_error_msg("cfd_plan_create: ndim must be 2 or 3");
+  if (batch < 1) return set_error_msg("batch must be >= 1");
+  for (int j = 0; j < ndim; ++j) {
+    if (shape[j] < 1) return set_error_msg("every grid axis needs at least one cell");
+    if (!(step[j] > 0)) return set_error_msg("grid step must be positive");
+  }
+  if (implementation < CFD_IMPL_AUTO || implementation > CFD_IMPL_MATMUL)
+    return set_error_msg("unknown fast-diagonalisation implementation");
+  const char* fft_problem = fft_shape_problem(ndim, shape);
+  if (implementation == CFD_IMPL_RFFT && fft_problem) return set_error_msg(fft_problem);
+  const int impl = (implementation == CFD_IMPL_MATMUL || (implementation == CFD_IMPL_AUTO && fft_problem)) ? 1 : 0;
+  if (impl == 1) {
+    for (int j = 0; j < ndim; ++j)
+      if (shape[j] > 4096)
+        return set_error_msg("the matmul implementation is meant for small grids: axes up to 4096 cells");
+  }
+  if (device < 0 || cfd_device_count() <= device) return set_error_msg("no such CUDA device (no CPU fallback)");
+  DeviceGuard guard_;
+  CFD_CUDA_OK(cudaSetDevice(device));
+  cfd_plan* p = new cfd_plan();
+  p->ndim = ndim;
+  p->batch = batch;
+  p->device = device;
+  p->impl = impl;
+  p->cells = 1;
+  for (int j = 0; j < ndim; ++j) {
+    p->shape[j] = shape[j];
+    p->step[j] = step[j];
+    p->cells *= (size_t)shape[j];
+  }
+  p->cutoff = 10.0 * 1.1920928955078125e-07;  // 10 * finfo(float32).eps, fast_diagonalization.py:257-258
+  const size_t fbytes = (size_t)batch * p->cells * sizeof(float);
+  p->workspace_bytes = (size_t)(ndim + 2) * fbytes;
+  int err = impl == 1 ? create_matmul_tables(p) : create_fft_tables(p);
+  for (int a = 0; a < ndim && !err; ++a) {
+    if (cudaMalloc((void**)&p->us[a], fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  }
+  if (!err && cudaMalloc((void**)&p->rhs, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
+  if (!err && cudaMalloc((void**)&p->qbuf, fbytes) != cudaSuccess) err = set_error_msg("workspace allocation failed");
   if (!err && cudaMalloc((void**)&p->diag_dev, 8 * sizeof(double)) != cudaSuccess) err = set_error_msg("workspace allocation failed");
-  p->workspace_bytes = (size_t)(ndim + 3) * fbytes;
   if (err) {
     cudaGetLastError();
     cfd_plan_destroy(p);
@@ -482,6 +617,13 @@ int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double
   *out = p;
   return 0;
 }
+
+int cfd_plan_create(cfd_plan** out, int ndim, const int64_t* shape, const double* step, int batch,
+                    int device) {
+  return cfd_plan_create_impl(out, ndim, shape, step, batch, device, CFD_IMPL_AUTO);
+}
+
+int cfd_plan_implementation(const cfd_plan* p) { return p ? (p->impl == 1 ? CFD_IMPL_MATMUL : CFD_IMPL_RFFT) : 0; }
 
 void cfd_plan_destroy(cfd_plan* p) {
   if (p == nullptr) return;
@@ -514,6 +656,13 @@ void cfd_plan_destroy(cfd_plan* p) {
   }
   for (int c = 0; c < 8; ++c)
     if (p->ev_comp[c]) cudaEventDestroy(p->ev_comp[c]);
+  for (int j = 0; j < CFD_MAX_DIM; ++j) {
+    cudaFree(p->mm_V[j]);
+    cudaFree(p->mm_Vt[j]);
+  }
+  cudaFree(p->mm_diag);
+  cudaFree(p->mm_w1);
+  cudaFree(p->mm_w2);
   cudaFree(p->tw_y);
   cudaFree(p->T2);
   cudaFree(p->nut);
@@ -553,13 +702,9 @@ int cfd_step(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* co
   StepConsts c;
   if (int e = make_consts(p, params, &c)) return e;
   if (p->ndim == 3) return step_3d(p, st, v_in, v_out, q_out, c);
-  const int Nx = (int)p->shape[0], Ny = (int)p->shape[1];
   float* q = q_out ? q_out : p->qbuf;
   prof_mark(p, st, "begin");
-  if (int e = launch_explicit_2d(st, v_in[0], v_in[1], nullptr, p->us[0], p->us[1], p->rhs,
-                                 p->batch, Nx, Ny, c, 0))
-    return e;
-  prof_mark(p, st, "explicit_2d");
+  if (int e = explicit_2d_full(p, st, v_in[0], v_in[1], p->us[0], p->us[1], p->rhs, c, 0)) return e;
   if (int e = solve_2d(p, st, q)) return e;
   return correct_2d(p, st, p->us[0], p->us[1], q, v_out[0], v_out[1]);
 }
@@ -702,7 +847,14 @@ int cfd_repeated(cfd_plan* p, cfd_stream stream, float* const* v_a, float* const
   if (nsteps == 0) return 0;
   float* const* dst = (nsteps & 1) ? v_b : v_a;
   if (nsteps == 1) return cfd_step(p, stream, v_a, dst, nullptr, params);
-  if (p->ndim == 3) {  // 3-D: plain ping-pong (no lazy chain yet)
+  bool plain = !lazy_capable(p);  // 3-D, matmul plans, odd shapes: plain ping-pong
+  if (!plain) {
+    // the Smagorinsky closure is evaluated from the projected state: no lazy chain either
+    StepConsts c;
+    if (int e = make_consts(p, params, &c)) return e;
+    plain = has_smag(c);
+  }
+  if (plain) {
     for (int n = 0; n < nsteps; ++n) {
       float* const* src = (n & 1) ? v_b : v_a;
       float* const* out = (n & 1) ? v_a : v_b;
@@ -734,8 +886,7 @@ int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,
     return launch_explicit_3d((cudaStream_t)stream, v_in[0], v_in[1], v_in[2], nut, sfield, dvdt_out[0],
                               dvdt_out[1], dvdt_out[2], p->batch, N0, N1, N2, c, 1);
   }
-  return launch_explicit_2d((cudaStream_t)stream, v_in[0], v_in[1], nullptr, dvdt_out[0],
-                            dvdt_out[1], nullptr, p->batch, (int)p->shape[0], (int)p->shape[1], c, 1);
+  return explicit_2d_full(p, (cudaStream_t)stream, v_in[0], v_in[1], dvdt_out[0], dvdt_out[1], nullptr, c, 1);
 }
 
 int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out,
@@ -761,6 +912,37 @@ int cfd_project(cfd_plan* p, cfd_stream stream, const float* const* v_in, float*
   float* q = q_out ? q_out : p->qbuf;
   if (int e = solve_2d(p, st, q)) return e;
   return correct_2d(p, st, v_in[0], v_in[1], q, v_out[0], v_out[1]);
+}
+
+int cfd_transform_rfft(cfd_plan* p, cfd_stream stream, const float* in, float* out, const float* diag_lines) {
+  DeviceGuard guard_;
+  if (int e = check_plan(p)) return e;
+  if (!in || !out || !diag_lines) return set_error_msg("null argument");
+  if (p->impl != 0) return set_error_msg("cfd_transform_rfft needs a plan of the rfft implementation");
+  // the row kernels read `in` completely before `out` is written: aliasing is fine
+  return p->ndim == 3 ? transform_3d(p, (cudaStream_t)stream, in, out, diag_lines)
+                      : transform_2d(p, (cudaStream_t)stream, in, out, diag_lines);
+}
+
+int cfd_transform_matmul(cfd_plan* p, cfd_stream stream, const float* in, float* out,
+                         const double* const* eigvecs, const double* const* eigvecs_t, const double* diag) {
+  DeviceGuard guard_;
+  if (int e = check_plan(p)) return e;
+  if (!in || !out || !eigvecs || !eigvecs_t || !diag) return set_error_msg("null argument");
+  if (p->impl != 1) return set_error_msg("cfd_transform_matmul needs a plan of the matmul implementation");
+  return matmul_transform((cudaStream_t)stream, p->ndim, p->shape, p->batch, in, out, eigvecs, eigvecs_t, diag,
+                          p->mm_w1, p->mm_w2);
+}
+
+int cfd_scale(cfd_plan* p, cfd_stream stream, const float* const* x, double numer, double denom,
+              float* const* out) {
+  DeviceGuard guard_;
+  if (int e = check_plan(p)) return e;
+  if (!x || !out) return set_error_msg("null argument");
+  const size_t n = (size_t)p->batch * p->cells;
+  for (int a = 0; a < p->ndim; ++a)
+    if (int e = launch_scale((cudaStream_t)stream, x[a], (float)numer, (float)denom, out[a], n)) return e;
+  return 0;
 }
 
 int cfd_axpy(cfd_plan* p, cfd_stream stream, const float* const* x, int nterms,
@@ -864,8 +1046,14 @@ int cfd_step_profile(cfd_plan* p, cfd_stream stream, const float* const* v_in, f
     p->prof_events.clear();
     p->prof_names.clear();
     p->profiling = true;
-    int e = p->ndim == 3 ? cfd_step(p, stream, v_in, v_out, nullptr, params)
-                         : repeated_lazy(p, st, v_in, v_out, 3, params);
+    bool single = !lazy_capable(p);
+    if (!single) {
+      StepConsts c;
+      if (int e = make_consts(p, params, &c)) return e;
+      single = has_smag(c);
+    }
+    int e = single ? cfd_step(p, stream, v_in, v_out, nullptr, params)
+                   : repeated_lazy(p, st, v_in, v_out, 3, params);
     p->profiling = false;
     if (e) return e;
     CFD_CUDA_OK(cudaStreamSynchronize(st));

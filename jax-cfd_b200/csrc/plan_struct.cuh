@@ -36,6 +36,14 @@ struct cfd_plan {
   float* qbuf2 = nullptr;  // pong
   float2* T = nullptr;
   int t_paired = 0;  // 2-D spectrum layout: 1 = pairs of ky lines interleaved (poisson_2d.cu)
+  // implementation of the fast-diagonalisation transform (fast_diagonalization.py:101-108):
+  // 0 = line FFTs (rfft; every axis a power of two), 1 = matmul along each axis (any shape)
+  int impl = 0;
+  double* mm_V[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};   // eigenvectors, N_j x N_j row-major, f64
+  double* mm_Vt[CFD_MAX_DIM] = {nullptr, nullptr, nullptr};  // ... transposed
+  double* mm_diag = nullptr;                                 // pseudo-inverse diagonal in the eigenbasis
+  double* mm_w1 = nullptr;                                   // f64 workspaces, batch * cells each
+  double* mm_w2 = nullptr;
   // small grids: two chained lazy steps (us -> us2 -> us) captured once as a CUDA graph and
   // replayed, so that the 8 launches per pair cost one graph launch (plan.cu, repeated_lazy)
   cudaGraphExec_t pair_graph = nullptr;

@@ -113,8 +113,12 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
                                            const double* __restrict__ lamy,
                                            const float* __restrict__ lamxf,
                                            const float* __restrict__ lamyf, double cutoff,
-                                           float norm) {
+                                           float norm, const float* __restrict__ dtab) {
   constexpr int M = P::M, G = P::G, E = P::E;
+  // dtab != nullptr (only with FASTD == false): the diagonal comes from a caller-supplied table in
+  // line layout, dtab[ky][kx] with My + 1 lines of kmul * M entries (cfd_transform: any real
+  // func(eigenvalues), fast_diagonalization.py:28-126) instead of the pseudo-inverse
+  const float* trow = dtab ? dtab + (size_t)ky * (size_t)(kmul * M) : nullptr;
   if (!cta_has_packed || ky != 0) {
     if (FASTD) {
       // only the mean mode is below the cutoff (checked on the host in f64): float eigenvalues,
@@ -127,13 +131,22 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
         v[e].y *= d;
       }
     } else {
-      const double ly = __ldg(lamy + ky);
+      if (trow) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const double lam = __ldg(lamx + kmul * (t + G * e) + kadd) + ly;
-        const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
-        v[e].x *= d;
-        v[e].y *= d;
+        for (int e = 0; e < E; ++e) {
+          const float d = norm * __ldg(trow + kmul * (t + G * e) + kadd);
+          v[e].x *= d;
+          v[e].y *= d;
+        }
+      } else {
+        const double ly = __ldg(lamy + ky);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const double lam = __ldg(lamx + kmul * (t + G * e) + kadd) + ly;
+          const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
+          v[e].x *= d;
+          v[e].y *= d;
+        }
       }
     }
   }
@@ -151,10 +164,16 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
         const int d = t + G * e;
         const int dp = kadd ? (M - 1 - d) : ((M - d) & (M - 1));  // sub-index of N - kx
         const float2 cp = s[P::pad(dp)];
-        const double lx = __ldg(lamx + kmul * d + kadd);
-        const double l0 = lx + ly0, lM = lx + lyM;
-        const float d0 = (fabs(l0) > cutoff) ? 0.5f * norm * fast_rcp((float)l0) : 0.f;
-        const float dM = (fabs(lM) > cutoff) ? 0.5f * norm * fast_rcp((float)lM) : 0.f;
+        float d0, dM;
+        if (dtab) {
+          d0 = 0.5f * norm * __ldg(dtab + kmul * d + kadd);
+          dM = 0.5f * norm * __ldg(dtab + (size_t)My * (size_t)(kmul * M) + kmul * d + kadd);
+        } else {
+          const double lx = __ldg(lamx + kmul * d + kadd);
+          const double l0 = lx + ly0, lM = lx + lyM;
+          d0 = (fabs(l0) > cutoff) ? 0.5f * norm * fast_rcp((float)l0) : 0.f;
+          dM = (fabs(lM) > cutoff) ? 0.5f * norm * fast_rcp((float)lM) : 0.f;
+        }
         const float2 c = v[e];
         const float2 sum = make_float2(c.x + cp.x, c.y - cp.y);
         const float2 dif = make_float2(c.x - cp.x, c.y + cp.y);
@@ -184,7 +203,8 @@ __global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX, 4>::G,
 xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
-              const float* __restrict__ lamyf, double cutoff, float norm) {
+              const float* __restrict__ lamyf, double cutoff, float norm,
+              const float* __restrict__ dtab) {
   using P = FftPlan<LM, LEMAX, BAL ? 5 : 4, BAL>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, 16);
@@ -232,7 +252,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   // only the first line(s) of a CTA can be ky = 0 (split: both halves of that line)
   const bool cta_has_packed = (line0 % My) == 0;
   scale_line<P, FASTD>(v, t, s, ky, My, cta_has_packed, kmul, kadd, lamx, lamy, lamxf, lamyf, cutoff,
-                       norm);
+                       norm, FASTD ? nullptr : dtab);
   if (DB && cta_has_packed) __syncthreads();  // scale_line's reads of buffer 0 are done
   FftRun<P, +1, SyncCta, DB, (P::NP - 1) & 1, PRE>::run(v, t, s, tw, 0, ALT);
 #pragma unroll
@@ -503,7 +523,9 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
 template <int LM, int LEMAX>
 int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
                      size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
-                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired) {
+                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired,
+                     const float* dtab) {
+  if (dtab) fastd = 0;  // the table mode lives in the variant that tests every eigenvalue
   using P = FftPlan<LM, LEMAX, 4>;
   constexpr int LINES = (P::G >= 256) ? 1 : (256 / P::G > 16 ? 16 : 256 / P::G);
   // two exchange buffers (one barrier per pass) whenever both fit beside a second CTA's
@@ -513,7 +535,7 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
   auto go = [&](auto k) -> int {
     if (int e = set_smem(k, smem)) return e;
     k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx, lamy,
-                                                            lamxf, lamyf, cutoff, norm);
+                                                            lamxf, lamyf, cutoff, norm, dtab);
     return 0;
   };
   int e;
@@ -566,12 +588,13 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
 template <int LM>
 int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
                     size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
-                    const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired) {
+                    const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired,
+                    const float* dtab) {
   if (xlines_lemax(LM) == 5)
     return launch_xlines_le<LM, 5>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
-                                   lamyf, fastd, cutoff, norm, paired);
+                                   lamyf, fastd, cutoff, norm, paired, dtab);
   return launch_xlines_le<LM, 4>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
-                                 lamyf, fastd, cutoff, norm, paired);
+                                 lamyf, fastd, cutoff, norm, paired, dtab);
 }
 
 template <int LM>
@@ -630,7 +653,7 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig, const SideStreams* side, int paired) {
+                        const float2* wbig, const SideStreams* side, int paired, const float* dtab) {
   if (lm_x == 15) {
     if (!scratch || !wbig) return set_error_msg("internal: 32768-point lines need the split scratch");
     const int half = 1 << 14;
@@ -659,7 +682,7 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
       LinePeers local;
       for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = sc;
       if (int e = launch_xlines_t<14>(s, local, 14, lb, 2 * chunk, My, 1, tw, lamx, lamy, lamxf, lamyf,
-                                      fastd, cutoff, norm, 0))
+                                      fastd, cutoff, norm, 0, dtab))
         return e;
       if (paired)
         merge_pairs_kernel<<<pgrid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
@@ -678,20 +701,27 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
   }
   CFD_DISPATCH_LM(lm_x, 4, 14,
                   return launch_xlines_t<LM_>(st, peers, lnloc, line_begin, nlines, My, 0, tw, lamx, lamy,
-                                              lamxf, lamyf, fastd, cutoff, norm, paired));
+                                              lamxf, lamyf, fastd, cutoff, norm, paired, dtab));
   return 0;
 }
 int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const float2* tw,
                   const double* lamx, const double* lamy, const float* lamxf, const float* lamyf,
                   int fastd, double cutoff, float norm, float2* scratch, const float2* wbig,
-                  const SideStreams* side, int paired) {
+                  const SideStreams* side, int paired, const float* dtab) {
   LinePeers peers;
   for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
   return launch_xlines_peers(st, lm_x, peers, lm_x, 0, (size_t)batch * My, My, tw, lamx, lamy, lamxf,
-                             lamyf, fastd, cutoff, norm, scratch, wbig, side, paired);
+                             lamyf, fastd, cutoff, norm, scratch, wbig, side, paired, dtab);
 }
+int launch_divergence_generic(cudaStream_t st, const float* u, const float* v, const float* w, float* rhs,
+                              int batch, int N0, int N1, int N2, float ih0, float ih1, float ih2);
+int launch_correct_generic(cudaStream_t st, const float* us, const float* vs, const float* ws, const float* q,
+                           float* uo, float* vo, float* wo, int batch, int N0, int N1, int N2, float ih0,
+                           float ih1, float ih2);
+
 int launch_divergence_2d(cudaStream_t st, const float* u, const float* v, float* rhs, int batch,
                          int Nx, int Ny, float inv_hx, float inv_hy) {
+  if (Ny % 4) return launch_divergence_generic(st, u, v, nullptr, rhs, batch, Nx, Ny, 1, inv_hx, inv_hy, 0.f);
   const int threads = 128;
   dim3 grid((Ny / 4 + threads - 1) / threads, Nx, batch);
   divergence2d_kernel<<<grid, threads, 0, st>>>(u, v, rhs, Nx, Ny, inv_hx, inv_hy);
@@ -711,6 +741,10 @@ int launch_irfft_rows(cudaStream_t st, int lm_row, const float2* T, float* q, in
 int launch_correct_2d(cudaStream_t st, const float* us, const float* vs, const float* q,
                       const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
                       float inv_hx, float inv_hy) {
+  if (Ny % 4) {
+    if (qnext && qnext != q) return set_error_msg("internal: slab grids need rows of a multiple of 4 columns");
+    return launch_correct_generic(st, us, vs, nullptr, q, uo, vo, nullptr, batch, Nx, Ny, 1, inv_hx, inv_hy, 0.f);
+  }
   const int threads = 128;
   dim3 grid((Ny / 4 + threads - 1) / threads, Nx, batch);
   correct2d_kernel<<<grid, threads, 0, st>>>(us, vs, q, qnext ? qnext : q, uo, vo, Nx, Ny, inv_hx,

@@ -192,7 +192,7 @@ xlines3_kernel(float2* __restrict__ T, int N1, int NZP, const float2* __restrict
                const double* __restrict__ lamx, const double* __restrict__ lamy,
                const double* __restrict__ lamz, const float* __restrict__ lamxf,
                const float* __restrict__ lamyf, const float* __restrict__ lamzf, double cutoff,
-               float norm) {
+               float norm, const float* __restrict__ dtab) {
   using P = FftPlan<LM>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, 16);
@@ -216,6 +216,15 @@ xlines3_kernel(float2* __restrict__ T, int N1, int NZP, const float2* __restrict
       const int kx = t + G * e;
       float d = norm * fast_rcp(__ldg(lamxf + kx) + lyz);
       if (mean_line && kx == 0) d = 0.f;
+      v[e].x *= d;
+      v[e].y *= d;
+    }
+  } else if (dtab) {
+    // caller-supplied real diagonal in line layout dtab[(kz * N1 + ky) * M + kx] (cfd_transform)
+    const float* trow = dtab + ((size_t)kz * N1 + ky) * M;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float d = norm * __ldg(trow + t + G * e);
       v[e].x *= d;
       v[e].y *= d;
     }
@@ -344,7 +353,8 @@ int launch_lines_gather_t(cudaStream_t st, const float2* B, float2* A, int plane
 template <int LM>
 int launch_xlines3_t(cudaStream_t st, float2* T, size_t nlines, int N1, int NZP, const float2* tw,
                      const double* const* lam, const float* const* lamf, int fastd, double cutoff,
-                     float norm) {
+                     float norm, const float* dtab) {
+  if (dtab) fastd = 0;
   constexpr int LINES = lines_for(LM);
   using P = FftPlan<LM>;
   constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
@@ -353,12 +363,12 @@ int launch_xlines3_t(cudaStream_t st, float2* T, size_t nlines, int N1, int NZP,
     auto k = xlines3_kernel<LM, LINES, true>;
     if (int e = set_smem(k, smem)) return e;
     k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, N1, NZP, tw, lam[0], lam[1], lam[2],
-                                                            lamf[0], lamf[1], lamf[2], cutoff, norm);
+                                                            lamf[0], lamf[1], lamf[2], cutoff, norm, dtab);
   } else {
     auto k = xlines3_kernel<LM, LINES, false>;
     if (int e = set_smem(k, smem)) return e;
     k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, N1, NZP, tw, lam[0], lam[1], lam[2],
-                                                            lamf[0], lamf[1], lamf[2], cutoff, norm);
+                                                            lamf[0], lamf[1], lamf[2], cutoff, norm, dtab);
   }
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
@@ -389,13 +399,20 @@ int launch_lines_gather(cudaStream_t st, int lm, const float2* B, float2* A, int
 }
 int launch_xlines3(cudaStream_t st, int lm, float2* T, size_t nlines, int N1, int NZP,
                    const float2* tw, const double* const* lam, const float* const* lamf, int fastd,
-                   double cutoff, float norm) {
+                   double cutoff, float norm, const float* dtab) {
   CFD_DISPATCH_LM(lm, 4, 14,
-                  return launch_xlines3_t<LM_>(st, T, nlines, N1, NZP, tw, lam, lamf, fastd, cutoff, norm));
+                  return launch_xlines3_t<LM_>(st, T, nlines, N1, NZP, tw, lam, lamf, fastd, cutoff, norm, dtab));
   return 0;
 }
+int launch_divergence_generic(cudaStream_t st, const float* u, const float* v, const float* w, float* rhs,
+                              int batch, int N0, int N1, int N2, float ih0, float ih1, float ih2);
+int launch_correct_generic(cudaStream_t st, const float* us, const float* vs, const float* ws, const float* q,
+                           float* uo, float* vo, float* wo, int batch, int N0, int N1, int N2, float ih0,
+                           float ih1, float ih2);
+
 int launch_divergence_3d(cudaStream_t st, const float* u, const float* v, const float* w, float* rhs,
                          int batch, int N0, int N1, int N2, float ihx, float ihy, float ihz) {
+  if (N2 % 4) return launch_divergence_generic(st, u, v, w, rhs, batch, N0, N1, N2, ihx, ihy, ihz);
   const int threads = N2 / 4 < 128 ? N2 / 4 : 128;
   dim3 grid(((N2 / 4 + threads - 1) / threads) * N0 * N1, batch);
   divergence3d_kernel<<<grid, threads, 0, st>>>(u, v, w, rhs, N0, N1, N2, ihx, ihy, ihz);
@@ -406,6 +423,7 @@ int launch_divergence_3d(cudaStream_t st, const float* u, const float* v, const 
 int launch_correct_3d(cudaStream_t st, const float* us, const float* vs, const float* ws,
                       const float* q, float* uo, float* vo, float* wo, int batch, int N0, int N1,
                       int N2, float ihx, float ihy, float ihz) {
+  if (N2 % 4) return launch_correct_generic(st, us, vs, ws, q, uo, vo, wo, batch, N0, N1, N2, ihx, ihy, ihz);
   const int threads = N2 / 4 < 128 ? N2 / 4 : 128;
   dim3 grid(((N2 / 4 + threads - 1) / threads) * N0 * N1, batch);
   correct3d_kernel<<<grid, threads, 0, st>>>(us, vs, ws, q, uo, vo, wo, N0, N1, N2, ihx, ihy, ihz);

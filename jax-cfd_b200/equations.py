@@ -50,6 +50,12 @@ def navier_stokes_explicit_terms(density: float, viscosity: float, dt: float, gr
   return _engine.NativeExplicitTerms(grid, dt, density, viscosity, _engine.as_forcing(forcing))
 
 
+def _check_grid(grid: grids.Grid):
+  """Build-time validation (the reference raises at trace time too): what the kernels take."""
+  if grid.ndim not in (2, 3):
+    raise NotImplementedError(f'the B200 path implements 2-D and 3-D grids; got ndim={grid.ndim}')
+
+
 def semi_implicit_navier_stokes(density: float, viscosity: float, dt: float, grid: grids.Grid,
                                 convect=None, diffuse=diffusion.diffuse,
                                 pressure_solve: Callable = pressure.solve_fast_diag,
@@ -58,17 +64,43 @@ def semi_implicit_navier_stokes(density: float, viscosity: float, dt: float, gri
   """equations.py:120-151.  Returns `step_fn(v) -> v'` with the same GridVariable in/out types.
 
   Supported (anything else raises NotImplementedError at build time, there is no fallback):
-  all-periodic boundaries, offsets == grid.cell_faces, float32, power-of-two grid,
-  convect=None, diffuse=diffusion.diffuse, pressure_solve=pressure.solve_fast_diag, forcing from
-  `forcings.*`; time_stepper any of time_stepping.{forward_euler, midpoint_rk2, heun_rk2,
-  classic_rk4} (or a custom tableau through navier_stokes_rk).  Not differentiable.
+  all-periodic boundaries, offsets == grid.cell_faces, float32, any grid shape with axes of at
+  least 4 cells (power-of-two axes take the line-FFT pressure solve, other shapes the matmul one),
+  convect=None, diffuse=diffusion.diffuse, pressure_solve=pressure.solve_fast_diag (or a
+  functools.partial of it selecting `implementation`), forcing from `forcings.*`; time_stepper any
+  of time_stepping.{forward_euler, midpoint_rk2, heun_rk2, classic_rk4} (or a custom tableau
+  through navier_stokes_rk).  Not differentiable.
   """
   _check_terms(convect, diffuse)
-  if pressure_solve is not pressure.solve_fast_diag:
-    raise NotImplementedError('the B200 path implements pressure_solve=pressure.solve_fast_diag only')
+  _check_grid(grid)
+  impl = pressure.implementation_of(pressure_solve)
   f = _engine.as_forcing(forcing)
-  explicit_terms = _engine.NativeExplicitTerms(grid, dt, density, viscosity, f)
-  ode = time_stepping.ExplicitNavierStokesODE(explicit_terms, _engine.NativeProjection(grid))
+  explicit_terms = _engine.NativeExplicitTerms(grid, dt, density, viscosity, f, implementation=impl)
+  ode = time_stepping.ExplicitNavierStokesODE(explicit_terms, _engine.NativeProjection(grid, impl))
   ode.native_projection = True
-  ode.fused_step = _engine.NativeStep(grid, dt, density, viscosity, f)
+  ode.fused_step = _engine.NativeStep(grid, dt, density, viscosity, f, implementation=impl)
   return time_stepper(ode, dt)
+
+
+def implicit_diffusion_navier_stokes(density: float, viscosity: float, dt: float, grid: grids.Grid,
+                                     convect=None, diffusion_solve: Callable = diffusion.solve_fast_diag,
+                                     pressure_solve: Callable = pressure.solve_fast_diag,
+                                     forcing=None) -> Callable:
+  """equations.py:154-195: v* = v + dt (conv + forcing / rho); v = P(v*); then the implicit
+  diffusion solve (1 - nu dt lap)^-1 per component (diffusion.py:166-212).  On the device: the fused
+  step with the explicit Laplacian switched off (one stencil kernel + the pressure projection),
+  then one table-driven fast-diagonalisation transform and one axpy per component.  Like the
+  reference, `viscosity` (not viscosity / density) multiplies the Laplacian here (equations.py:192)."""
+  if convect is not None:
+    raise NotImplementedError('the B200 path implements the default Van-Leer convection only; pass convect=None')
+  if diffusion_solve is not diffusion.solve_fast_diag:
+    raise NotImplementedError('the B200 path implements diffusion_solve=diffusion.solve_fast_diag only')
+  _check_grid(grid)
+  impl = pressure.implementation_of(pressure_solve)
+  f = _engine.as_forcing(forcing)
+  inviscid = _engine.NativeStep(grid, dt, density, None, f, implementation=impl)
+
+  def navier_stokes_step(v):
+    return diffusion.solve_fast_diag(inviscid(v), viscosity, dt)
+
+  return navier_stokes_step

@@ -6,7 +6,9 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 from . import _engine
+from . import _lib
 from . import boundaries
+from . import filter_utils
 from . import grids
 
 
@@ -28,26 +30,25 @@ def _log_normal_pdf(x, mode, variance=.25):
 def filtered_velocity_field(rng_key, grid: grids.Grid, maximum_velocity: float = 1,
                             peak_wavenumber: float = 3, iterations: int = 3):
   """initial_conditions.py:71-121.  `rng_key` is an int seed (numpy RandomState stands in for
-  jax.random: same distribution, different bits).  The spectral filter (filter_utils.py:32-42)
-  runs once on the host; the project-and-normalise iterations use the device projection and the
-  fused max-speed reduction."""
+  jax.random: same distribution, different bits).  Everything after the noise runs on the device:
+  the spectral filter (filter_utils.py:32-42) is one table-driven transform per component, and each
+  project-and-normalise iteration is the device projection, the fused max-speed reduction and one
+  scaling kernel; the state never returns to the host (device arrays are returned)."""
   rs = np.random.RandomState(int(rng_key))
-  freqs = np.meshgrid(*[2 * np.pi * np.fft.fftfreq(n, s) for n, s in zip(grid.shape, grid.step)],
-                      indexing='ij')
-  k = np.sqrt(sum(f ** 2 for f in freqs))
-  with np.errstate(divide='ignore', invalid='ignore'):
-    filt = np.where(k > 0, _log_normal_pdf(k, peak_wavenumber) / k ** (grid.ndim - 1), 0.0)
+
+  def spectral_density(k):
+    return _log_normal_pdf(k, peak_wavenumber) / k ** (grid.ndim - 1)
+
   comps = []
   for _ in range(grid.ndim):
-    noise = rs.standard_normal(grid.shape)
-    comps.append(np.fft.ifftn(np.fft.fftn(noise) * filt).real.astype(np.float32))
+    noise = _lib.DeviceArray.from_numpy(rs.standard_normal(grid.shape).astype(np.float32))
+    comps.append(filter_utils.filter(spectral_density, noise, grid,
+                                     cache_key=('log_normal', float(peak_wavenumber))))
   bcs = [boundaries.periodic_boundary_conditions(grid.ndim)] * grid.ndim
   v = wrap_variables(comps, grid, bcs)
   project = _engine.NativeProjection(grid)
   for _ in range(iterations):
     v = project(v)
-    vmax = float(np.sqrt(_engine.diagnostics(v)['max_speed_sq']))
-    v = tuple(grids.GridVariable(grids.GridArray(
-        (np.float32(maximum_velocity) * np.asarray(u.data) / np.float32(vmax)).astype(np.float32),
-        u.offset, u.grid), u.bc) for u in v)
+    vmax = float(np.sqrt(_engine.diagnostics(v)['max_speed_sq']))  # initial_conditions.py:67-68
+    v = _engine.scale(v, maximum_velocity, vmax)                    # maximum_velocity * u / vmax
   return v

@@ -7,6 +7,9 @@ __path__.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.absp
 from . import _lib  # noqa: E402,F401
 from . import grids  # noqa: E402,F401
 from . import boundaries  # noqa: E402,F401
+from . import array_utils  # noqa: E402,F401
+from . import fast_diagonalization  # noqa: E402,F401
+from . import filter_utils  # noqa: E402,F401
 from . import advection  # noqa: E402,F401
 from . import diffusion  # noqa: E402,F401
 from . import forcings  # noqa: E402,F401

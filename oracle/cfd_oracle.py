@@ -297,6 +297,37 @@ def step(v, dt, h, density=1.0, viscosity: Optional[float] = None,
   return res[0] if len(res) == 1 else tuple(res)
 
 
+def diffusion_diagonals(shape, h, nu, dt, dtype=np.float32):
+  """Diagonal of diffusion.solve_fast_diag's transform in rfftn layout: diffusion.py:175-177
+  func(x) = dt nu x / (1 - dt nu x) on the summed circulant eigenvalues (array_utils.py:168-173,
+  fast_diagonalization.py:199-214), narrowed to complex64 for float32 data like x64-disabled jax."""
+  eig = []
+  for ax, (n, step) in enumerate(zip(shape, h)):
+    col = np.zeros(n)
+    col[0] = -2 / step ** 2
+    col[1] = col[-1] = 1 / step ** 2
+    eig.append(np.fft.rfft(col) if ax == len(shape) - 1 else np.fft.fft(col))
+  import functools
+  summed = functools.reduce(np.add.outer, eig)
+  dt_nu_x = (dt * nu) * summed
+  diag = dt_nu_x / (1 - dt_nu_x)
+  return diag.astype(np.complex64 if np.dtype(dtype) == np.float32 else np.complex128)
+
+
+def implicit_diffusion_step(v, dt, h, density=1.0, viscosity=0.0, forcing: Optional[Forcing] = None,
+                            diag=None, ddiag=None):
+  """`implicit_diffusion_navier_stokes`: equations.py:154-195 with diffusion.solve_fast_diag
+  (diffusion.py:166-212; periodic; even last axis -> the rfft implementation):
+  v* = v + (conv + forcing / rho) dt;  v = P(v*);  v = v + irfftn(D rfftn(v))."""
+  k0 = explicit_terms(v, dt, h, None, forcing, density)          # no explicit diffusion
+  ustar = tuple(u + k * dt for u, k in zip(v, k0))               # equations.py:186-188
+  vp, _ = projection(ustar, h, diag)
+  if ddiag is None:
+    ddiag = diffusion_diagonals(vp[0].shape, h, viscosity, dt, vp[0].dtype)  # nu = viscosity (equations.py:192)
+  axes = tuple(range(vp[0].ndim))
+  return tuple(u + np.fft.irfftn(ddiag * np.fft.rfftn(u), s=u.shape, axes=axes).astype(u.dtype) for u in vp)
+
+
 def rk_step(v, dt, h, tableau_a, tableau_b, density=1.0, viscosity=None, forcing=None, diag=None):
   """`navier_stokes_rk`: time_stepping.py:59-106 (projection after every stage)."""
   nu = None if viscosity is None else viscosity / density

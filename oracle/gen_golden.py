@@ -133,47 +133,104 @@ def run_projection_case(name, shape, domain, seed):
   print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
 
 
-def main():
-  os.makedirs(OUT, exist_ok=True)
+def run_implicit_case(name, shape, domain, seed, density, viscosity, dt, forcing_spec, nsteps):
+  """equations.implicit_diffusion_navier_stokes (equations.py:154-195) run by the reference."""
+  grid = cfd.grids.Grid(shape, domain=domain)
+  v0 = cfd_oracle.filtered_velocity_field(seed, shape, domain, 1.0, 2, dtype=np.float64)
+  rec = dict(shape=np.array(shape), domain=np.array(domain, dtype=np.float64), seed=seed,
+             density=density, viscosity=viscosity, dt=dt, smag_cs=-1.0,
+             forcing_spec=repr(forcing_spec), nsteps=np.array(nsteps), stepper='implicit_diffusion')
+  for i, a in enumerate(v0):
+    rec[f'v0_{i}'] = a.astype(np.float32)
+  for prec in ('f32', 'f64'):
+    jax.config.update('jax_enable_x64', prec == 'f64')
+    dtype = np.float32 if prec == 'f32' else np.float64
+    v = wrap(grid, [a.astype(np.float32).astype(dtype) for a in v0])
+    step = cfd.equations.implicit_diffusion_navier_stokes(
+        density=density, viscosity=viscosity, dt=dt, grid=grid, forcing=build_forcing(grid, forcing_spec))
+    cur, done = v, 0
+    for n in nsteps:
+      for _ in range(n - done):
+        cur = step(cur)
+      done = n
+      for i, a in enumerate(cur):
+        assert a.data.dtype == dtype, (a.data.dtype, dtype)
+        rec[f'{prec}_v{n}_{i}'] = np.asarray(a.data)
+  jax.config.update('jax_enable_x64', False)
+  path = os.path.join(OUT, name + '.npz')
+  np.savez_compressed(path, **rec)
+  print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
+
+
+def cases():
+  """name -> thunk.  New fixtures are appended at the end; running without arguments rewrites every
+  fixture (bit-identical on re-generation), `gen_golden.py NAME...` only the named ones."""
   two_pi = 2 * np.pi
   d2 = ((0.0, two_pi), (0.0, two_pi))
   d3 = d2 + ((0.0, two_pi),)
   kolm = [('kolmogorov', dict(scale=1.0, k=4)), ('linear', -0.1)]
+  c = {}
+
+  def case(name, *a, **k):
+    c[name] = lambda: run_case(name, *a, **k)
+
+  def pcase(name, *a, **k):
+    c[name] = lambda: run_projection_case(name, *a, **k)
+
   # K64x32: Kolmogorov (paper config: scale 1, k 4, linear -0.1, nu 1e-3), non-square pow2 grid
-  run_case('k2d_64x32', (64, 32), d2, 1, 3.0, 3, 1.0, 1e-3,
-           0.5 * (two_pi / 64) / 3.0, kolm, None, [1, 10])
+  case('k2d_64x32', (64, 32), d2, 1, 3.0, 3, 1.0, 1e-3, 0.5 * (two_pi / 64) / 3.0, kolm, None, [1, 10])
   # demo.ipynb-like decaying turbulence (no forcing), square
-  run_case('d2d_128', (128, 128), d2, 2, 2.0, 3, 1.0, 1e-3,
-           0.5 * (two_pi / 128) / 2.0, None, None, [1, 20])
+  case('d2d_128', (128, 128), d2, 2, 2.0, 3, 1.0, 1e-3, 0.5 * (two_pi / 128) / 2.0, None, None, [1, 20])
   # density != 1, anisotropic domain, swap_xy kolmogorov
-  run_case('k2d_32x64_rho', (32, 64), ((0.0, two_pi), (0.0, 2 * two_pi)), 3, 1.5, 2, 2.0, 5e-3,
-           0.01, [('linear', 0.05), ('kolmogorov', dict(scale=0.5, k=2, swap_xy=True))], None, [1, 5])
-  # non power-of-two grid (oracle only)
-  run_case('d2d_48x36', (48, 36), d2, 4, 1.0, 3, 1.0, 1e-2, 0.02, None, None, [1, 3])
+  case('k2d_32x64_rho', (32, 64), ((0.0, two_pi), (0.0, 2 * two_pi)), 3, 1.5, 2, 2.0, 5e-3,
+       0.01, [('linear', 0.05), ('kolmogorov', dict(scale=0.5, k=2, swap_xy=True))], None, [1, 5])
+  # non power-of-two grid
+  case('d2d_48x36', (48, 36), d2, 4, 1.0, 3, 1.0, 1e-2, 0.02, None, None, [1, 3])
   # inviscid (viscosity=None is allowed by equations.py:106) with taylor-green forcing
-  run_case('tg2d_32', (32, 32), d2, 5, 1.0, 2, 1.0, 1e-2, 0.02,
-           [('taylor_green', dict(scale=0.7, k=2))], None, [1, 4])
+  case('tg2d_32', (32, 32), d2, 5, 1.0, 2, 1.0, 1e-2, 0.02,
+       [('taylor_green', dict(scale=0.7, k=2))], None, [1, 4])
   # 3-D with Smagorinsky closure (config #5 in miniature)
-  run_case('s3d_16', (16, 16, 16), d3, 6, 1.0, 2, 1.0, 1.0 / 1600, 0.05, None, 0.2, [1, 5])
-  run_case('s3d_16x8x32_kolm', (16, 8, 32), d3, 7, 1.0, 2, 1.0, 1e-2, 0.03,
-           [('kolmogorov', dict(scale=1.0, k=2)), ('linear', -0.1)], 0.17, [1, 3])
-  run_case('d3d_16', (16, 16, 16), d3, 8, 1.0, 2, 1.0, 1e-2, 0.05, None, None, [1, 3])
+  case('s3d_16', (16, 16, 16), d3, 6, 1.0, 2, 1.0, 1.0 / 1600, 0.05, None, 0.2, [1, 5])
+  case('s3d_16x8x32_kolm', (16, 8, 32), d3, 7, 1.0, 2, 1.0, 1e-2, 0.03,
+       [('kolmogorov', dict(scale=1.0, k=2)), ('linear', -0.1)], 0.17, [1, 3])
+  case('d3d_16', (16, 16, 16), d3, 8, 1.0, 2, 1.0, 1e-2, 0.05, None, None, [1, 3])
   # 3-D cases at sizes the CUDA line FFTs accept (axes >= 16, last axis >= 32)
-  run_case('s3d_16x16x32', (16, 16, 32), d3, 14, 1.0, 2, 1.0, 1.0 / 1600, 0.04,
-           [('kolmogorov', dict(scale=1.0, k=2)), ('linear', -0.1)], 0.2, [1, 3])
-  run_case('d3d_32x16x32', (32, 16, 32), d3, 15, 1.0, 2, 1.0, 1e-2, 0.04, None, None, [1, 3])
-  run_case('tg3d_16x32x32', (16, 32, 32), d3, 16, 1.0, 2, 1.0, 5e-3, 0.03,
-           [('taylor_green', dict(scale=0.5, k=1))], 0.15, [1, 2])
+  case('s3d_16x16x32', (16, 16, 32), d3, 14, 1.0, 2, 1.0, 1.0 / 1600, 0.04,
+       [('kolmogorov', dict(scale=1.0, k=2)), ('linear', -0.1)], 0.2, [1, 3])
+  case('d3d_32x16x32', (32, 16, 32), d3, 15, 1.0, 2, 1.0, 1e-2, 0.04, None, None, [1, 3])
+  case('tg3d_16x32x32', (16, 32, 32), d3, 16, 1.0, 2, 1.0, 5e-3, 0.03,
+       [('taylor_green', dict(scale=0.5, k=1))], 0.15, [1, 2])
   # RK steppers ("next" row f2)
-  run_case('rk4_2d_32', (32, 32), d2, 9, 1.0, 2, 1.0, 1e-2, 0.04, kolm, None, [1, 3],
-           stepper='classic_rk4')
-  run_case('rk2_2d_32', (32, 32), d2, 9, 1.0, 2, 1.0, 1e-2, 0.04, kolm, None, [1, 3],
-           stepper='midpoint_rk2')
-  run_projection_case('proj2d_64x32', (64, 32), d2, 11)
-  run_projection_case('proj3d_16x8x32', (16, 8, 32), d3, 12)
-  run_projection_case('proj3d_32x16x64', (32, 16, 64), d3, 17)
-  run_projection_case('proj2d_step1_30x20', (30, 20), ((0.0, 30.0), (0.0, 20.0)), 13)
+  case('rk4_2d_32', (32, 32), d2, 9, 1.0, 2, 1.0, 1e-2, 0.04, kolm, None, [1, 3], stepper='classic_rk4')
+  case('rk2_2d_32', (32, 32), d2, 9, 1.0, 2, 1.0, 1e-2, 0.04, kolm, None, [1, 3], stepper='midpoint_rk2')
+  pcase('proj2d_64x32', (64, 32), d2, 11)
+  pcase('proj3d_16x8x32', (16, 8, 32), d3, 12)
+  pcase('proj3d_32x16x64', (32, 16, 64), d3, 17)
+  pcase('proj2d_step1_30x20', (30, 20), ((0.0, 30.0), (0.0, 20.0)), 13)
+  # ---- round 2 ----
+  # Smagorinsky closure in 2-D (subgrid_models.py is dimension agnostic; subgrid_models_test.py:117-217)
+  case('s2d_64x32', (64, 32), d2, 21, 2.0, 3, 1.0, 1e-3, 0.01, kolm, 0.2, [1, 4])
+  case('s2d_100', (100, 100), d2, 22, 1.0, 3, 1.0, 1e-3, 0.01, None, 0.2, [1, 3])
+  # grids that are not powers of two, odd axes (fast_diagonalization.py:101-108: matmul fallback)
+  case('d2d_100', (100, 100), d2, 23, 1.0, 3, 1.0, 1e-2, 0.02, kolm, None, [1, 3])
+  case('d2d_33x27', (33, 27), d2, 24, 1.0, 2, 1.0, 1e-2, 0.02, None, None, [1, 3])
+  case('d3d_20x24x36', (20, 24, 36), d3, 25, 1.0, 2, 1.0, 1e-2, 0.04, None, None, [1, 2])
+  case('s3d_24x20x12', (24, 20, 12), d3, 26, 1.0, 2, 1.0, 1e-2, 0.04, [('linear', -0.1)], 0.2, [1, 2])
+  # implicit diffusion (equations.py:154-195; what the ML configs step with)
+  c['imp2d_64x32'] = lambda: run_implicit_case('imp2d_64x32', (64, 32), d2, 31, 1.5, 5e-2, 0.02, kolm, [1, 4])
+  c['imp2d_48x36'] = lambda: run_implicit_case('imp2d_48x36', (48, 36), d2, 32, 1.0, 1e-2, 0.02, None, [1, 3])
+  c['imp3d_16x16x32'] = lambda: run_implicit_case('imp3d_16x16x32', (16, 16, 32), d3, 33, 1.0, 2e-2, 0.03,
+                                                  [('linear', -0.1)], [1, 2])
+  return c
+
+
+def main(argv):
+  os.makedirs(OUT, exist_ok=True)
+  table = cases()
+  names = argv or list(table)
+  for n in names:
+    table[n]()
 
 
 if __name__ == '__main__':
-  main()
+  main(sys.argv[1:])

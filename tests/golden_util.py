@@ -32,7 +32,11 @@ def load(name):
 
 def step_cases():
   return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                if not os.path.basename(p).startswith('proj'))
+                if not os.path.basename(p).startswith(('proj', 'imp')))
+
+
+def implicit_cases():
+  return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 'imp*.npz')))
 
 
 def oracle_forcing(rec, dtype=np.float32):

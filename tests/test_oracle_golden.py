@@ -30,7 +30,13 @@ def test_step_matches_reference(name, prec):
           vnew, q, ustar = out
           for i in range(d):
             assert gu.rel_l2(ustar[i], rec[f'{prec}_ustar_{i}']) < tol
-          assert gu.rel_l2(q, rec[f'{prec}_q']) < 10 * tol
+          want_q = rec[f'{prec}_q']
+          if rec['shape'][-1] % 2:
+            # odd last axis: the reference falls back to the matmul transform
+            # (fast_diagonalization.py:101-108), whose eigh-computed zero eigenvalue is ~1e-13, not 0,
+            # so in float64 the mean mode of q is amplified rounding noise: compare q up to a constant
+            q, want_q = q - q.mean(), want_q - want_q.mean()
+          assert gu.rel_l2(q, want_q) < 10 * tol
         v = out[0]
       else:
         v = cfd_oracle.rk_step(v, rec['dt'], rec['h'], a, b, rec['density'], rec['viscosity'],
@@ -91,3 +97,26 @@ def test_pinv_poisson_kat():
   x = np.fft.irfftn(diag * np.fft.rfftn(b), s=shape, axes=(0, 1))
   ax = cfd_oracle.laplacian(x, h)
   np.testing.assert_allclose(ax, b - b.mean(), atol=1e-5)
+
+
+@pytest.mark.parametrize('name', gu.implicit_cases())
+@pytest.mark.parametrize('prec', ['f32', 'f64'])
+def test_implicit_diffusion_step_matches_reference(name, prec):
+  """equations.implicit_diffusion_navier_stokes (equations.py:154-195) run by the reference itself
+  vs cfd_oracle.implicit_diffusion_step."""
+  rec = gu.load(name)
+  dtype = np.float32 if prec == 'f32' else np.float64
+  tol = 2e-6 if prec == 'f32' else 1e-6
+  v = tuple(rec[f'v0_{i}'].astype(dtype) for i in range(rec['ndim']))
+  forcing = gu.oracle_forcing(rec, dtype)
+  diag = cfd_oracle.pinv_diagonals(rec['shape'], rec['h'], np.float32)
+  ddiag = cfd_oracle.diffusion_diagonals(rec['shape'], rec['h'], rec['viscosity'], rec['dt'], np.float32)
+  done = 0
+  for n in rec['nsteps']:
+    for _ in range(n - done):
+      v = cfd_oracle.implicit_diffusion_step(v, rec['dt'], rec['h'], rec['density'], rec['viscosity'], forcing,
+                                             diag=diag, ddiag=ddiag)
+    done = n
+    for i in range(rec['ndim']):
+      assert v[i].dtype == dtype
+      assert gu.rel_l2(v[i], rec[f'{prec}_v{n}_{i}']) < tol * max(1, n), (name, n, i)
