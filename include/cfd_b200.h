@@ -120,6 +120,11 @@ int cfd_step(cfd_plan* plan, cfd_stream stream, const float* const* v_in, float*
 int cfd_repeated(cfd_plan* plan, cfd_stream stream, float* const* v_a, float* const* v_b,
                  int nsteps, const cfd_params* params, int* result_in_b);
 
+/* `nsteps` >= 1 steps from v_in into v_out without ever writing v_in (operands of an XLA custom
+ * call are immutable): what csrc/xla_ffi_shim.cc forwards to.  v_out must not alias v_in. */
+int cfd_advance(cfd_plan* plan, cfd_stream stream, const float* const* v_in, float* const* v_out,
+                int nsteps, const cfd_params* params);
+
 /* dv/dt = conv + (nu/rho) lap + forcing/rho  (equations.navier_stokes_explicit_terms,
  * equations.py:77-116) -- the F of navier_stokes_rk (time_stepping.py:59-106). */
 int cfd_explicit_terms(cfd_plan* plan, cfd_stream stream, const float* const* v_in,

@@ -84,6 +84,8 @@ _SIGS = {
     'cfd_repeated': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                     ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
                                     ctypes.POINTER(Params), ctypes.POINTER(ctypes.c_int)]),
+    'cfd_advance': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                   ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(Params)]),
     'cfd_explicit_terms': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.POINTER(ctypes.c_void_p),
                                           ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(Params)]),

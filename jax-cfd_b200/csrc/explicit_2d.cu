@@ -68,7 +68,7 @@ template <int PATTERN, int C, bool LAZY>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
                   float* __restrict__ vs, float* __restrict__ rhs, int Nx, int Ny, int row0,
-                  int nx_global, StepConsts c, int dvdt_mode, int TX) {
+                  int nx_global, StepConsts c, int dvdt_mode, int TX, int tile_begin) {
   using Row = FC<C>;
   // Halo lanes: the divergence needs v* one column to the left of the first stored column, whose
   // own stencil reaches 2 further columns: 4 columns = 1 lane (C = 4) or 2 lanes (C = 2) on the
@@ -86,7 +86,7 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
   if (jg < 0) jg += Ny;
   const bool store_ok = (lane >= kHaloL) && (lane < 32 - kHaloR) && (jbase < Ny);
   const size_t boff = (size_t)blockIdx.z * (size_t)Nx * (size_t)Ny;
-  const int i0 = blockIdx.y * TX;
+  const int i0 = (blockIdx.y + tile_begin) * TX;  // row tiles [tile_begin, tile_begin + gridDim.y)
   const int iend = min(i0 + TX, Nx);  // exclusive
 
   // row i in [-Nx, 2 Nx) of a slab-decomposed field
@@ -359,16 +359,30 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
 
 // sq.own == nullptr: (u, v) is a projected state.  sq.own != nullptr: LAZY mode, (u, v) = (u*, v*)
 // of the previous step and q its pressure.  Nx = local rows; row0 / nx_global place the slab.
-int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc sq, float* us,
-                            float* vs, float* rhs, int batch, int Nx, int Ny, int row0,
-                            int nx_global, const StepConsts& c, int dvdt_mode) {
-  const float* qprev = sq.own;
-  if (Nx < 3) return set_error_msg("a slab needs at least 3 rows");
-  // rows per warp: 64 normally (5 warm-up rows = 8 % redundant work); 16 on small grids, where 64
-  // would leave most SMs without a warp (2048^2: 576 warps for 148 SMs)
+// rows per warp: 64 normally (5 warm-up rows = 8 % redundant work); 16 on small grids, where 64
+// would leave most SMs without a warp (2048^2: 576 warps for 148 SMs)
+int explicit_2d_tile_rows(int batch, int Nx, int Ny) {
   const int cols0 = 120;
   const long warps64 = (long)((Ny + cols0 - 1) / cols0) * ((Nx + 63) / 64) * batch;
-  const int TX = warps64 >= 148L * 12 ? 64 : 16;
+  return warps64 >= 148L * 12 ? 64 : 16;
+}
+
+// tile_begin / tile_count: the range of row tiles (explicit_2d_tile_rows rows each) this launch
+// covers; tile_count < 0 = all of them.  The slab-decomposed step launches the stencil block by
+// block so that the row FFT and the NVLink transfer of a block overlap the stencil of the next.
+int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc sq, float* us,
+                            float* vs, float* rhs, int batch, int Nx, int Ny, int row0,
+                            int nx_global, const StepConsts& c, int dvdt_mode, int tile_begin,
+                            int tile_count) {
+  const float* qprev = sq.own;
+  if (Nx < 3) return set_error_msg("a slab needs at least 3 rows");
+  const int TX = explicit_2d_tile_rows(batch, Nx, Ny);
+  const int tiles_all = (Nx + TX - 1) / TX;
+  if (tile_count < 0) {
+    tile_begin = 0;
+    tile_count = tiles_all;
+  }
+  if (tile_begin < 0 || tile_begin + tile_count > tiles_all) return set_error_msg("internal: bad stencil tile range");
   static const int forced_cols = [] {  // tuning knob: CFD_EXPLICIT_COLS=2|4 columns per lane
     const char* e = getenv("CFD_EXPLICIT_COLS");
     return (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
@@ -378,7 +392,7 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
   const int cols = forced_cols ? forced_cols : (work2 < work4 ? 2 : 4);
   const int warp_cols = cols == 4 ? 120 : 56;
   const int strips = (Ny + warp_cols - 1) / warp_cols;
-  dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, (Nx + TX - 1) / TX, batch);
+  dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, tile_count, batch);
   int pattern = 0, nt = 0;
   for (int t = 0; t < c.n_terms; ++t) {
     const int kind = c.term_kind[t];
@@ -391,7 +405,7 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
   }
 #define CFD_EXPL_LAUNCH(P, CC, LZ)                                                          \
   explicit2d_kernel<P, CC, LZ><<<grid, 32 * kWarpsPerCta, 0, stream>>>(                        \
-      su, sv, sq, us, vs, rhs, Nx, Ny, row0, nx_global, c, dvdt_mode, TX)
+      su, sv, sq, us, vs, rhs, Nx, Ny, row0, nx_global, c, dvdt_mode, TX, tile_begin)
 #define CFD_EXPL_CASE(P)                    \
   case P:                                   \
     if (cols == 2) {                        \
@@ -425,7 +439,7 @@ int launch_explicit_2d(cudaStream_t stream, const float* u, const float* v, cons
                        float* us, float* vs, float* rhs, int batch, int Nx, int Ny,
                        const StepConsts& c, int dvdt_mode) {
   const SlabSrc su = {u, u, u}, sv = {v, v, v}, sq = {qprev, qprev, qprev};
-  return launch_explicit_2d_slab(stream, su, sv, sq, us, vs, rhs, batch, Nx, Ny, 0, Nx, c, dvdt_mode);
+  return launch_explicit_2d_slab(stream, su, sv, sq, us, vs, rhs, batch, Nx, Ny, 0, Nx, c, dvdt_mode, 0, -1);
 }
 
 }  // namespace cfd

@@ -10,6 +10,20 @@
 //   * ordering: a one-CTA flag barrier kernel (system-scope stores/loads on peer-mapped flags)
 //     between the phases.  No NCCL on the data path; the host side only exchanges 64-byte IPC
 //     handles once (any transport: torch.distributed in jax_cfd_b200.distributed).
+//
+// Default since round 2 ("push" mode, CFD_DIST_MODE=pull selects the scheme above): the two
+// transposes are PUSHED by copy kernels on a second, high-priority stream while the compute kernels
+// keep running on local memory only:
+//   * the stencil and the row FFT run block by block over the slab's rows; as soon as a block of
+//     rows is transformed its part of every ky line is stored into the line owners' line buffers
+//     (posted NVLink writes of >= 2 KB pieces), overlapping the stencil / row FFT of the next block;
+//   * the x-direction kernel then works on a purely local line buffer (no peer table, same speed
+//     as on one GPU), chunk of lines by chunk of lines; finished chunks are pushed back to the slab
+//     owners while the next chunk is transformed;
+//   * per-(rank, block) flags written after each push replace two of the three global barriers:
+//     a rank waits only for the data it is about to read; the barrier before the stencil becomes
+//     a neighbour-only flag.  Line buffers are double buffered across steps.
+// Results stay bit-identical to the single-GPU path (same kernels, same arithmetic).
 #include <stdlib.h>
 #include <string.h>
 
@@ -22,7 +36,11 @@ namespace cfd {
 
 int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc sq, float* us,
                             float* vs, float* rhs, int batch, int Nx, int Ny, int row0,
-                            int nx_global, const StepConsts& c, int dvdt_mode);
+                            int nx_global, const StepConsts& c, int dvdt_mode, int tile_begin,
+                            int tile_count);
+int explicit_2d_tile_rows(int batch, int Nx, int Ny);
+int launch_rfft_rows_block(cudaStream_t st, int lm_row, const float* rhs, float2* T, int batch, int Nx,
+                           const float2* tw, const float2* rtw, int paired, int x_begin, int x_count);
 int launch_rfft_rows(cudaStream_t, int lm_row, const float* rhs, float2* T, int batch, int Nx,
                      const float2* tw, const float2* rtw, int paired);
 int launch_irfft_rows(cudaStream_t, int lm_row, const float2* T, float* q, int batch, int Nx,
@@ -46,29 +64,134 @@ struct FlagPeers {
 // waits until every peer has published it in r's own array.  The kernels before it on the stream
 // have completed (their stores are performed), so observing a peer's flag implies its data is
 // visible.  A cycle budget bounds the spin so that a lost peer cannot hang the GPU.
+// Spin budget of the device-side waits, in clock cycles (CFD_DIST_TIMEOUT_S seconds, default 120):
+// calls are enqueue-only, so ordinary host skew between ranks (first-call set-up, a pause in the
+// host program) must fit inside it.  After a time-out the error word is set and every later wait
+// returns at once, so a lost peer cannot hang the GPU; cfd_dist_check reports it.
+long long spin_budget() {
+  static const long long v = [] {
+    const char* e = getenv("CFD_DIST_TIMEOUT_S");
+    const double s = e ? atof(e) : 120.0;
+    return (long long)((s > 0 ? s : 120.0) * 1.9e9);
+  }();
+  return v;
+}
+
+__device__ __forceinline__ void spin_until(volatile unsigned long long* flag, unsigned long long value,
+                                           volatile unsigned long long* err, long long budget) {
+  if (*err) return;  // a previous wait already timed out: do not stall the chain again
+  const long long t0 = clock64();
+  while (*flag < value) {
+    if (clock64() - t0 > budget) {
+      *err = value;
+      break;
+    }
+  }
+}
+
 __global__ void slab_barrier_kernel(FlagPeers fp, int rank, int world, unsigned long long epoch,
-                                    unsigned long long* err) {
+                                    unsigned long long* err, long long budget) {
   const int p = threadIdx.x;
   if (p >= world) return;
   __threadfence_system();
   volatile unsigned long long* remote = fp.p[p] + rank;
   *remote = epoch;
   __threadfence_system();
-  volatile unsigned long long* mine = fp.p[rank] + p;
-  const long long t0 = clock64();
-  while (*mine < epoch) {
-    if (clock64() - t0 > 8000000000LL) {  // ~4 s
-      *err = epoch;
-      break;
+  spin_until(fp.p[rank] + p, epoch, err, budget);
+  __threadfence_system();
+}
+
+// flag slots (8 bytes each) inside every rank's flag block
+constexpr int kSlotErr = 16;    // 0..15: the all-to-all barrier above
+constexpr int kSlotFwd = 32;    // + src * 8 + block   : row block `block` of rank `src` has arrived
+constexpr int kSlotBack = 96;   // + src * 8 + chunk   : line chunk `chunk` of rank `src` has arrived
+constexpr int kSlotNbr = 160;   // + 0 / 1             : previous / next rank has finished the step
+constexpr int kFlagSlots = 192;
+constexpr int kMaxBlocks = 8;
+
+// thread p < ntargets: publish `value` in `slot` of target p's flag block.  The copy kernel before
+// it on the stream has completed, so observing the flag implies its data is visible.
+__global__ void slab_signal_kernel(FlagPeers fp, int ntargets, int slot, unsigned long long value) {
+  const int p = threadIdx.x;
+  if (p >= ntargets) return;
+  __threadfence_system();
+  volatile unsigned long long* f = fp.p[p] + slot;
+  *f = value;
+}
+
+// thread i < nsrc * nper: wait until flags[base + (i / nper) * 8 + i % nper] >= value
+__global__ void slab_wait_kernel(unsigned long long* flags, int base, int nsrc, int nper,
+                                 unsigned long long value, long long budget) {
+  const int i = threadIdx.x;
+  if (i < nsrc * nper) spin_until(flags + base + (i / nper) * kMaxBlocks + i % nper, value, flags + kSlotErr, budget);
+  __threadfence_system();
+}
+
+// Block copy between a slab-local spectrum T[ky][x_loc] (plain or pair-interleaved) and the line
+// buffers L[line][x_global] (always plain): for every destination rank (blockIdx.y) `nlines` lines
+// of `len` points.  One float4 (two points, or one point of both lines of a pair) per thread and trip.
+//   FWD  = true:  src = own T, lines [r * nlines, (r + 1) * nlines), points [x0, x0 + len)
+//                 dst = rank r's line buffer, line l, points [dst_x0, dst_x0 + len)
+//   FWD  = false: src = own line buffer, lines [l0, l0 + nlines), points [r * len, (r + 1) * len)
+//                 dst = rank r's T, lines [dst_l0, dst_l0 + nlines), all `len` = Nloc points
+struct PushDst {
+  float2* p[CFD_MAX_PEERS];
+};
+template <bool FWD, bool PAIRED>
+__global__ void __launch_bounds__(256)
+slab_push_kernel(const float2* __restrict__ src, PushDst dst, int nlines, int len, int nloc, size_t nxg,
+                 int x0, int dst_x0, int l0, int dst_l0) {
+  const int r = blockIdx.y;
+  float2* __restrict__ d = dst.p[r];
+  if (!PAIRED) {
+    const int nvec = len / 2;  // float4 = two consecutive points
+    for (int l = blockIdx.x; l < nlines; l += gridDim.x) {
+      const float2* s;
+      float2* o;
+      if (FWD) {
+        s = src + ((size_t)r * nlines + l) * nloc + x0;
+        o = d + (size_t)l * nxg + dst_x0;
+      } else {
+        s = src + (size_t)(l0 + l) * nxg + (size_t)r * len;
+        o = d + (size_t)(dst_l0 + l) * nloc;
+      }
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < nvec; i += 256) o4[i] = __ldcs(s4 + i);
+    }
+  } else {
+    // T is pair-interleaved: T[(ky >> 1)][x][ky & 1]; a thread moves point x of both lines of a pair
+    for (int lp = blockIdx.x; lp < nlines / 2; lp += gridDim.x) {
+      if (FWD) {
+        const size_t pair = ((size_t)r * nlines) / 2 + lp;
+        const float4* s4 = reinterpret_cast<const float4*>(src + (pair * nloc + x0) * 2);
+        float2* o0 = d + (size_t)(2 * lp) * nxg + dst_x0;
+        float2* o1 = o0 + nxg;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < len; i += 256) {
+          const float4 v = __ldcs(s4 + i);
+          o0[i] = make_float2(v.x, v.y);
+          o1[i] = make_float2(v.z, v.w);
+        }
+      } else {
+        const float2* s0 = src + (size_t)(l0 + 2 * lp) * nxg + (size_t)r * len;
+        const float2* s1 = s0 + nxg;
+        float4* o4 = reinterpret_cast<float4*>(d + ((size_t)((dst_l0 >> 1) + lp) * nloc) * 2);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < len; i += 256) {
+          const float2 a = __ldcs(s0 + i), b = __ldcs(s1 + i);
+          o4[i] = make_float4(a.x, a.y, b.x, b.y);
+        }
+      }
     }
   }
-  __threadfence_system();
 }
 
 // layout of the shared (IPC-exported) allocation, identical on every rank; units = floats
 struct SharedLayout {
   size_t field;  // floats per local field
-  size_t off_vin[2], off_us[2][2], off_q[2], off_T, off_flags, total_bytes;
+  size_t off_vin[2], off_us[2][2], off_q[2], off_T, off_L[2], off_flags, total_bytes;
 };
 SharedLayout shared_layout(size_t nloc, size_t ny) {
   SharedLayout L;
@@ -79,7 +202,10 @@ SharedLayout shared_layout(size_t nloc, size_t ny) {
     for (int a = 0; a < 2; ++a) { L.off_us[s][a] = o; o += L.field; }
   for (int s = 0; s < 2; ++s) { L.off_q[s] = o; o += L.field; }
   L.off_T = o; o += L.field;  // My * Nloc float2 = Nloc * Ny floats
-  L.off_flags = o; o += 64;   // 16 x 8-byte flags + error word
+  // line buffers of the push mode: (My / world) lines of Nx_global points = one field each,
+  // double buffered across steps
+  for (int s = 0; s < 2; ++s) { L.off_L[s] = o; o += L.field; }
+  L.off_flags = o; o += 2 * kFlagSlots;  // kFlagSlots 8-byte flags
   L.total_bytes = o * sizeof(float);
   return L;
 }
@@ -93,8 +219,8 @@ int barrier(cfd_plan* p, cudaStream_t st) {
   for (int r = 0; r < CFD_MAX_PEERS; ++r)
     fp.p[r] = reinterpret_cast<unsigned long long*>(fptr(p->peer_shared[r < p->world ? r : p->rank], L.off_flags));
   p->epoch += 1;
-  unsigned long long* err = reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + 16;
-  slab_barrier_kernel<<<1, 32, 0, st>>>(fp, p->rank, p->world, p->epoch, err);
+  unsigned long long* err = reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + kSlotErr;
+  slab_barrier_kernel<<<1, 32, 0, st>>>(fp, p->rank, p->world, p->epoch, err, spin_budget());
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   prof_mark(p, st, "barrier");
@@ -109,6 +235,16 @@ int staged_mode() {
     return e ? atoi(e) : 0;
   }();
   return v;
+}
+
+// CFD_DIST_MODE=pull selects the round-1 scheme (x-line kernel loads / stores peer memory, three
+// global barriers per step); default: push (see the header of this file)
+bool push_mode() {
+  static const bool v = [] {
+    const char* e = getenv("CFD_DIST_MODE");
+    return !(e && strcmp(e, "pull") == 0);
+  }();
+  return v && !staged_mode();
 }
 
 // The x pass of the distributed FFT with the transposes on the COPY ENGINES.
@@ -179,6 +315,149 @@ int xpass_staged(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int lnloc)
   return 0;
 }
 
+int signal_flags(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int ntargets, const int* targets,
+                 int slot, unsigned long long value) {
+  FlagPeers fp;
+  for (int i = 0; i < CFD_MAX_PEERS; ++i)
+    fp.p[i] = reinterpret_cast<unsigned long long*>(
+        fptr(p->peer_shared[i < ntargets ? targets[i] : p->rank], L.off_flags));
+  slab_signal_kernel<<<1, 32, 0, st>>>(fp, ntargets, slot, value);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int wait_flags(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int base, int nsrc, int nper,
+               unsigned long long value, const char* name) {
+  slab_wait_kernel<<<1, 64, 0, st>>>(reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)), base,
+                                     nsrc, nper, value, spin_budget());
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  prof_mark(p, st, name);
+  return 0;
+}
+
+// how many row blocks / line chunks a step is pipelined in (CFD_DIST_BLOCKS / CFD_DIST_CHUNKS
+// override): the largest count <= the wish whose pieces are whole stencil tiles / kernel line groups
+int pick_pieces(int total, int unit, int wish) {
+  int n = wish < 1 ? 1 : (wish > kMaxBlocks ? kMaxBlocks : wish);
+  while (n > 1 && (total % n || (total / n) % unit)) --n;
+  return n;
+}
+
+// One step in push mode (see the header).  cur / nxt: ping-pong slots of (u*, v*, q).
+int step_push(cfd_plan* p, cudaStream_t st, const SharedLayout& L, const StepConsts& c) {
+  const int W = p->world, rank = p->rank;
+  const int nloc = (int)p->shape[0], Ny = (int)p->shape[1], My = Ny / 2;
+  const size_t nxg = (size_t)p->nx_global;
+  const int lines = My / W;
+  const int prev = (rank + W - 1) % W, next = (rank + 1) % W;
+  const int cur = p->dist_cur, nxt = cur ^ 1;
+  auto src3 = [&](size_t off) {
+    return SlabSrc{fptr(p->peer_shared[prev], off), fptr(p->shared, off), fptr(p->peer_shared[next], off)};
+  };
+  const unsigned long long step_id = ++p->dist_step;
+  const int parity = (int)(step_id & 1);
+  float2* Tloc = reinterpret_cast<float2*>(fptr(p->shared, L.off_T));
+  float2* Lown = reinterpret_cast<float2*>(fptr(p->shared, L.off_L[parity]));
+  static const int wish_blocks = [] { const char* e = getenv("CFD_DIST_BLOCKS"); return e ? atoi(e) : 4; }();
+  static const int wish_chunks = [] { const char* e = getenv("CFD_DIST_CHUNKS"); return e ? atoi(e) : 4; }();
+  const int TX = explicit_2d_tile_rows(1, nloc, Ny);
+  const int NB = pick_pieces(nloc, TX < 32 ? 32 : TX, wish_blocks);      // whole tiles and row-kernel CTAs
+  const int NC = pick_pieces(lines, 32, wish_chunks);
+  const int bx = nloc / NB, lc = lines / NC;
+  const int paired = p->t_paired;
+  int all[CFD_MAX_PEERS];
+  for (int r = 0; r < W; ++r) all[r] = r;
+  const int push_ctas = W <= 2 ? 24 : (W <= 4 ? 12 : 8);  // per destination rank
+
+  prof_mark(p, st, "begin");
+  // ---- neighbours' (u*, v*, q) of the previous step are complete (first step after a load: everyone's input)
+  if (p->dist_state == 1 || p->dist_nbr_epoch == 0) {
+    if (int e = barrier(p, st)) return e;
+  } else {
+    if (int e = wait_flags(p, st, L, kSlotNbr, 1, 2, p->dist_nbr_epoch, "wait_nbr")) return e;
+  }
+  // ---- stencil + row FFT block by block; each finished block is pushed to the line owners
+  for (int b = 0; b < NB; ++b) {
+    const SlabSrc none = {nullptr, nullptr, nullptr};
+    int e;
+    if (p->dist_state == 1)
+      e = launch_explicit_2d_slab(st, src3(L.off_vin[0]), src3(L.off_vin[1]), none,
+                                  fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1,
+                                  nloc, Ny, rank * nloc, (int)p->nx_global, c, 0, b * (bx / TX), bx / TX);
+    else
+      e = launch_explicit_2d_slab(st, src3(L.off_us[cur][0]), src3(L.off_us[cur][1]), src3(L.off_q[cur]),
+                                  fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1,
+                                  nloc, Ny, rank * nloc, (int)p->nx_global, c, 0, b * (bx / TX), bx / TX);
+    if (e) return e;
+    prof_mark(p, st, "explicit_2d_slab");
+    if (int e2 = launch_rfft_rows_block(st, p->lm_row, p->rhs, Tloc, 1, nloc, p->tw_row, p->rtw, paired, b * bx, bx))
+      return e2;
+    prof_mark(p, st, "rfft_rows");
+    CFD_CUDA_OK(cudaEventRecord(p->ev_blk[b], st));
+    CFD_CUDA_OK(cudaStreamWaitEvent(p->st_comm, p->ev_blk[b], 0));
+    PushDst dst;
+    for (int r = 0; r < CFD_MAX_PEERS; ++r)
+      dst.p[r] = reinterpret_cast<float2*>(fptr(p->peer_shared[r < W ? r : rank], L.off_L[parity]));
+    dim3 grid(push_ctas, W);
+    if (paired)
+      slab_push_kernel<true, true><<<grid, 256, 0, p->st_comm>>>(Tloc, dst, lines, bx, nloc, nxg, b * bx,
+                                                               rank * nloc + b * bx, 0, 0);
+    else
+      slab_push_kernel<true, false><<<grid, 256, 0, p->st_comm>>>(Tloc, dst, lines, bx, nloc, nxg, b * bx,
+                                                                rank * nloc + b * bx, 0, 0);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    if (int e3 = signal_flags(p, p->st_comm, L, W, all, kSlotFwd + rank * kMaxBlocks + b, step_id)) return e3;
+  }
+  // ---- every rank's blocks of MY lines have arrived
+  if (int e = wait_flags(p, st, L, kSlotFwd, W, NB, step_id, "wait_fwd")) return e;
+  // ---- x lines on the local line buffer, chunk by chunk; finished chunks go back to the slab owners
+  LinePeers local;  // the kernel addresses lines by their GLOBAL number
+  for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = Lown - (size_t)rank * lines * nxg;
+  int lnx = 0;
+  while (((size_t)1 << lnx) < nxg) ++lnx;
+  for (int ch = 0; ch < NC; ++ch) {
+    if (int e = launch_xlines_peers(st, p->lm_x, local, lnx, (size_t)rank * lines + (size_t)ch * lc, lc, My, p->tw_x,
+                                    p->lam[0], p->lam[1], p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
+                                    p->xscratch, p->wbig, nullptr, 0, nullptr))
+      return e;
+    prof_mark(p, st, "xlines");
+    CFD_CUDA_OK(cudaEventRecord(p->ev_chk[ch], st));
+    CFD_CUDA_OK(cudaStreamWaitEvent(p->st_comm, p->ev_chk[ch], 0));
+    PushDst dst;
+    for (int r = 0; r < CFD_MAX_PEERS; ++r)
+      dst.p[r] = reinterpret_cast<float2*>(fptr(p->peer_shared[r < W ? r : rank], L.off_T));
+    dim3 grid(push_ctas, W);
+    if (paired)
+      slab_push_kernel<false, true><<<grid, 256, 0, p->st_comm>>>(Lown, dst, lc, nloc, nloc, nxg, 0, 0, ch * lc,
+                                                                rank * lines + ch * lc);
+    else
+      slab_push_kernel<false, false><<<grid, 256, 0, p->st_comm>>>(Lown, dst, lc, nloc, nloc, nxg, 0, 0, ch * lc,
+                                                                 rank * lines + ch * lc);
+    count_launch();
+    CFD_CUDA_OK(cudaGetLastError());
+    if (int e = signal_flags(p, p->st_comm, L, W, all, kSlotBack + rank * kMaxBlocks + ch, step_id)) return e;
+  }
+  // ---- all ky lines of MY rows are back
+  if (int e = wait_flags(p, st, L, kSlotBack, W, NC, step_id, "wait_back")) return e;
+  if (int e = launch_irfft_rows(st, p->lm_row, Tloc, fptr(p->shared, L.off_q[nxt]), 1, nloc, p->tw_row, p->rtw,
+                                paired))
+    return e;
+  prof_mark(p, st, "irfft_rows");
+  // ---- tell the neighbours that this rank's (u*, v*, q) of this step are complete
+  {
+    const int nb[2] = {next, prev};  // I am `prev` of my next rank (its slot 0) and `next` of my previous (slot 1)
+    if (int e = signal_flags(p, st, L, 1, &nb[0], kSlotNbr + 0, step_id)) return e;
+    if (int e = signal_flags(p, st, L, 1, &nb[1], kSlotNbr + 1, step_id)) return e;
+  }
+  p->dist_nbr_epoch = step_id;
+  p->dist_cur = nxt;
+  p->dist_state = 2;
+  return 0;
+}
+
 }  // namespace
 }  // namespace cfd
 
@@ -222,6 +501,25 @@ int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const doub
   cudaMemset(p->shared, 0, L.total_bytes);
   p->shared_bytes = L.total_bytes;
   for (int r = 0; r < CFD_MAX_PEERS; ++r) p->peer_shared[r] = p->shared;
+  p->dist_push = (world > 1 && push_mode()) ? 1 : 0;
+  if (p->dist_push) {
+    // the x-line kernel only ever sees the plain local line buffer: the slab spectrum may take the
+    // pair-interleaved layout whenever the row kernels profit from it (rows of >= 16384 reals)
+    p->t_paired = p->lm_row >= 13 ? 1 : 0;
+    if (const char* e = getenv("CFD_T_PAIRED")) p->t_paired = atoi(e) != 0;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+    bool ok = cudaStreamCreateWithPriority(&p->st_comm, cudaStreamNonBlocking, hi) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&p->ev_blk[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p->ev_chk[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p->ev_comm_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      cfd_plan_destroy(p);
+      return set_error_msg("push-mode streams could not be created");
+    }
+  }
   if (world > 1 && staged_mode()) {
     // world blocks of (My / world) x Nloc float2 = one field's bytes (the own block stays unused)
     bool ok = cudaMalloc(&p->xstage, L.field * sizeof(float)) == cudaSuccess;
@@ -314,6 +612,14 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
   int lnloc = 0;
   while ((1 << lnloc) < nloc) ++lnloc;
   const size_t lines_per_rank = (size_t)My / p->world;
+  if (p->dist_push) {
+    for (int n = 0; n < nsteps; ++n)
+      if (int e = step_push(p, st, L, c)) return e;
+    // the caller's stream owns the plan again only when the comm stream has drained
+    CFD_CUDA_OK(cudaEventRecord(p->ev_comm_done, p->st_comm));
+    CFD_CUDA_OK(cudaStreamWaitEvent(st, p->ev_comm_done, 0));
+    return 0;
+  }
   for (int n = 0; n < nsteps; ++n) {
     const int cur = p->dist_cur, nxt = cur ^ 1;
     prof_mark(p, st, "begin");
@@ -322,13 +628,13 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
       const SlabSrc none = {nullptr, nullptr, nullptr};
       if (int e = launch_explicit_2d_slab(st, src3(L.off_vin[0]), src3(L.off_vin[1]), none,
                                           fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]),
-                                          p->rhs, 1, nloc, Ny, p->rank * nloc, (int)p->nx_global, c, 0))
+                                          p->rhs, 1, nloc, Ny, p->rank * nloc, (int)p->nx_global, c, 0, 0, -1))
         return e;
     } else {
       if (int e = launch_explicit_2d_slab(st, src3(L.off_us[cur][0]), src3(L.off_us[cur][1]),
                                           src3(L.off_q[cur]), fptr(p->shared, L.off_us[nxt][0]),
                                           fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1, nloc, Ny,
-                                          p->rank * nloc, (int)p->nx_global, c, 0))
+                                          p->rank * nloc, (int)p->nx_global, c, 0, 0, -1))
         return e;
     }
     prof_mark(p, st, "explicit_2d_slab");
@@ -384,8 +690,9 @@ int cfd_dist_store(cfd_plan* p, cfd_stream stream, float* const* v_local_out, fl
   return barrier(p, st);
 }
 
-// Per-kernel CUDA-event times of `nsteps` slab steps (aggregated by kernel name, mean per launch;
-// barrier kernels appear as "barrier").  Every rank must call it.
+// Per-phase CUDA-event times of `nsteps` slab steps, aggregated by name: milliseconds per STEP (a
+// phase that is launched block by block is summed; waits on peers appear as "barrier" / "wait_*").
+// Every rank must call it.
 int cfd_dist_profile(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_params* params,
                      int max_kernels, float* ms, const char** names, int* n_kernels) {
   if (!p || !p->shared) return set_error_msg("not a distributed plan");
@@ -419,7 +726,7 @@ int cfd_dist_profile(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
   const int n = (int)uniq.size();
   if (n_kernels) *n_kernels = n < max_kernels ? n : max_kernels;
   for (int i = 0; i < n && i < max_kernels; ++i) {
-    ms[i] = (float)(tot[i] / cnt[i]);
+    ms[i] = (float)(tot[i] / (nsteps > 0 ? nsteps : 1));
     names[i] = uniq[i];
   }
   return 0;
@@ -430,7 +737,7 @@ int cfd_dist_check(cfd_plan* p) {
   if (!p || !p->shared) return set_error_msg("not a distributed plan");
   const SharedLayout L = shared_layout((size_t)p->shape[0], (size_t)p->shape[1]);
   unsigned long long err = 0;
-  CFD_CUDA_OK(cudaMemcpy(&err, reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + 16,
+  CFD_CUDA_OK(cudaMemcpy(&err, reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + kSlotErr,
                          sizeof err, cudaMemcpyDeviceToHost));
   if (err) return set_error_msg("a slab barrier timed out (a peer rank did not arrive)");
   return 0;

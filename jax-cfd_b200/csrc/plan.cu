@@ -644,6 +644,12 @@ void cfd_plan_destroy(cfd_plan* p) {
     cudaEventDestroy(p->side.done[i]);
   }
   if (p->side.start) cudaEventDestroy(p->side.start);
+  if (p->st_comm) cudaStreamDestroy(p->st_comm);
+  for (int i = 0; i < 8; ++i) {
+    if (p->ev_blk[i]) cudaEventDestroy(p->ev_blk[i]);
+    if (p->ev_chk[i]) cudaEventDestroy(p->ev_chk[i]);
+  }
+  if (p->ev_comm_done) cudaEventDestroy(p->ev_comm_done);
   if (p->pair_graph) cudaGraphExecDestroy(p->pair_graph);
   cudaFree(p->xstage);
   if (p->ev_ready) cudaEventDestroy(p->ev_ready);
@@ -864,6 +870,37 @@ int cfd_repeated(cfd_plan* p, cfd_stream stream, float* const* v_a, float* const
   }
   // the chain reads v_a only in its first kernel, so writing the result back into v_a is safe
   return repeated_lazy(p, (cudaStream_t)stream, v_a, dst, nsteps, params);
+}
+
+// nsteps steps from v_in into v_out; v_in is never written (what an XLA FFI handler needs: operands
+// are immutable).  Lazy-capable plans chain inside the workspace; the others ping-pong between
+// v_out and one plan-owned scratch state, arranged so that the last step lands in v_out.
+int cfd_advance(cfd_plan* p, cfd_stream stream, const float* const* v_in, float* const* v_out, int nsteps,
+                const cfd_params* params) {
+  DeviceGuard guard_;
+  if (int e = check_plan(p)) return e;
+  if (!v_in || !v_out || !params) return set_error_msg("null argument");
+  if (nsteps < 1) return set_error_msg("nsteps must be >= 1");
+  for (int a = 0; a < p->ndim; ++a)
+    if (!v_in[a] || !v_out[a] || v_in[a] == v_out[a]) return set_error_msg("cfd_advance: bad buffers");
+  if (nsteps == 1) return cfd_step(p, stream, v_in, v_out, nullptr, params);
+  bool plain = !lazy_capable(p);
+  if (!plain) {
+    StepConsts c;
+    if (int e = make_consts(p, params, &c)) return e;
+    plain = has_smag(c);
+  }
+  if (!plain) return repeated_lazy(p, (cudaStream_t)stream, v_in, v_out, nsteps, params);
+  const size_t bytes = (size_t)p->batch * p->cells * sizeof(float);
+  for (int a = 0; a < p->ndim; ++a)
+    if (!p->dev_b[a]) CFD_CUDA_OK(cudaMalloc((void**)&p->dev_b[a], bytes));
+  const float* src[CFD_MAX_DIM] = {v_in[0], v_in[1], p->ndim == 3 ? v_in[2] : nullptr};
+  for (int k = 1; k <= nsteps; ++k) {
+    float* const* dst = ((nsteps - k) % 2 == 0) ? v_out : p->dev_b;
+    if (int e = cfd_step(p, stream, src, dst, nullptr, params)) return e;
+    for (int a = 0; a < p->ndim; ++a) src[a] = dst[a];
+  }
+  return 0;
 }
 
 int cfd_explicit_terms(cfd_plan* p, cfd_stream stream, const float* const* v_in,

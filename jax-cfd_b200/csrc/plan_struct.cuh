@@ -70,6 +70,12 @@ struct cfd_plan {
   cudaEvent_t ev_ready = nullptr, ev_out[CFD_MAX_PEERS] = {nullptr};
   cudaEvent_t ev_in[8][CFD_MAX_PEERS] = {{nullptr}}, ev_comp[8] = {nullptr};
   int dist_state = 0, dist_cur = 0;               // see multi_gpu.cu
+  // push mode (multi_gpu.cu): copy kernels on a high-priority stream move the transposes
+  int dist_push = 0;
+  unsigned long long dist_step = 0;       // steps taken (flag value of the per-block / per-chunk flags)
+  unsigned long long dist_nbr_epoch = 0;  // step the neighbour flags must have reached (0: use the barrier)
+  cudaStream_t st_comm = nullptr;
+  cudaEvent_t ev_blk[8] = {nullptr}, ev_chk[8] = {nullptr}, ev_comm_done = nullptr;
   // per-kernel timing
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;

@@ -42,14 +42,14 @@ namespace {
 template <int LM, int ROWS, int LEMAX, bool PAIRED>
 __global__ void __launch_bounds__(ROWS * FftPlan<LM, LEMAX, 4>::G, (ROWS * FftPlan<LM, LEMAX, 4>::G <= 512) ? 2 : 0)
 rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
-                 const float2* __restrict__ tw, const float2* __restrict__ rtw) {
+                 const float2* __restrict__ tw, const float2* __restrict__ rtw, int x_begin) {
   using P = FftPlan<LM, LEMAX, 4>;
   constexpr int M = P::M, G = P::G, E = P::E;
   constexpr int RS = row_stride(M, ROWS);
   extern __shared__ float2 smem[];
   const int tid = threadIdx.x;
   const int row = tid / G, t = tid % G;
-  const int x0 = blockIdx.x * ROWS;
+  const int x0 = x_begin + blockIdx.x * ROWS;  // rows [x_begin, x_begin + gridDim.x * ROWS)
   const size_t b = blockIdx.y;
   float2* s = smem + row * RS;
 
@@ -482,26 +482,27 @@ __global__ void divergence2d_kernel(const float* __restrict__ u, const float* __
 
 template <int LM>
 int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, int Nx,
-                       const float2* tw, const float2* rtw, int paired) {
+                       const float2* tw, const float2* rtw, int paired, int x_begin, int x_count) {
   constexpr int ROWS_MAX = rows_for(LM);
   using P = FftPlan<LM>;
   // ROWS must divide Nx
   auto go = [&](auto rows_c) -> int {
     constexpr int ROWS = decltype(rows_c)::value;
     constexpr size_t smem = (size_t)ROWS * row_stride(P::M, ROWS) * sizeof(float2);
+    if (x_begin % ROWS || x_count % ROWS) return set_error_msg("internal: row block not a multiple of the rows per CTA");
     if (rows_lemax(LM) == 5 && LM >= 5) {
       using P5 = FftPlan<LM, 5, 4>;
       auto k = rfft_rows_kernel<LM, ROWS, 5, false>;
       if (int e = set_smem(k, smem)) return e;
-      k<<<dim3(Nx / ROWS, batch), ROWS * P5::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+      k<<<dim3(x_count / ROWS, batch), ROWS * P5::G, smem, st>>>(rhs, T, Nx, tw, rtw, x_begin);
     } else if (paired) {
       auto k = rfft_rows_kernel<LM, ROWS, 4, true>;
       if (int e = set_smem(k, smem)) return e;
-      k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+      k<<<dim3(x_count / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw, x_begin);
     } else {
       auto k = rfft_rows_kernel<LM, ROWS, 4, false>;
       if (int e = set_smem(k, smem)) return e;
-      k<<<dim3(Nx / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw);
+      k<<<dim3(x_count / ROWS, batch), ROWS * P::G, smem, st>>>(rhs, T, Nx, tw, rtw, x_begin);
     }
     count_launch();
     CFD_CUDA_OK(cudaGetLastError());
@@ -639,10 +640,20 @@ int launch_irfft_rows_t(cudaStream_t st, const float2* T, float* q, int batch, i
 }  // namespace
 
 // lm_row = log2(Ny / 2)
+// x_begin / x_count: the block of rows to transform (x_count < 0: all Nx rows)
+int launch_rfft_rows_block(cudaStream_t st, int lm_row, const float* rhs, float2* T, int batch, int Nx,
+                           const float2* tw, const float2* rtw, int paired, int x_begin, int x_count) {
+  if (x_count < 0) {
+    x_begin = 0;
+    x_count = Nx;
+  }
+  CFD_DISPATCH_LM(lm_row, 4, 14,
+                  return launch_rfft_rows_t<LM_>(st, rhs, T, batch, Nx, tw, rtw, paired, x_begin, x_count));
+  return 0;
+}
 int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, int batch, int Nx,
                      const float2* tw, const float2* rtw, int paired) {
-  CFD_DISPATCH_LM(lm_row, 4, 14, return launch_rfft_rows_t<LM_>(st, rhs, T, batch, Nx, tw, rtw, paired));
-  return 0;
+  return launch_rfft_rows_block(st, lm_row, rhs, T, batch, Nx, tw, rtw, paired, 0, -1);
 }
 // lm_x = log2(Nx)
 // `scratch` / `wbig` are only needed for lm_x == 15 (32768-point lines): scratch holds

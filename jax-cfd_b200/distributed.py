@@ -57,16 +57,98 @@ def torch_exchange(blob: bytes) -> List[bytes]:
   return out
 
 
+def tcp_exchange(rank: int, world: int, addr: str = '127.0.0.1', port: int = 29655,
+                 timeout: float = 120.0) -> Callable[[bytes], List[bytes]]:
+  """A torch-free all-gather of small byte strings over TCP (standard library only): rank 0
+  listens on (addr, port), collects one blob per rank and sends every rank the full list.  All the
+  host-side communication the slab-decomposed step ever needs is one such exchange of 64-byte
+  CUDA-IPC handles at start-up."""
+  import socket
+  import struct
+  import time
+
+  def recv_exact(sock, n):
+    buf = b''
+    while len(buf) < n:
+      part = sock.recv(n - len(buf))
+      if not part:
+        raise ConnectionError('peer closed the connection during the handle exchange')
+      buf += part
+    return buf
+
+  def exchange(blob: bytes) -> List[bytes]:
+    if world == 1:
+      return [blob]
+    if rank == 0:
+      srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+      srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+      srv.bind((addr, port))
+      srv.listen(world)
+      srv.settimeout(timeout)
+      blobs, conns = {0: blob}, []
+      try:
+        while len(blobs) < world:
+          c, _ = srv.accept()
+          c.settimeout(timeout)
+          r, n = struct.unpack('!ii', recv_exact(c, 8))
+          blobs[r] = recv_exact(c, n)
+          conns.append(c)
+        out = [blobs[r] for r in range(world)]
+        payload = b''.join(struct.pack('!i', len(b)) + b for b in out)
+        for c in conns:
+          c.sendall(payload)
+      finally:
+        for c in conns:
+          c.close()
+        srv.close()
+      return out
+    deadline = time.time() + timeout
+    while True:
+      try:
+        c = socket.create_connection((addr, port), timeout=timeout)
+        break
+      except OSError:
+        if time.time() > deadline:
+          raise
+        time.sleep(0.05)
+    try:
+      c.sendall(struct.pack('!ii', rank, len(blob)) + blob)
+      out = []
+      for _ in range(world):
+        (n,) = struct.unpack('!i', recv_exact(c, 4))
+        out.append(recv_exact(c, n))
+    finally:
+      c.close()
+    return out
+
+  return exchange
+
+
+def default_exchange(rank: int, world: int) -> Callable[[bytes], List[bytes]]:
+  """torch.distributed when the caller has already initialised it (plumbing only), else the
+  torch-free TCP rendezvous on MASTER_ADDR / MASTER_PORT + 1."""
+  import os
+  import sys
+  td = sys.modules.get('torch.distributed')
+  if td is not None and td.is_available() and td.is_initialized():
+    return torch_exchange
+  return tcp_exchange(rank, world, os.environ.get('MASTER_ADDR', '127.0.0.1'),
+                      int(os.environ.get('MASTER_PORT', '29654')) + 1)
+
+
 class SlabStepper:
   """Distributed counterpart of `funcutils.repeated(equations.semi_implicit_navier_stokes(...))`."""
 
   def __init__(self, grid: grids.Grid, dt: float, density: float, viscosity: Optional[float],
                forcing=None, *, rank: int, world: int, device: int,
-               exchange: Callable[[bytes], List[bytes]] = torch_exchange):
+               exchange: Optional[Callable[[bytes], List[bytes]]] = None):
     if grid.ndim != 2:
       raise NotImplementedError('slab decomposition is implemented for 2-D grids')
     check_decomposition(grid.shape, world)
     _lib.require_device()
+    if exchange is None:
+      exchange = default_exchange(rank, world)
+    self._exchange = exchange
     self.grid, self.rank, self.world, self.device = grid, rank, world, device
     self.rows = slab_rows(grid.shape[0], rank, world)
     self.local_shape = (self.rows[1] - self.rows[0], grid.shape[1])
@@ -82,10 +164,6 @@ class SlabStepper:
     assert len(blobs) == world and all(len(b) == nb for b in blobs)
     allb = ctypes.create_string_buffer(b''.join(blobs), nb * world)
     check(lib().cfd_dist_connect(self.handle, allb))
-    local_grid = grids.Grid(self.local_shape, domain=(
-        (grid.domain[0][0] + self.rows[0] * grid.step[0], grid.domain[0][0] + self.rows[1] * grid.step[0]),
-        grid.domain[1]))
-    del local_grid
     self.params, self._keep = _engine.make_params(grid, dt, density, viscosity,
                                                   _engine.as_forcing(forcing))
     self.stream = _lib.Stream()
@@ -141,9 +219,28 @@ class SlabStepper:
     return {names[i].decode(): float(ms[i]) for i in range(nk.value)}
 
   def sync(self):
+    """Waits for the enqueued steps and raises if a device-side wait on a peer ever timed out."""
     self.stream.sync()
+    check(lib().cfd_dist_check(self.handle))
 
   def close(self):
-    if self.handle:
-      lib().cfd_plan_destroy(self.handle)
+    """Collective: every rank must call it.  The peers' kernels may still be reading this rank's
+    buffers, so the ranks meet on the host (one more exchange) before the memory is released."""
+    if getattr(self, 'handle', None):
+      try:
+        self.stream.sync()
+        if self.world > 1:
+          self._exchange(b'close')
+      finally:
+        lib().cfd_plan_destroy(self.handle)
+        self.handle = None
+
+  def __del__(self):
+    # not collective (the peers may be gone already): release without the meeting
+    h = getattr(self, 'handle', None)
+    if h and _lib._lib is not None:
+      try:
+        _lib._lib.cfd_plan_destroy(h)
+      except Exception:  # interpreter shutdown
+        pass
       self.handle = None

@@ -57,3 +57,27 @@ def test_handle_exchange_world2_gloo():
   for p in procs:
     p.join(timeout=60)
   assert sorted(res) == [(0, True), (1, True)]
+
+
+def _tcp_worker(rank, world, port, q):
+  ex = D.tcp_exchange(rank, world, '127.0.0.1', port, timeout=60)
+  first = ex(bytes([rank + 1]) * 64)
+  second = ex(b'close')  # the collective close() of SlabStepper reuses the same rendezvous
+  q.put((rank, first == [bytes([r + 1]) * 64 for r in range(world)] and second == [b'close'] * world))
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_torch_free_tcp_exchange(world):
+  """The host side of the slab decomposition without torch: one all-gather of 64-byte handles over
+  a standard-library TCP rendezvous ('ship a torch-free exchange')."""
+  import multiprocessing as mp
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = 30100 + (os.getpid() % 300) + world
+  procs = [ctx.Process(target=_tcp_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=120) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+  assert sorted(res) == [(r, True) for r in range(world)]
