@@ -49,7 +49,8 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig, const SideStreams* side, int paired, const float* dtab);
+                        const float2* wbig, const SideStreams* side, int paired, const float* dtab,
+                        const LinePeers* peers_out);
 int launch_correct_2d(cudaStream_t, const float* us, const float* vs, const float* q,
                       const float* qnext, float* uo, float* vo, int batch, int Nx, int Ny,
                       float inv_hx, float inv_hy);
@@ -127,9 +128,9 @@ __global__ void slab_wait_kernel(unsigned long long* flags, int base, int nsrc, 
   __threadfence_system();
 }
 
-// Block copy between a slab-local spectrum T[ky][x_loc] (plain or pair-interleaved) and the line
-// buffers L[line][x_global] (always plain): for every destination rank (blockIdx.y) `nlines` lines
-// of `len` points.  One float4 (two points, or one point of both lines of a pair) per thread and trip.
+// Block copy between a slab-local spectrum T[ky][x_loc] and the line buffers L[line][x_global] (same
+// layout: plain, or pair-interleaved with a pair of lines as one row): for every destination rank
+// (blockIdx.y) `nlines` rows of `len` points, one float4 per thread and trip.
 //   FWD  = true:  src = own T, lines [r * nlines, (r + 1) * nlines), points [x0, x0 + len)
 //                 dst = rank r's line buffer, line l, points [dst_x0, dst_x0 + len)
 //   FWD  = false: src = own line buffer, lines [l0, l0 + nlines), points [r * len, (r + 1) * len)
@@ -141,50 +142,24 @@ template <bool FWD, bool PAIRED>
 __global__ void __launch_bounds__(256)
 slab_push_kernel(const float2* __restrict__ src, PushDst dst, int nlines, int len, int nloc, size_t nxg,
                  int x0, int dst_x0, int l0, int dst_l0) {
+  static_assert(!PAIRED, "both buffers share the layout: a pair of lines is one row of twice the length");
   const int r = blockIdx.y;
   float2* __restrict__ d = dst.p[r];
-  if (!PAIRED) {
-    const int nvec = len / 2;  // float4 = two consecutive points
-    for (int l = blockIdx.x; l < nlines; l += gridDim.x) {
-      const float2* s;
-      float2* o;
-      if (FWD) {
-        s = src + ((size_t)r * nlines + l) * nloc + x0;
-        o = d + (size_t)l * nxg + dst_x0;
-      } else {
-        s = src + (size_t)(l0 + l) * nxg + (size_t)r * len;
-        o = d + (size_t)(dst_l0 + l) * nloc;
-      }
-      const float4* s4 = reinterpret_cast<const float4*>(s);
-      float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll 4
-      for (int i = threadIdx.x; i < nvec; i += 256) o4[i] = __ldcs(s4 + i);
+  const int nvec = len / 2;  // float4 = two consecutive points
+  for (int l = blockIdx.x; l < nlines; l += gridDim.x) {
+    const float2* s;
+    float2* o;
+    if (FWD) {
+      s = src + ((size_t)r * nlines + l) * nloc + x0;
+      o = d + (size_t)l * nxg + dst_x0;
+    } else {
+      s = src + (size_t)(l0 + l) * nxg + (size_t)r * len;
+      o = d + (size_t)(dst_l0 + l) * nloc;
     }
-  } else {
-    // T is pair-interleaved: T[(ky >> 1)][x][ky & 1]; a thread moves point x of both lines of a pair
-    for (int lp = blockIdx.x; lp < nlines / 2; lp += gridDim.x) {
-      if (FWD) {
-        const size_t pair = ((size_t)r * nlines) / 2 + lp;
-        const float4* s4 = reinterpret_cast<const float4*>(src + (pair * nloc + x0) * 2);
-        float2* o0 = d + (size_t)(2 * lp) * nxg + dst_x0;
-        float2* o1 = o0 + nxg;
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll 4
-        for (int i = threadIdx.x; i < len; i += 256) {
-          const float4 v = __ldcs(s4 + i);
-          o0[i] = make_float2(v.x, v.y);
-          o1[i] = make_float2(v.z, v.w);
-        }
-      } else {
-        const float2* s0 = src + (size_t)(l0 + 2 * lp) * nxg + (size_t)r * len;
-        const float2* s1 = s0 + nxg;
-        float4* o4 = reinterpret_cast<float4*>(d + ((size_t)((dst_l0 >> 1) + lp) * nloc) * 2);
-#pragma unroll 4
-        for (int i = threadIdx.x; i < len; i += 256) {
-          const float2 a = __ldcs(s0 + i), b = __ldcs(s1 + i);
-          o4[i] = make_float4(a.x, a.y, b.x, b.y);
-        }
-      }
-    }
+    for (int i = threadIdx.x; i < nvec; i += 256) o4[i] = __ldcs(s4 + i);
   }
 }
 
@@ -202,9 +177,10 @@ SharedLayout shared_layout(size_t nloc, size_t ny) {
     for (int a = 0; a < 2; ++a) { L.off_us[s][a] = o; o += L.field; }
   for (int s = 0; s < 2; ++s) { L.off_q[s] = o; o += L.field; }
   L.off_T = o; o += L.field;  // My * Nloc float2 = Nloc * Ny floats
-  // line buffers of the push mode: (My / world) lines of Nx_global points = one field each,
-  // double buffered across steps
-  for (int s = 0; s < 2; ++s) { L.off_L[s] = o; o += L.field; }
+  // receive buffers of the push mode: one block of (My / world) lines x Nloc points per source
+  // rank (the own slot stays unused) = one field
+  L.off_L[0] = o; o += L.field;
+  L.off_L[1] = L.off_L[0];
   L.off_flags = o; o += 2 * kFlagSlots;  // kFlagSlots 8-byte flags
   L.total_bytes = o * sizeof(float);
   return L;
@@ -296,7 +272,7 @@ int xpass_staged(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int lnloc)
     prof_mark(p, st, "xwait_in");
     if (int e = launch_xlines_peers(st, p->lm_x, tab, lnloc, gl0 + lb, chunk, My, p->tw_x, p->lam[0],
                                     p->lam[1], p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
-                                    p->xscratch, p->wbig, nullptr, p->t_paired, nullptr))
+                                    p->xscratch, p->wbig, nullptr, p->t_paired, nullptr, nullptr))
       return e;
     CFD_CUDA_OK(cudaEventRecord(p->ev_comp[c], st));
     prof_mark(p, st, "xchunk");
@@ -313,6 +289,115 @@ int xpass_staged(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int lnloc)
     CFD_CUDA_OK(cudaStreamWaitEvent(st, p->ev_out[r], 0));
   }
   return 0;
+}
+
+// ---- the same block copies with the TMA (bulk asynchronous copies, SASS UBLKCP) -----------------------
+// One thread per CTA drives a ring of shared-memory stages: cp.async.bulk global -> shared (completion
+// on an mbarrier), then cp.async.bulk shared -> global (local HBM or the peer's memory over NVLink).
+// Megabytes stay in flight per CTA-sized footprint of 32 threads, so a few dozen CTAs saturate
+// NVLink while the SMs keep computing -- the LSU-driven slab_push_kernel above needed the whole GPU
+// for that (scripts/ubench/p2p.cu: 650 GB/s with >= 148 CTAs, 200 GB/s with 48).
+// A "row" is a line (plain layout) or a pair of lines (pair-interleaved layout): both buffers use
+// the same layout in push mode, so every piece is one contiguous run of bytes.
+struct TmaPush {
+  const char* src;          // + r * src_rank_stride + row * src_row_stride
+  char* dst[CFD_MAX_PEERS]; // + row * dst_row_stride
+  size_t src_rank_stride, src_row_stride, dst_row_stride;
+  int nrows;
+  unsigned row_bytes, chunk_bytes;  // chunk_bytes divides row_bytes, multiple of 16
+};
+constexpr int kTmaStages = 6;
+constexpr unsigned kTmaChunk = 16384;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(32) slab_push_tma_kernel(TmaPush a) {
+  extern __shared__ __align__(128) unsigned char stage_mem[];
+  __shared__ __align__(8) unsigned long long full[kTmaStages];
+  if (threadIdx.x != 0) return;
+  const int r = blockIdx.y;
+  const char* src = a.src + (size_t)r * a.src_rank_stride;
+  char* dst = a.dst[r];
+  if (dst == nullptr) return;  // nothing to send to this rank (itself)
+  const unsigned cpr = a.row_bytes / a.chunk_bytes;
+  const long long nitems = (long long)a.nrows * cpr;
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long mine = first < nitems ? (nitems - first + stride - 1) / stride : 0;
+  for (int s = 0; s < kTmaStages; ++s)
+    asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(smem_u32(&full[s])) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  auto src_of = [&](long long it) {
+    const long long item = first + it * stride;
+    return src + (size_t)(item / cpr) * a.src_row_stride + (size_t)(item % cpr) * a.chunk_bytes;
+  };
+  auto dst_of = [&](long long it) {
+    const long long item = first + it * stride;
+    return dst + (size_t)(item / cpr) * a.dst_row_stride + (size_t)(item % cpr) * a.chunk_bytes;
+  };
+  auto load = [&](long long it) {
+    const int s = (int)(it % kTmaStages);
+    const unsigned bar = smem_u32(&full[s]);
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(a.chunk_bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(stage_mem + (size_t)s * kTmaChunk)),
+                 "l"(src_of(it)), "r"(a.chunk_bytes), "r"(bar)
+                 : "memory");
+  };
+  // prologue: fill the ring
+  for (long long it = 0; it < mine && it < kTmaStages; ++it) load(it);
+  for (long long it = 0; it < mine; ++it) {
+    const int s = (int)(it % kTmaStages);
+    const unsigned bar = smem_u32(&full[s]), parity = (unsigned)((it / kTmaStages) & 1);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_of(it)),
+                 "r"(smem_u32(stage_mem + (size_t)s * kTmaChunk)), "r"(a.chunk_bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    // the stage of the PREVIOUS item is free once its store has read shared memory: refill it
+    if (it >= 1 && it - 1 + kTmaStages < mine) {
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      load(it - 1 + kTmaStages);
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes performed before the kernel ends
+}
+
+// CFD_DIST_COPY=lsu selects slab_push_kernel instead
+bool tma_copies() {
+  static const bool v = [] {
+    const char* e = getenv("CFD_DIST_COPY");
+    return !(e && strcmp(e, "lsu") == 0);
+  }();
+  return v;
+}
+
+int launch_push_tma(cudaStream_t st, const TmaPush& a, int ctas, int world) {
+  static bool attr = false;
+  constexpr int smem = kTmaStages * (int)kTmaChunk;
+  if (!attr) {
+    CFD_CUDA_OK(cudaFuncSetAttribute(slab_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  slab_push_tma_kernel<<<dim3(ctas, world), 32, smem, st>>>(a);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+unsigned pick_chunk(unsigned row_bytes) {
+  unsigned c = row_bytes < kTmaChunk ? row_bytes : kTmaChunk;
+  while (row_bytes % c) c -= 16;
+  return c;
 }
 
 int signal_flags(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int ntargets, const int* targets,
@@ -346,10 +431,16 @@ int pick_pieces(int total, int unit, int wish) {
 }
 
 // One step in push mode (see the header).  cur / nxt: ping-pong slots of (u*, v*, q).
+//
+// Forward transpose: every finished row block is stored by the TMA copy kernel (comm stream) into
+// the line owners' receive buffers R_s[rank] (layout of the slab spectrum, lines of s only), overlapping
+// the stencil / row FFT of the next block.  The x-line kernel then READS only local memory (its own
+// spectrum + the receive buffers, through the peer table) and WRITES its results straight into the
+// slab owners' spectra -- posted NVLink stores that drain while other CTAs compute -- so the
+// backward transpose needs neither a copy nor a buffer; one flag per rank says "my lines are back".
 int step_push(cfd_plan* p, cudaStream_t st, const SharedLayout& L, const StepConsts& c) {
   const int W = p->world, rank = p->rank;
   const int nloc = (int)p->shape[0], Ny = (int)p->shape[1], My = Ny / 2;
-  const size_t nxg = (size_t)p->nx_global;
   const int lines = My / W;
   const int prev = (rank + W - 1) % W, next = (rank + 1) % W;
   const int cur = p->dist_cur, nxt = cur ^ 1;
@@ -357,19 +448,23 @@ int step_push(cfd_plan* p, cudaStream_t st, const SharedLayout& L, const StepCon
     return SlabSrc{fptr(p->peer_shared[prev], off), fptr(p->shared, off), fptr(p->peer_shared[next], off)};
   };
   const unsigned long long step_id = ++p->dist_step;
-  const int parity = (int)(step_id & 1);
   float2* Tloc = reinterpret_cast<float2*>(fptr(p->shared, L.off_T));
-  float2* Lown = reinterpret_cast<float2*>(fptr(p->shared, L.off_L[parity]));
-  static const int wish_blocks = [] { const char* e = getenv("CFD_DIST_BLOCKS"); return e ? atoi(e) : 4; }();
-  static const int wish_chunks = [] { const char* e = getenv("CFD_DIST_CHUNKS"); return e ? atoi(e) : 4; }();
+  static const int env_blocks = [] { const char* e = getenv("CFD_DIST_BLOCKS"); return e ? atoi(e) : 0; }();
+  const int wish_blocks = env_blocks > 0 ? env_blocks : (W <= 2 ? 2 : 4);
   const int TX = explicit_2d_tile_rows(1, nloc, Ny);
-  const int NB = pick_pieces(nloc, TX < 32 ? 32 : TX, wish_blocks);      // whole tiles and row-kernel CTAs
-  const int NC = pick_pieces(lines, 32, wish_chunks);
-  const int bx = nloc / NB, lc = lines / NC;
+  const int NB = pick_pieces(nloc, TX < 32 ? 32 : TX, wish_blocks);  // whole tiles and row-kernel CTAs
+  const int bx = nloc / NB;
   const int paired = p->t_paired;
+  const size_t esz = paired ? 16 : 8;                 // bytes per point of a row (line or line pair)
+  const int nrows = paired ? lines / 2 : lines;       // rows per rank
+  const size_t blk = (size_t)lines * nloc;            // float2 per (owner, source) receive buffer
   int all[CFD_MAX_PEERS];
   for (int r = 0; r < W; ++r) all[r] = r;
-  const int push_ctas = W <= 2 ? 24 : (W <= 4 ? 12 : 8);  // per destination rank
+  static const int wish_ctas = [] { const char* e = getenv("CFD_DIST_COPY_CTAS"); return e ? atoi(e) : 0; }();
+  const int tma_ctas = wish_ctas > 0 ? wish_ctas : (W <= 2 ? 8 : (W <= 4 ? 6 : 4));  // per destination rank
+  auto recv = [&](int owner, int source) {  // R_owner[source]
+    return reinterpret_cast<float2*>(fptr(p->peer_shared[owner], L.off_L[0])) + (size_t)source * blk;
+  };
 
   prof_mark(p, st, "begin");
   // ---- neighbours' (u*, v*, q) of the previous step are complete (first step after a load: everyone's input)
@@ -378,70 +473,68 @@ int step_push(cfd_plan* p, cudaStream_t st, const SharedLayout& L, const StepCon
   } else {
     if (int e = wait_flags(p, st, L, kSlotNbr, 1, 2, p->dist_nbr_epoch, "wait_nbr")) return e;
   }
-  // ---- stencil + row FFT block by block; each finished block is pushed to the line owners
+  // ---- stencil + row FFT block by block; each finished block is pushed to the line owners.
+  // The stencil is split like the row FFT (measured on 2 x 8192^2: one stencil launch 0.42 ms, four
+  // 0.50 ms, but with a single launch the first push starts 0.4 ms later and the step is 0.2 ms
+  // longer); CFD_DIST_STENCIL_PARTS overrides the number of stencil launches.
+  static const int wish_parts = [] { const char* e = getenv("CFD_DIST_STENCIL_PARTS"); return e ? atoi(e) : 0; }();
+  int nst = wish_parts > 0 ? (wish_parts > NB ? NB : wish_parts) : NB;
+  while (NB % nst) --nst;
+  const int bpst = NB / nst;  // row blocks per stencil launch
   for (int b = 0; b < NB; ++b) {
     const SlabSrc none = {nullptr, nullptr, nullptr};
-    int e;
-    if (p->dist_state == 1)
-      e = launch_explicit_2d_slab(st, src3(L.off_vin[0]), src3(L.off_vin[1]), none,
-                                  fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1,
-                                  nloc, Ny, rank * nloc, (int)p->nx_global, c, 0, b * (bx / TX), bx / TX);
-    else
-      e = launch_explicit_2d_slab(st, src3(L.off_us[cur][0]), src3(L.off_us[cur][1]), src3(L.off_q[cur]),
-                                  fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1,
-                                  nloc, Ny, rank * nloc, (int)p->nx_global, c, 0, b * (bx / TX), bx / TX);
-    if (e) return e;
+    int e = 0;
+    if (b % bpst == 0) {
+      const int t0 = b * (bx / TX), tn = bpst * (bx / TX);
+      if (p->dist_state == 1)
+        e = launch_explicit_2d_slab(st, src3(L.off_vin[0]), src3(L.off_vin[1]), none,
+                                    fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1,
+                                    nloc, Ny, rank * nloc, (int)p->nx_global, c, 0, t0, tn);
+      else
+        e = launch_explicit_2d_slab(st, src3(L.off_us[cur][0]), src3(L.off_us[cur][1]), src3(L.off_q[cur]),
+                                    fptr(p->shared, L.off_us[nxt][0]), fptr(p->shared, L.off_us[nxt][1]), p->rhs, 1,
+                                    nloc, Ny, rank * nloc, (int)p->nx_global, c, 0, t0, tn);
+      if (e) return e;
+    }
     prof_mark(p, st, "explicit_2d_slab");
     if (int e2 = launch_rfft_rows_block(st, p->lm_row, p->rhs, Tloc, 1, nloc, p->tw_row, p->rtw, paired, b * bx, bx))
       return e2;
     prof_mark(p, st, "rfft_rows");
     CFD_CUDA_OK(cudaEventRecord(p->ev_blk[b], st));
     CFD_CUDA_OK(cudaStreamWaitEvent(p->st_comm, p->ev_blk[b], 0));
-    PushDst dst;
+    TmaPush a;
+    a.src = reinterpret_cast<const char*>(Tloc) + (size_t)(b * bx) * esz;
+    a.nrows = nrows;
+    a.src_rank_stride = (size_t)nrows * nloc * esz;
+    a.src_row_stride = (size_t)nloc * esz;
+    a.dst_row_stride = (size_t)nloc * esz;
+    a.row_bytes = (unsigned)(bx * esz);
+    a.chunk_bytes = pick_chunk(a.row_bytes);
     for (int r = 0; r < CFD_MAX_PEERS; ++r)
-      dst.p[r] = reinterpret_cast<float2*>(fptr(p->peer_shared[r < W ? r : rank], L.off_L[parity]));
-    dim3 grid(push_ctas, W);
-    if (paired)
-      slab_push_kernel<true, true><<<grid, 256, 0, p->st_comm>>>(Tloc, dst, lines, bx, nloc, nxg, b * bx,
-                                                               rank * nloc + b * bx, 0, 0);
-    else
-      slab_push_kernel<true, false><<<grid, 256, 0, p->st_comm>>>(Tloc, dst, lines, bx, nloc, nxg, b * bx,
-                                                                rank * nloc + b * bx, 0, 0);
-    count_launch();
-    CFD_CUDA_OK(cudaGetLastError());
+      a.dst[r] = (r < W && r != rank) ? reinterpret_cast<char*>(recv(r, rank)) + (size_t)(b * bx) * esz : nullptr;
+    if (int e4 = launch_push_tma(p->st_comm, a, tma_ctas, W)) return e4;
     if (int e3 = signal_flags(p, p->st_comm, L, W, all, kSlotFwd + rank * kMaxBlocks + b, step_id)) return e3;
   }
   // ---- every rank's blocks of MY lines have arrived
   if (int e = wait_flags(p, st, L, kSlotFwd, W, NB, step_id, "wait_fwd")) return e;
-  // ---- x lines on the local line buffer, chunk by chunk; finished chunks go back to the slab owners
-  LinePeers local;  // the kernel addresses lines by their GLOBAL number
-  for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = Lown - (size_t)rank * lines * nxg;
-  int lnx = 0;
-  while (((size_t)1 << lnx) < nxg) ++lnx;
-  for (int ch = 0; ch < NC; ++ch) {
-    if (int e = launch_xlines_peers(st, p->lm_x, local, lnx, (size_t)rank * lines + (size_t)ch * lc, lc, My, p->tw_x,
-                                    p->lam[0], p->lam[1], p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
-                                    p->xscratch, p->wbig, nullptr, 0, nullptr))
-      return e;
-    prof_mark(p, st, "xlines");
-    CFD_CUDA_OK(cudaEventRecord(p->ev_chk[ch], st));
-    CFD_CUDA_OK(cudaStreamWaitEvent(p->st_comm, p->ev_chk[ch], 0));
-    PushDst dst;
-    for (int r = 0; r < CFD_MAX_PEERS; ++r)
-      dst.p[r] = reinterpret_cast<float2*>(fptr(p->peer_shared[r < W ? r : rank], L.off_T));
-    dim3 grid(push_ctas, W);
-    if (paired)
-      slab_push_kernel<false, true><<<grid, 256, 0, p->st_comm>>>(Lown, dst, lc, nloc, nloc, nxg, 0, 0, ch * lc,
-                                                                rank * lines + ch * lc);
-    else
-      slab_push_kernel<false, false><<<grid, 256, 0, p->st_comm>>>(Lown, dst, lc, nloc, nloc, nxg, 0, 0, ch * lc,
-                                                                 rank * lines + ch * lc);
-    count_launch();
-    CFD_CUDA_OK(cudaGetLastError());
-    if (int e = signal_flags(p, p->st_comm, L, W, all, kSlotBack + rank * kMaxBlocks + ch, step_id)) return e;
+  // ---- x lines: read locally (own spectrum + receive buffers), write to the slab owners
+  LinePeers rd, wr;
+  for (int r = 0; r < CFD_MAX_PEERS; ++r) {
+    const int q = r < W ? r : rank;
+    // the kernel addresses lines by their GLOBAL number: a receive buffer holds lines rank * L ..
+    rd.p[r] = (q == rank) ? Tloc : recv(rank, q) - (size_t)rank * blk;
+    wr.p[r] = reinterpret_cast<float2*>(fptr(p->peer_shared[q], L.off_T));
   }
+  int lnloc = 0;
+  while ((1 << lnloc) < nloc) ++lnloc;
+  if (int e = launch_xlines_peers(st, p->lm_x, rd, lnloc, (size_t)rank * lines, lines, My, p->tw_x, p->lam[0],
+                                  p->lam[1], p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm, p->xscratch,
+                                  p->wbig, &p->side, paired, nullptr, &wr))
+    return e;
+  prof_mark(p, st, "xlines");
+  if (int e = signal_flags(p, st, L, W, all, kSlotBack + rank * kMaxBlocks, step_id)) return e;
   // ---- all ky lines of MY rows are back
-  if (int e = wait_flags(p, st, L, kSlotBack, W, NC, step_id, "wait_back")) return e;
+  if (int e = wait_flags(p, st, L, kSlotBack, W, 1, step_id, "wait_back")) return e;
   if (int e = launch_irfft_rows(st, p->lm_row, Tloc, fptr(p->shared, L.off_q[nxt]), 1, nloc, p->tw_row, p->rtw,
                                 paired))
     return e;
@@ -503,10 +596,8 @@ int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const doub
   for (int r = 0; r < CFD_MAX_PEERS; ++r) p->peer_shared[r] = p->shared;
   p->dist_push = (world > 1 && push_mode()) ? 1 : 0;
   if (p->dist_push) {
-    // the x-line kernel only ever sees the plain local line buffer: the slab spectrum may take the
-    // pair-interleaved layout whenever the row kernels profit from it (rows of >= 16384 reals)
-    p->t_paired = p->lm_row >= 13 ? 1 : 0;
-    if (const char* e = getenv("CFD_T_PAIRED")) p->t_paired = atoi(e) != 0;
+    // the line buffers use the layout of the slab spectrum (plain or pair-interleaved, chosen by
+    // choose_t_paired, plan.cu), so every transposed piece is one contiguous run of bytes
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
     bool ok = cudaStreamCreateWithPriority(&p->st_comm, cudaStreamNonBlocking, hi) == cudaSuccess;
@@ -648,7 +739,7 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
     } else if (int e = launch_xlines_peers(st, p->lm_x, peers, lnloc, (size_t)p->rank * lines_per_rank,
                                            lines_per_rank, My, p->tw_x, p->lam[0], p->lam[1],
                                            p->lamf[0], p->lamf[1], p->fastd, p->cutoff, p->norm,
-                                           p->xscratch, p->wbig, &p->side, p->t_paired, nullptr)) {
+                                           p->xscratch, p->wbig, &p->side, p->t_paired, nullptr, nullptr)) {
       return e;
     }
     prof_mark(p, st, "xlines_peers");

@@ -200,7 +200,7 @@ __device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, 
 template <int LM, int LINES, bool FASTD, int LEMAX, bool SPLIT, bool DB, bool PAIRED, bool BAL = false>
 __global__ void __launch_bounds__(LINES * FftPlan<LM, LEMAX, 4>::G,
                                   (LEMAX == 5 && LINES * FftPlan<LM, LEMAX, 4>::G <= 256) ? 2 : CFD_XL_MINB)
-xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
+xlines_kernel(LinePeers peers, LinePeers peers_w, int lnloc, size_t line_begin, int My,
               const float2* __restrict__ tw, const double* __restrict__ lamx,
               const double* __restrict__ lamy, const float* __restrict__ lamxf,
               const float* __restrict__ lamyf, double cutoff, float norm,
@@ -228,15 +228,24 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   constexpr int XS = (!SPLIT && PAIRED) ? 2 : 1;
   // One GPU (lnloc == LM): plain contiguous line.  Several GPUs: peer table in shared memory (a
   // dynamically indexed kernel parameter would live in local memory).
+  // peers: where the line is READ; peers_w: where the result is WRITTEN (the same buffers in place,
+  // or -- slab decomposition, push mode -- local receive buffers in, the slab owners' spectra out)
   __shared__ float2* s_peer[CFD_MAX_PEERS];
+  __shared__ float2* s_peer_w[CFD_MAX_PEERS];
   const bool single = (lnloc == LM);
   if (!single) {
-    if (tid < CFD_MAX_PEERS) s_peer[tid] = peers.p[tid];
+    if (tid < CFD_MAX_PEERS) {
+      s_peer[tid] = peers.p[tid];
+      s_peer_w[tid] = peers_w.p[tid];
+    }
     __syncthreads();
   }
   float2* const Tl = peers.p[0] + loff;
   auto elem = [&](int x) -> float2* {
     return single ? Tl + XS * x : s_peer[x >> lnloc] + loff + XS * (x & nloc_mask);
+  };
+  auto elem_w = [&](int x) -> float2* {
+    return single ? Tl + XS * x : s_peer_w[x >> lnloc] + loff + XS * (x & nloc_mask);
   };
 
   float2 v[E];
@@ -256,7 +265,7 @@ xlines_kernel(LinePeers peers, int lnloc, size_t line_begin, int My,
   if (DB && cta_has_packed) __syncthreads();  // scale_line's reads of buffer 0 are done
   FftRun<P, +1, SyncCta, DB, (P::NP - 1) & 1, PRE>::run(v, t, s, tw, 0, ALT);
 #pragma unroll
-  for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
+  for (int e = 0; e < E; ++e) *elem_w(t + G * e) = v[e];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -522,7 +531,7 @@ int launch_rfft_rows_t(cudaStream_t st, const float* rhs, float2* T, int batch, 
 }
 
 template <int LM, int LEMAX>
-int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
+int launch_xlines_le(cudaStream_t st, const LinePeers& peers, const LinePeers& peers_w, int lnloc, size_t line_begin,
                      size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
                      const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired,
                      const float* dtab) {
@@ -535,7 +544,7 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
   if (nlines % LINES || (!split && line_begin % LINES)) return set_error_msg("internal: line count not divisible");
   auto go = [&](auto k) -> int {
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, My, tw, lamx, lamy,
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, peers_w, lnloc, line_begin, My, tw, lamx, lamy,
                                                             lamxf, lamyf, cutoff, norm, dtab);
     return 0;
   };
@@ -587,14 +596,14 @@ int launch_xlines_le(cudaStream_t st, const LinePeers& peers, int lnloc, size_t 
 }
 
 template <int LM>
-int launch_xlines_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin,
+int launch_xlines_t(cudaStream_t st, const LinePeers& peers, const LinePeers& peers_w, int lnloc, size_t line_begin,
                     size_t nlines, int My, int split, const float2* tw, const double* lamx, const double* lamy,
                     const float* lamxf, const float* lamyf, int fastd, double cutoff, float norm, int paired,
                     const float* dtab) {
   if (xlines_lemax(LM) == 5)
-    return launch_xlines_le<LM, 5>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
+    return launch_xlines_le<LM, 5>(st, peers, peers_w, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
                                    lamyf, fastd, cutoff, norm, paired, dtab);
-  return launch_xlines_le<LM, 4>(st, peers, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
+  return launch_xlines_le<LM, 4>(st, peers, peers_w, lnloc, line_begin, nlines, My, split, tw, lamx, lamy, lamxf,
                                  lamyf, fastd, cutoff, norm, paired, dtab);
 }
 
@@ -664,7 +673,9 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         size_t line_begin, size_t nlines, int My, const float2* tw,
                         const double* lamx, const double* lamy, const float* lamxf,
                         const float* lamyf, int fastd, double cutoff, float norm, float2* scratch,
-                        const float2* wbig, const SideStreams* side, int paired, const float* dtab) {
+                        const float2* wbig, const SideStreams* side, int paired, const float* dtab,
+                        const LinePeers* peers_out) {
+  const LinePeers& peers_w = peers_out ? *peers_out : peers;  // results go back in place by default
   if (lm_x == 15) {
     if (!scratch || !wbig) return set_error_msg("internal: 32768-point lines need the split scratch");
     const int half = 1 << 14;
@@ -692,13 +703,13 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
       CFD_CUDA_OK(cudaGetLastError());
       LinePeers local;
       for (int i = 0; i < CFD_MAX_PEERS; ++i) local.p[i] = sc;
-      if (int e = launch_xlines_t<14>(s, local, 14, lb, 2 * chunk, My, 1, tw, lamx, lamy, lamxf, lamyf,
+      if (int e = launch_xlines_t<14>(s, local, local, 14, lb, 2 * chunk, My, 1, tw, lamx, lamy, lamxf, lamyf,
                                       fastd, cutoff, norm, 0, dtab))
         return e;
       if (paired)
-        merge_pairs_kernel<<<pgrid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+        merge_pairs_kernel<<<pgrid, 256, 0, s>>>(peers_w, lnloc, lb, half, sc, wbig);
       else
-        merge_lines_kernel<<<grid, 256, 0, s>>>(peers, lnloc, lb, half, sc, wbig);
+        merge_lines_kernel<<<grid, 256, 0, s>>>(peers_w, lnloc, lb, half, sc, wbig);
       count_launch();
       CFD_CUDA_OK(cudaGetLastError());
     }
@@ -711,7 +722,7 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
     return 0;
   }
   CFD_DISPATCH_LM(lm_x, 4, 14,
-                  return launch_xlines_t<LM_>(st, peers, lnloc, line_begin, nlines, My, 0, tw, lamx, lamy,
+                  return launch_xlines_t<LM_>(st, peers, peers_w, lnloc, line_begin, nlines, My, 0, tw, lamx, lamy,
                                               lamxf, lamyf, fastd, cutoff, norm, paired, dtab));
   return 0;
 }
@@ -722,7 +733,7 @@ int launch_xlines(cudaStream_t st, int lm_x, float2* T, int batch, int My, const
   LinePeers peers;
   for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
   return launch_xlines_peers(st, lm_x, peers, lm_x, 0, (size_t)batch * My, My, tw, lamx, lamy, lamxf,
-                             lamyf, fastd, cutoff, norm, scratch, wbig, side, paired, dtab);
+                             lamyf, fastd, cutoff, norm, scratch, wbig, side, paired, dtab, nullptr);
 }
 int launch_divergence_generic(cudaStream_t st, const float* u, const float* v, const float* w, float* rhs,
                               int batch, int N0, int N1, int N2, float ih0, float ih1, float ih2);
