@@ -55,6 +55,7 @@ KERNEL_BYTES = {'explicit_2d': 20.0, 'explicit_2d_lazy': 24.0, 'rfft_rows': 8.0,
                 'xlines3': 8.0, 'ifft_y': 8.0, 'irfft_z': 8.0, 'correct_3d': 28.0}
 CHAIN_KERNELS = ('explicit_2d_lazy', 'rfft_rows', 'xlines', 'irfft_rows')  # one chained step
 STEP_BYTES_PER_CELL = 40.0  # 2-D, working set > L2
+STEP_BYTES_PER_CELL_3D = 52.0  # ... 3-D
 
 
 def synth_ic(shape, batch, seed, vmax, kpeak):
@@ -135,13 +136,13 @@ SLAB_SHAPES_32K = {1: (32768, 32768), 2: (32768, 32768), 4: (32768, 32768), 8: (
 
 
 def is_slab(name, world):
-  return (world > 1 and name == 'K8192') or name == 'K32768'
+  return (world > 1 and name in ('K8192', 'TGV512', 'TGV256')) or name == 'K32768'
 
 
 def workload_grid(wl, name, world):
   """(shape, domain) of the grid the arm runs at `world` GPUs -- shared by the GPU arm and the
   reference arm so that both describe the same configuration."""
-  if is_slab(name, world):
+  if is_slab(name, world) and len(wl['shape']) == 2:
     shape = (SLAB_SHAPES_32K if name == 'K32768' else SLAB_SHAPES)[world]
     if os.environ.get('CFD_SLAB_SHAPE'):  # tuning aid, e.g. CFD_SLAB_SHAPE=32768x8192
       shape = tuple(int(x) for x in os.environ['CFD_SLAB_SHAPE'].split('x'))
@@ -156,6 +157,8 @@ def gpu_config(wl, name, world):
   slab = is_slab(name, world)
   cells_per_gpu = int(np.prod(shape)) // world if slab else int(np.prod(shape)) * batch
   desc = wl['desc'] + (f' -- weak-scaled to {shape[0]}x{shape[1]}' if slab and name == 'K8192' else '')
+  if slab and len(shape) == 3:
+    desc += f' -- slab-decomposed along axis 0 over {world} GPUs (strong scaling)'
   return {'workload': f'{name}-slab' if slab and name == 'K8192' else name, 'description': desc,
           'grid': list(shape), 'batch': batch, 'cells_per_gpu': cells_per_gpu}
 
@@ -304,19 +307,81 @@ def slab_parity_check(cfd, _lib, dist, rank, world, local_rank):
   return flag[0]
 
 
+def taylor_green_slab(shape, rows):
+  """u = sin x cos y cos z, v = -cos x sin y cos z, w = 0 sampled at grid.cell_faces (SURVEY.md
+  section 8(d), TGV512) on the planes [rows) of axis 0."""
+  n0, n1, n2 = shape
+  r0, r1 = rows
+  ax = lambda n, off, lo=0, hi=None: ((np.arange(lo, n if hi is None else hi, dtype=np.float64) + off) * (TWO_PI / n))
+  xf, xc = ax(n0, 1.0, r0, r1), ax(n0, 0.5, r0, r1)
+  yf, yc = ax(n1, 1.0), ax(n1, 0.5)
+  zc = ax(n2, 0.5)
+  u = (np.sin(xf)[:, None, None] * np.cos(yc)[None, :, None] * np.cos(zc)[None, None, :]).astype(np.float32)
+  v = (-np.cos(xc)[:, None, None] * np.sin(yf)[None, :, None] * np.cos(zc)[None, None, :]).astype(np.float32)
+  return u, v, np.zeros_like(u)
+
+
+def slab_parity_check_3d(cfd, _lib, dist, rank, world, local_rank):
+  """3-D counterpart: 2 steps of a 128x128x64 Taylor-Green problem with the Smagorinsky closure
+  through SlabStepper on all ranks and through the single-GPU path on rank 0, bit for bit."""
+  shape, nsteps = (128, 128, 64), 2
+  dom = ((0.0, TWO_PI),) * 3
+  grid = cfd.grids.Grid(shape, domain=dom)
+  nu, cs = 1.0 / 1600, 0.2
+  dt = cfd.equations.stable_time_step(1.0, 0.5, nu, grid)
+  forcing = cfd._engine.ForcingFn([cfd._engine.SmagorinskyTerm(cs)])
+  st = cfd.distributed.SlabStepper(grid, dt, 1.0, nu, forcing, rank=rank, world=world, device=local_rank)
+  v0 = list(taylor_green_slab(shape, (0, shape[0])))
+  rs = np.random.RandomState(0)
+  v0 = [a + 0.05 * rs.standard_normal(shape).astype(np.float32) for a in v0]
+  r0, r1 = st.rows
+  st.load([a[r0:r1] for a in v0])
+  st.advance(nsteps)
+  outs, q = st.store(want_q=True)
+  loc = [o.numpy() for o in outs] + [q.numpy()]
+  gathered = [None] * world
+  dist.all_gather_object(gathered, loc)
+  st.close()
+  res = None
+  if rank == 0:
+    full = [np.concatenate([g[i] for g in gathered], axis=0) for i in range(4)]
+    bc = cfd.boundaries.periodic_boundary_conditions(3)
+    step = cfd.subgrid_models.explicit_smagorinsky_navier_stokes(
+        dt=dt, cs=cs, forcing=None, density=1.0, viscosity=nu, grid=grid)
+    v = tuple(cfd.grids.GridVariable(cfd.grids.GridArray(_lib.DeviceArray.from_numpy(a), o, grid), bc)
+              for a, o in zip(v0, grid.cell_faces))
+    ref, rq = step.advance(v, nsteps, return_q=True)
+    ref = [np.asarray(x.data) for x in ref] + [np.asarray(rq)]
+    bitwise = all(np.array_equal(a, b) for a, b in zip(full, ref))
+    err = max(float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
+              for a, b in zip(full, ref))
+    res = {'bitwise': bool(bitwise), 'max_rel_l2': err, 'grid': list(shape), 'steps': nsteps,
+           'against': 'single-GPU path on rank 0 (itself checked against the oracle in tests/)'}
+  flag = [res]
+  dist.broadcast_object_list(flag, src=0)
+  if not flag[0]['bitwise']:
+    raise SystemExit(f'slab-decomposed 3-D step differs from the single-GPU step: {flag[0]}')
+  return flag[0]
+
+
 def time_slab(cfd, _lib, dist, torch, wl, shape, dom, steps, warmup, rank, world, local_rank, full=True):
   """Times `steps` chained steps of the slab-decomposed grid (CUDA events on the launching stream,
   barrier + device sync both sides, max over ranks)."""
   lib = _lib.lib()
   grid = cfd.grids.Grid(shape, domain=dom)
   dt = cfd.equations.stable_time_step(wl['vmax'], 0.5, wl['nu'], grid)
-  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
-                                      cfd.forcings.linear_forcing(grid, -0.1))
+  nd = len(shape)
+  if nd == 2:
+    forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
+                                        cfd.forcings.linear_forcing(grid, -0.1))
+  else:
+    cs = wl.get('smagorinsky')
+    forcing = cfd._engine.ForcingFn([cfd._engine.SmagorinskyTerm(cs)]) if cs else None
   st = cfd.distributed.SlabStepper(grid, dt, 1.0, wl['nu'], forcing, rank=rank, world=world,
                                    device=local_rank)
-  u0, v0 = analytic_ic(shape, st.rows, wl['vmax'])
-  st.load([u0, v0])
-  del u0, v0
+  ic = analytic_ic(shape, st.rows, wl['vmax']) if nd == 2 else taylor_green_slab(shape, st.rows)
+  st.load(list(ic))
+  del ic
   out = {'cells_local': int(np.prod(st.local_shape)), 'local_shape': st.local_shape}
 
   def barrier():
@@ -348,10 +413,10 @@ def time_slab(cfd, _lib, dist, torch, wl, shape, dom, steps, warmup, rank, world
   loc = outs[0].numpy()
   if full:
     # e2e at N GPUs: every step copies the rank's slab host->device, steps once, copies it back
-    pin_in = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
-    pin_out = [_lib.PinnedArray(st.local_shape) for _ in range(2)]
-    pin_in[0].array[...] = loc
-    pin_in[1].array[...] = outs[1].numpy()
+    pin_in = [_lib.PinnedArray(st.local_shape) for _ in range(nd)]
+    pin_out = [_lib.PinnedArray(st.local_shape) for _ in range(nd)]
+    for pa, o in zip(pin_in, outs):
+      pa.array[...] = o.numpy()
     e2e_steps = 3
     barrier()
     t0 = time.perf_counter()
@@ -392,8 +457,12 @@ def run_gpu_slab(args, wl, name):
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
   lib = _lib.lib()
   _lib.check(lib.cfd_set_device(local_rank))
-  parity = slab_parity_check(cfd, _lib, dist, rank, world, local_rank) if world > 1 else None
   shape, dom = workload_grid(wl, name, world)
+  nd = len(shape)
+  if nd == 3:
+    parity = slab_parity_check_3d(cfd, _lib, dist, rank, world, local_rank) if world > 1 else None
+  else:
+    parity = slab_parity_check(cfd, _lib, dist, rank, world, local_rank) if world > 1 else None
   r = time_slab(cfd, _lib, dist, torch, wl, shape, dom, args.steps, args.warmup, rank, world, local_rank)
   # the north-star multi-GPU configuration itself (32768^2, BASELINE config #4) beside the
   # weak-scaling family member, on the same box in the same run
@@ -414,32 +483,34 @@ def run_gpu_slab(args, wl, name):
     ms_step = r['ms_total'] / args.steps
     cells = cells_local * world
     value = cells * args.steps / (r['ms_total'] * 1e-3) / 1e9
-    step_gbs = STEP_BYTES_PER_CELL * cells_local / (ms_step * 1e-3) / 1e9
+    bpc = STEP_BYTES_PER_CELL if nd == 2 else STEP_BYTES_PER_CELL_3D
+    step_gbs = bpc * cells_local / (ms_step * 1e-3) / 1e9
     # NVLink bytes per rank per step and direction: (world-1)/world of the packed spectrum
     # (4 B/cell), once to the line owners and once back
     nvl = 2 * cells_local * 4 * (world - 1) / world
     config = gpu_config(wl, name, world)
     config.update({
-        'l2_policy': 'per-GPU working set (9 fields x %.0f MB) larger than L2 (126 MB)' % (cells_local * 4 / 1e6),
+        'l2_policy': 'per-GPU working set (%d fields x %.0f MB) larger than L2 (126 MB)'
+                     % (9 if nd == 2 else 14, cells_local * 4 / 1e6),
         'parallelism': f'slab decomposition along axis 0 over {world} GPUs; halo rows and the FFT '
                        'all-to-all move over NVLink through CUDA-IPC peer mappings driven by this '
                        'library\'s own kernels; device-side flags, no NCCL on the data path'})
     line = {
         'metric': 'cell-updates/sec', 'value': value, 'unit': 'Gcell*step/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'higher_is_better': True, 'scaling': 'weak' if nd == 2 else 'strong', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': config,
         'value_kind': 'chained steps (SlabStepper.advance), state resident in HBM',
         'roofline': {'bound': 'hbm', 'kernel': 'whole step (per GPU)', 'achieved': step_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': step_gbs / peak, 'traffic': None, 'peak_source': peak_src,
-                     'bytes_per_cell_model': STEP_BYTES_PER_CELL},
+                     'bytes_per_cell_model': bpc},
         'kernel_ms_rank0': r['kern'],
         'nvlink': {'bytes_per_gpu_per_step_each_direction': nvl,
                    'lower_bound_ms_at_770GBs': nvl / 770e9 * 1e3},
         'parity': parity, 'k32768': k32,
         'cpu_baseline': None,
         'e2e': {'value': cells * r['e2e_steps'] / r['e2e_s'] / 1e9, 'unit': 'Gcell*step/s',
-                'h2d_bytes_per_step': 2 * cells * 4, 'd2h_bytes_per_step': 2 * cells * 4,
+                'h2d_bytes_per_step': nd * cells * 4, 'd2h_bytes_per_step': nd * cells * 4,
                 'steps': r['e2e_steps'], 'ms_per_step': r['e2e_s'] / r['e2e_steps'] * 1e3,
                 'api': 'SlabStepper.load(pinned numpy) / advance(1) / store(host_out=pinned numpy) on every rank'},
         'gpu_launches': int(r['launches']), 'clocks': r['clocks'],

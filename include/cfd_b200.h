@@ -172,13 +172,17 @@ int cfd_step_host(cfd_plan* plan, const float* const* v_in_host, float* const* v
 
 /* ---- slab-decomposed multi-GPU step (one process per GPU) -----------
  * The reference has no distributed solver; this is the new path for
- * BASELINE config #4.  The grid is split along axis 0; halo rows and the FFT transpose move over
- * NVLink through CUDA-IPC peer mappings inside the kernels.  Protocol per rank:
+ * BASELINE configs #4 (2-D, 32768^2) and #5 (3-D, 512^3 with the Smagorinsky closure:
+ * cfd_dist_plan_create_nd with ndim = 3).  The grid is split along axis 0; halo rows / planes and
+ * the FFT transposes move over NVLink through CUDA-IPC peer mappings inside the kernels.
+ * Protocol per rank:
  *   cfd_dist_plan_create -> cfd_dist_export (64-byte blob) -> [host all-gathers the blobs]
  *   -> cfd_dist_connect(all blobs) -> cfd_dist_load(local rows) -> cfd_dist_advance(n) ...
  *   -> cfd_dist_store(local rows).  Every rank must make the same calls (device-side barriers). */
 int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const double* step, int rank,
-                         int world, int device);
+                         int world, int device); /* 2-D */
+int cfd_dist_plan_create_nd(cfd_plan** out, int ndim, const int64_t* global_shape, const double* step,
+                            int rank, int world, int device); /* ndim = 2 or 3 */
 size_t cfd_dist_handle_bytes(void);
 int cfd_dist_export(cfd_plan* plan, void* blob);
 int cfd_dist_connect(cfd_plan* plan, const void* all_blobs);

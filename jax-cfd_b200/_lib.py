@@ -115,6 +115,9 @@ _SIGS = {
     'cfd_dist_plan_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
                                             ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int]),
+    'cfd_dist_plan_create_nd': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double),
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'cfd_dist_handle_bytes': (ctypes.c_size_t, []),
     'cfd_dist_export': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'cfd_dist_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -243,6 +243,21 @@ explicit3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
 // evaluated on both sides (13.5 face evaluations per cell vs 18 in the one-thread-per-cell kernel,
 // and ~2 global loads per cell instead of ~75).  Smagorinsky is added by smag_add3d_kernel.
 constexpr int kBY = 8, kBZ = 64, kHY = kBY + 4, kSlots = 4;
+
+// Plane i in [-N0, 2 N0) of a field that is slab-decomposed along axis 0 (multi_gpu_3d.cu): planes
+// below 0 / from N0 on live in the previous / next rank's buffer, read over NVLink through the
+// CUDA-IPC mapping.  On one GPU prev = next = own, which is the periodic wrap.
+__device__ __forceinline__ const float* slab_plane(const SlabSrc& s, int i, int N0, size_t planeN) {
+  const float* base = s.own;
+  if (i < 0) {
+    base = s.prev;
+    i += N0;
+  } else if (i >= N0) {
+    base = s.next;
+    i -= N0;
+  }
+  return base + (size_t)i * planeN;
+}
 constexpr int kHZ = kBZ + 8;  // row: [pad pad h h | 64 interior (16-byte aligned) | h h pad pad]
 constexpr int kZ0 = 4;        // column of the first interior cell
 constexpr int kPlane = kHY * kHZ;  // floats per component per slot
@@ -251,10 +266,9 @@ constexpr int kPlane = kHY * kHZ;  // floats per component per slot
 // runtime walk over the term list, 6 times per plane, is compiled out.
 template <bool HAS_FORCE>
 __global__ void __launch_bounds__(256, 4)
-explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
-                        const float* __restrict__ w, float* __restrict__ us,
+explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ us,
                         float* __restrict__ vs, float* __restrict__ ws, int N0, int N1, int N2,
-                        StepConsts c, int dvdt_mode, int TX) {
+                        StepConsts c, int dvdt_mode, int TX, int row0) {
   extern __shared__ __align__(16) float sm3[];  // [slot][comp][kHY][kHZ]
   const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
   const int tilesz = N2 / kBZ, tilesy = N1 / kBY;
@@ -262,7 +276,7 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
   const int xb = blockIdx.x / (tilesz * tilesy);
   const size_t cells = (size_t)N0 * N1 * N2;
   const size_t boff = (size_t)blockIdx.y * cells;
-  const float* f[3] = {u + boff, v + boff, w + boff};
+  const SlabSrc f[3] = {su, sv, sw};
   float* o[3] = {us + boff, vs + boff, ws + boff};
   const int j0 = tyb * kBY, k0 = tz * kBZ;
   const int i0 = xb * TX, iend = min(i0 + TX, N0);
@@ -293,17 +307,16 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
   }
   auto slot_base = [&](int plane) { return sm3 + ((plane + kSlots) & (kSlots - 1)) * (3 * kPlane); };
   auto load_plane = [&](int i) {
-    const int iw = i < 0 ? i + N0 : (i >= N0 ? i - N0 : i);
     float* dst = slot_base(i);
     if (tid < 192) {
 #pragma unroll
       for (int comp = 0; comp < 3; ++comp)
         *reinterpret_cast<float4*>(dst + comp * kPlane + ld_dst) =
-            ldg4(f[comp] + (size_t)iw * planeN + ld_src);
+            ldg4(slab_plane(f[comp], i, N0, planeN) + boff + ld_src);
     } else if (tid < 240) {
 #pragma unroll
       for (int comp = 0; comp < 3; ++comp)
-        dst[comp * kPlane + ld_dst] = __ldg(f[comp] + (size_t)iw * planeN + ld_src);
+        dst[comp * kPlane + ld_dst] = __ldg(slab_plane(f[comp], i, N0, planeN) + boff + ld_src);
     }
   };
   // value of component `comp` at plane (pa: i, pb: i+1, pm: i-1), row j + dy, column k + dz
@@ -323,11 +336,10 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
   load_plane(i0);
   load_plane(i0 + 1);
   {
-    const int iw = ((i0 - 2) % N0 + N0) % N0;
 #pragma unroll
     for (int comp = 0; comp < 3; ++comp) {
       const float2 t2 = __ldg(reinterpret_cast<const float2*>(
-          f[comp] + (size_t)iw * planeN + (size_t)(j0 + ty) * N2 + k0 + 2 * lane));
+          slab_plane(f[comp], i0 - 2, N0, planeN) + boff + (size_t)(j0 + ty) * N2 + k0 + 2 * lane));
       X[comp][1][0] = t2.x;  // will become offset -2 after the first shift
       X[comp][1][1] = t2.y;
     }
@@ -420,7 +432,7 @@ explicit3d_march_kernel(const float* __restrict__ u, const float* __restrict__ v
             if (kind == CFD_FORCE_SEPARABLE) {
               if (c.has_sep[A]) {
                 float p = 1.f;
-                if (c.sep_prof[A][0]) p = __ldg(c.sep_prof[A][0] + i);
+                if (c.sep_prof[A][0]) p = __ldg(c.sep_prof[A][0] + row0 + i);  // GLOBAL row of a slab
                 if (c.sep_prof[A][1]) p = p * __ldg(c.sep_prof[A][1] + jg);
                 if (c.sep_prof[A][2]) p = p * __ldg(c.sep_prof[A][2] + kg + col);
                 fsum += p * c.sep_scale[A];
@@ -669,22 +681,22 @@ __device__ __forceinline__ void plane_loader_offsets(int tid, int j0, int k0, in
   }
 }
 template <int NCOMP>
-__device__ __forceinline__ void load_plane_to(float* dst, const float* const* f, size_t plane_off,
-                                              int tid, int ld_src, int ld_dst) {
+__device__ __forceinline__ void load_plane_to(float* dst, const SlabSrc* f, int i, int N0, size_t planeN,
+                                              size_t boff, int tid, int ld_src, int ld_dst) {
   if (tid < 192) {
 #pragma unroll
     for (int comp = 0; comp < NCOMP; ++comp)
-      *reinterpret_cast<float4*>(dst + comp * kPlane + ld_dst) = ldg4(f[comp] + plane_off + ld_src);
+      *reinterpret_cast<float4*>(dst + comp * kPlane + ld_dst) =
+          ldg4(slab_plane(f[comp], i, N0, planeN) + boff + ld_src);
   } else if (tid < 240) {
 #pragma unroll
     for (int comp = 0; comp < NCOMP; ++comp)
-      dst[comp * kPlane + ld_dst] = __ldg(f[comp] + plane_off + ld_src);
+      dst[comp * kPlane + ld_dst] = __ldg(slab_plane(f[comp], i, N0, planeN) + boff + ld_src);
   }
 }
 
 __global__ void __launch_bounds__(256)
-smag_nut_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
-                      const float* __restrict__ w, float* __restrict__ nut, int N0, int N1, int N2,
+smag_nut_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ nut, int N0, int N1, int N2,
                       StepConsts c, int TX) {
   extern __shared__ __align__(16) float sm3[];  // [slot][comp][kHY][kHZ]
   const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
@@ -693,7 +705,7 @@ smag_nut_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
   const int xb = blockIdx.x / (tilesz * tilesy);
   const size_t cells = (size_t)N0 * N1 * N2;
   const size_t boff = (size_t)blockIdx.y * cells;
-  const float* f[3] = {u + boff, v + boff, w + boff};
+  const SlabSrc f[3] = {su, sv, sw};
   const int j0 = tyb * kBY, k0 = tz * kBZ;
   const int i0 = xb * TX, iend = min(i0 + TX, N0);
   const size_t planeN = (size_t)N1 * N2;
@@ -701,10 +713,7 @@ smag_nut_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
   int ld_src, ld_dst;
   plane_loader_offsets(tid, j0, k0, N1, N2, &ld_src, &ld_dst);
   auto slot = [&](int plane) { return sm3 + ((plane + kSlots) & (kSlots - 1)) * (3 * kPlane); };
-  auto load = [&](int i) {
-    const int iw = i < 0 ? i + N0 : (i >= N0 ? i - N0 : i);
-    load_plane_to<3>(slot(i), f, (size_t)iw * planeN, tid, ld_src, ld_dst);
-  };
+  auto load = [&](int i) { load_plane_to<3>(slot(i), f, i, N0, planeN, boff, tid, ld_src, ld_dst); };
   load(i0 - 1);
   load(i0);
   load(i0 + 1);
@@ -730,8 +739,7 @@ smag_nut_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
 }
 
 __global__ void __launch_bounds__(256)
-smag_acc_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
-                      const float* __restrict__ w, const float* __restrict__ nut,
+smag_acc_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, SlabSrc snut,
                       float* __restrict__ us, float* __restrict__ vs, float* __restrict__ ws, int N0,
                       int N1, int N2, StepConsts c, int dvdt_mode, int TX) {
   extern __shared__ __align__(16) float sm3[];  // velocity ring [slot][3][plane], then nu_t ring
@@ -742,8 +750,8 @@ smag_acc_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
   const int xb = blockIdx.x / (tilesz * tilesy);
   const size_t cells = (size_t)N0 * N1 * N2;
   const size_t boff = (size_t)blockIdx.y * cells;
-  const float* f[3] = {u + boff, v + boff, w + boff};
-  const float* fn[1] = {nut + boff};
+  const SlabSrc f[3] = {su, sv, sw};
+  const SlabSrc fn[1] = {snut};
   float* o[3] = {us + boff, vs + boff, ws + boff};
   const int j0 = tyb * kBY, k0 = tz * kBZ;
   const int i0 = xb * TX, iend = min(i0 + TX, N0);
@@ -754,9 +762,8 @@ smag_acc_march_kernel(const float* __restrict__ u, const float* __restrict__ v,
   auto slot = [&](int plane) { return sm3 + ((plane + kSlots) & (kSlots - 1)) * (3 * kPlane); };
   auto nslot = [&](int plane) { return smn + ((plane + kSlots) & (kSlots - 1)) * kPlane; };
   auto load = [&](int i) {
-    const int iw = i < 0 ? i + N0 : (i >= N0 ? i - N0 : i);
-    load_plane_to<3>(slot(i), f, (size_t)iw * planeN, tid, ld_src, ld_dst);
-    load_plane_to<1>(nslot(i), fn, (size_t)iw * planeN, tid, ld_src, ld_dst);
+    load_plane_to<3>(slot(i), f, i, N0, planeN, boff, tid, ld_src, ld_dst);
+    load_plane_to<1>(nslot(i), fn, i, N0, planeN, boff, tid, ld_src, ld_dst);
   };
   load(i0 - 1);
   load(i0);
@@ -885,24 +892,32 @@ bool smag_uses_tiles(int N0, int N1, int N2) {
   return v && explicit_3d_uses_march(N0, N1, N2);
 }
 
+// nu_t of a slab (or, with prev = next = own, of a whole periodic grid) by the plane-marching kernel
+int launch_smag_nut_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw, float* nut, int batch, int N0,
+                            int N1, int N2, const StepConsts& c) {
+  if (!explicit_3d_uses_march(N0, N1, N2)) return set_error_msg("slab needs N1 % 8 == 0, N2 % 64 == 0, >= 4 planes");
+  const int TX = march_tx(batch, N0, N1, N2);
+  constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CFD_CUDA_OK(cudaFuncSetAttribute(smag_nut_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    attr_set = true;
+  }
+  dim3 g((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
+  smag_nut_march_kernel<<<g, 256, smem, st>>>(su, sv, sw, nut, N0, N1, N2, c, TX);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // sfield != nullptr: 6 strain fields of batch * cells floats each (strain-field path)
 int launch_smag_nut_3d(cudaStream_t st, const float* u, const float* v, const float* w, float* nut,
                        float* sfield, int batch, int N0, int N1, int N2, const StepConsts& c) {
   const size_t cells = (size_t)N0 * N1 * N2;
   if (!sfield && smag_uses_tiles(N0, N1, N2)) {
-    const int TX = march_tx(batch, N0, N1, N2);
-    constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      CFD_CUDA_OK(cudaFuncSetAttribute(smag_nut_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-      attr_set = true;
-    }
-    dim3 g((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
-    smag_nut_march_kernel<<<g, 256, smem, st>>>(u, v, w, nut, N0, N1, N2, c, TX);
-    count_launch();
-    CFD_CUDA_OK(cudaGetLastError());
-    return 0;
+    const SlabSrc su = {u, u, u}, sv = {v, v, v}, sw = {w, w, w};
+    return launch_smag_nut_3d_slab(st, su, sv, sw, nut, batch, N0, N1, N2, c);
   }
   dim3 grid((unsigned)((cells + 127) / 128), batch);
   if (sfield) {
@@ -933,42 +948,62 @@ bool explicit_3d_uses_march(int N0, int N1, int N2) {
   return use_march && N1 % kBY == 0 && N2 % kBZ == 0 && N0 >= 4;
 }
 
+// the marching stencil on a slab (row0 = first GLOBAL plane of the slab, for the forcing profiles)
+int launch_explicit_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw, float* us, float* vs, float* ws,
+                            int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode, int row0) {
+  if (!explicit_3d_uses_march(N0, N1, N2)) return set_error_msg("slab needs N1 % 8 == 0, N2 % 64 == 0, >= 4 planes");
+  const int TX = march_tx(batch, N0, N1, N2);
+  constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
+  bool has_force = false;  // a non-zero forcing sum (an all-Smagorinsky list adds +0 here)
+  for (int t = 0; t < c.n_terms; ++t) has_force = has_force || c.term_kind[t] != CFD_FORCE_SMAGORINSKY;
+  if (has_force)
+    explicit3d_march_kernel<true><<<grid, 256, smem, st>>>(su, sv, sw, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX, row0);
+  else
+    explicit3d_march_kernel<false><<<grid, 256, smem, st>>>(su, sv, sw, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX, row0);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// u* += scale * (-div tau) on a slab: velocity and nu_t halo planes come from the neighbouring ranks
+int launch_smag_acc_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw, SlabSrc snut, float* us,
+                            float* vs, float* ws, int batch, int N0, int N1, int N2, const StepConsts& c,
+                            int dvdt_mode) {
+  if (!explicit_3d_uses_march(N0, N1, N2)) return set_error_msg("slab needs N1 % 8 == 0, N2 % 64 == 0, >= 4 planes");
+  const int TX = march_tx(batch, N0, N1, N2);
+  constexpr size_t smem2 = (size_t)kSlots * 4 * kPlane * sizeof(float);
+  static bool attr2_set = false;
+  if (!attr2_set) {
+    CFD_CUDA_OK(cudaFuncSetAttribute(smag_acc_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem2));
+    attr2_set = true;
+  }
+  dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
+  smag_acc_march_kernel<<<grid, 256, smem2, st>>>(su, sv, sw, snut, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const float* w,
                        const float* nut, const float* sfield, float* us, float* vs, float* ws,
                        int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode) {
   const size_t cells = (size_t)N0 * N1 * N2;
   if (explicit_3d_uses_march(N0, N1, N2)) {
-    const int TX = march_tx(batch, N0, N1, N2);
-    constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
-    dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
-    bool has_force = false;  // a non-zero forcing sum (an all-Smagorinsky list adds +0 here)
-    for (int t = 0; t < c.n_terms; ++t) has_force = has_force || c.term_kind[t] != CFD_FORCE_SMAGORINSKY;
-    if (has_force)
-      explicit3d_march_kernel<true><<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
-    else
-      explicit3d_march_kernel<false><<<grid, 256, smem, st>>>(u, v, w, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
-    count_launch();
-    CFD_CUDA_OK(cudaGetLastError());
+    const SlabSrc su = {u, u, u}, sv = {v, v, v}, sw = {w, w, w};
+    if (int e = launch_explicit_3d_slab(st, su, sv, sw, us, vs, ws, batch, N0, N1, N2, c, dvdt_mode, 0)) return e;
     if (nut && !sfield && smag_uses_tiles(N0, N1, N2)) {
-      constexpr size_t smem2 = (size_t)kSlots * 4 * kPlane * sizeof(float);
-      static bool attr2_set = false;
-      if (!attr2_set) {
-        CFD_CUDA_OK(cudaFuncSetAttribute(smag_acc_march_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        attr2_set = true;
-      }
-      smag_acc_march_kernel<<<grid, 256, smem2, st>>>(u, v, w, nut, us, vs, ws, N0, N1, N2, c, dvdt_mode,
-                                                     TX);
-      count_launch();
-      CFD_CUDA_OK(cudaGetLastError());
+      const SlabSrc sn = {nut, nut, nut};
+      if (int e = launch_smag_acc_3d_slab(st, su, sv, sw, sn, us, vs, ws, batch, N0, N1, N2, c, dvdt_mode)) return e;
     } else if (nut && sfield) {
       dim3 g2((unsigned)((cells + 127) / 128), batch);
       Sf si;

@@ -190,12 +190,11 @@ float* fptr(void* base, size_t off) { return reinterpret_cast<float*>(base) + of
 
 int barrier(cfd_plan* p, cudaStream_t st) {
   if (p->world == 1) return 0;
-  const SharedLayout L = shared_layout((size_t)p->shape[0], (size_t)p->shape[1]);
   FlagPeers fp;
   for (int r = 0; r < CFD_MAX_PEERS; ++r)
-    fp.p[r] = reinterpret_cast<unsigned long long*>(fptr(p->peer_shared[r < p->world ? r : p->rank], L.off_flags));
+    fp.p[r] = reinterpret_cast<unsigned long long*>(fptr(p->peer_shared[r < p->world ? r : p->rank], p->flags_off));
   p->epoch += 1;
-  unsigned long long* err = reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + kSlotErr;
+  unsigned long long* err = reinterpret_cast<unsigned long long*>(fptr(p->shared, p->flags_off)) + kSlotErr;
   slab_barrier_kernel<<<1, 32, 0, st>>>(fp, p->rank, p->world, p->epoch, err, spin_budget());
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
@@ -552,11 +551,22 @@ int step_push(cfd_plan* p, cudaStream_t st, const SharedLayout& L, const StepCon
 }
 
 }  // namespace
+
+int slab_barrier(cfd_plan* p, cudaStream_t st) { return barrier(p, st); }
+size_t slab_flag_floats() { return 2 * (size_t)kFlagSlots; }
+
 }  // namespace cfd
 
 using namespace cfd;
 
 extern "C" {
+
+int cfd_dist_plan_create_nd(cfd_plan** out, int ndim, const int64_t* global_shape, const double* step, int rank,
+                            int world, int device) {
+  if (ndim == 3) return dist3_plan_create(out, global_shape, step, rank, world, device);
+  if (ndim != 2) return set_error_msg("cfd_dist_plan_create_nd: ndim must be 2 or 3");
+  return cfd_dist_plan_create(out, global_shape, step, rank, world, device);
+}
 
 int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const double* step, int rank,
                          int world, int device) {
@@ -593,6 +603,7 @@ int cfd_dist_plan_create(cfd_plan** out, const int64_t* global_shape, const doub
   }
   cudaMemset(p->shared, 0, L.total_bytes);
   p->shared_bytes = L.total_bytes;
+  p->flags_off = L.off_flags;
   for (int r = 0; r < CFD_MAX_PEERS; ++r) p->peer_shared[r] = p->shared;
   p->dist_push = (world > 1 && push_mode()) ? 1 : 0;
   if (p->dist_push) {
@@ -669,6 +680,7 @@ int cfd_dist_connect(cfd_plan* p, const void* all_blobs) {
 int cfd_dist_load(cfd_plan* p, cfd_stream stream, const float* const* v_local) {
   if (!p || !p->shared) return set_error_msg("not a distributed plan");
   CFD_CUDA_OK(cudaSetDevice(p->device));
+  if (p->ndim == 3) return dist3_load(p, (cudaStream_t)stream, v_local);
   const SharedLayout L = shared_layout((size_t)p->shape[0], (size_t)p->shape[1]);
   for (int a = 0; a < 2; ++a)
     CFD_CUDA_OK(cudaMemcpyAsync(fptr(p->shared, L.off_vin[a]), v_local[a], L.field * sizeof(float),
@@ -685,6 +697,7 @@ int cfd_dist_advance(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
   cudaStream_t st = (cudaStream_t)stream;
   StepConsts c;
   if (int e = make_consts(p, params, &c)) return e;
+  if (p->ndim == 3) return dist3_advance(p, st, nsteps, c);
   for (int t = 0; t < c.n_terms; ++t) {
     if (c.term_kind[t] == CFD_FORCE_FIELD && p->world > 1)
       return set_error_msg("field forcing is not supported on slab-decomposed grids");
@@ -759,6 +772,7 @@ int cfd_dist_store(cfd_plan* p, cfd_stream stream, float* const* v_local_out, fl
   if (p->dist_state == 0) return set_error_msg("cfd_dist_store: no state loaded");
   CFD_CUDA_OK(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->ndim == 3) return dist3_store(p, st, v_local_out, q_local_out);
   const int nloc = (int)p->shape[0], Ny = (int)p->shape[1];
   const SharedLayout L = shared_layout((size_t)nloc, (size_t)Ny);
   if (p->dist_state == 1) {
@@ -826,9 +840,8 @@ int cfd_dist_profile(cfd_plan* p, cfd_stream stream, int nsteps, const cfd_param
 // 0 when no barrier ever timed out
 int cfd_dist_check(cfd_plan* p) {
   if (!p || !p->shared) return set_error_msg("not a distributed plan");
-  const SharedLayout L = shared_layout((size_t)p->shape[0], (size_t)p->shape[1]);
   unsigned long long err = 0;
-  CFD_CUDA_OK(cudaMemcpy(&err, reinterpret_cast<unsigned long long*>(fptr(p->shared, L.off_flags)) + kSlotErr,
+  CFD_CUDA_OK(cudaMemcpy(&err, reinterpret_cast<unsigned long long*>(fptr(p->shared, p->flags_off)) + kSlotErr,
                          sizeof err, cudaMemcpyDeviceToHost));
   if (err) return set_error_msg("a slab barrier timed out (a peer rank did not arrive)");
   return 0;

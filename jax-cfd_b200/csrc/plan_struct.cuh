@@ -62,6 +62,7 @@ struct cfd_plan {
   size_t shared_bytes = 0;
   void* peer_shared[CFD_MAX_PEERS] = {nullptr};  // peers' `shared` mapped here (own entry = shared)
   unsigned long long epoch = 0;                   // barrier generation
+  size_t flags_off = 0;                           // float offset of the flag block inside `shared`
   // staged transpose (multi_gpu.cu): the peers' blocks of this rank's ky lines are copied into
   // local buffers by the copy engines, chunk by chunk (one in / one out stream per peer), while
   // the x-line kernel works on the previous chunk
@@ -89,4 +90,14 @@ int make_consts(const cfd_plan* p, const cfd_params* prm, StepConsts* c);
 // (re)builds the tables that depend on the x extent for a slab plan: x-line twiddles, lambda_x,
 // fast-path flag and the 1/(2 Nx Ny) normalisation, from the GLOBAL shape
 int plan_tables_create(cfd_plan* p, int ndim, const int64_t* global_shape, const double* step);
+// multi_gpu.cu: all-to-all flag barrier of the ranks of a slab plan, enqueued on `st`; size of the
+// flag block every slab plan keeps at flags_off
+int slab_barrier(cfd_plan* p, cudaStream_t st);
+size_t slab_flag_floats();
+// multi_gpu_3d.cu: the slab-decomposed 3-D step behind the cfd_dist_* entry points
+int dist3_plan_create(cfd_plan** out, const int64_t* global_shape, const double* step, int rank, int world,
+                      int device);
+int dist3_load(cfd_plan* p, cudaStream_t st, const float* const* v_local);
+int dist3_advance(cfd_plan* p, cudaStream_t st, int nsteps, const StepConsts& c);
+int dist3_store(cfd_plan* p, cudaStream_t st, float* const* v_local_out, float* q_local_out);
 }  // namespace cfd

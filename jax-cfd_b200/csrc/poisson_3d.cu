@@ -188,7 +188,7 @@ cfft_lines_gather_kernel(const float2* __restrict__ B, float2* __restrict__ A, i
 // ---- X: lines B[line][0..M) with line = (b * (Mz + 1) + kz) * N1 + ky : fwd * D * inv in place ---------
 template <int LM, int LINES, bool FASTD>
 __global__ void __launch_bounds__(LINES * FftPlan<LM>::G)
-xlines3_kernel(float2* __restrict__ T, int N1, int NZP, const float2* __restrict__ tw,
+xlines3_kernel(LinePeers peers, int lnloc, size_t line_begin, int N1, int NZP, const float2* __restrict__ tw,
                const double* __restrict__ lamx, const double* __restrict__ lamy,
                const double* __restrict__ lamz, const float* __restrict__ lamxf,
                const float* __restrict__ lamyf, const float* __restrict__ lamzf, double cutoff,
@@ -199,14 +199,29 @@ xlines3_kernel(float2* __restrict__ T, int N1, int NZP, const float2* __restrict
   extern __shared__ float2 smem[];
   const int tid = threadIdx.x;
   const int ln = tid / G, t = tid % G;
-  const size_t line = (size_t)blockIdx.x * LINES + ln;
+  const size_t line = line_begin + (size_t)blockIdx.x * LINES + ln;
   const int ky = (int)(line % N1);
   const int kz = (int)((line / N1) % NZP);
   float2* s = smem + ln * RS;
-  float2* Tl = T + line * M;
+  // One GPU (lnloc == LM): the line is contiguous.  Slab decomposition: element x of the line lives
+  // in rank x >> lnloc, at [line][x & (Nloc - 1)] of its slab spectrum -- the all-to-all transposes
+  // of the distributed FFT are this kernel's loads and stores (peer table in shared memory: a
+  // dynamically indexed kernel parameter would live in local memory).
+  __shared__ float2* s_peer[CFD_MAX_PEERS];
+  const bool single = (lnloc == LM);
+  if (!single) {
+    if (tid < CFD_MAX_PEERS) s_peer[tid] = peers.p[tid];
+    __syncthreads();
+  }
+  const size_t loff = line << lnloc;
+  const int nloc_mask = (1 << lnloc) - 1;
+  float2* const Tl = peers.p[0] + loff;
+  auto elem = [&](int x) -> float2* {
+    return single ? Tl + x : s_peer[x >> lnloc] + loff + (x & nloc_mask);
+  };
   float2 v[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) v[e] = Tl[t + G * e];
+  for (int e = 0; e < E; ++e) v[e] = *elem(t + G * e);
   FftRun<P, -1>::run(v, t, s, tw);
   if (FASTD) {
     const float lyz = __ldg(lamyf + ky) + __ldg(lamzf + kz);
@@ -240,12 +255,15 @@ xlines3_kernel(float2* __restrict__ T, int N1, int NZP, const float2* __restrict
   }
   FftRun<P, +1>::run(v, t, s, tw);
 #pragma unroll
-  for (int e = 0; e < E; ++e) Tl[t + G * e] = v[e];
+  for (int e = 0; e < E; ++e) *elem(t + G * e) = v[e];
 }
 
 // ---- elementwise 3-D helpers -------------------------------------------------------------------------
 // rhs = divergence(v)  (finite_differences.py:136-143)
-__global__ void divergence3d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+// u_below: plane -1 of u (the previous rank's last plane on a slab-decomposed grid, multi_gpu_3d.cu;
+// u + (N0 - 1) * plane -- the periodic wrap -- on one GPU)
+__global__ void divergence3d_kernel(const float* __restrict__ u, const float* __restrict__ u_below,
+                                    const float* __restrict__ v,
                                     const float* __restrict__ w, float* __restrict__ rhs, int N0,
                                     int N1, int N2, float ihx, float ihy, float ihz) {
   const size_t b = blockIdx.y;
@@ -255,9 +273,10 @@ __global__ void divergence3d_kernel(const float* __restrict__ u, const float* __
   const int k = 4 * ((blockIdx.x % nchunk) * blockDim.x + threadIdx.x);
   if (k >= N2) return;
   const size_t plane = (size_t)N1 * N2, base = b * (size_t)N0 * plane;
-  const int xm = x == 0 ? N0 - 1 : x - 1, ym = y == 0 ? N1 - 1 : y - 1;
+  const int ym = y == 0 ? N1 - 1 : y - 1;
   const size_t off = base + x * plane + (size_t)y * N2 + k;
-  const float4 u0 = ldg4(u + off), um = ldg4(u + base + xm * plane + (size_t)y * N2 + k);
+  const float4 u0 = ldg4(u + off);
+  const float4 um = ldg4((x == 0 ? u_below + base : u + base + (x - 1) * plane) + (size_t)y * N2 + k);
   const float4 v0 = ldg4(v + off), vm = ldg4(v + base + x * plane + (size_t)ym * N2 + k);
   const float4 w0 = ldg4(w + off);
   const float wl = __ldg(w + base + x * plane + (size_t)y * N2 + (k == 0 ? N2 - 1 : k - 1));
@@ -270,9 +289,10 @@ __global__ void divergence3d_kernel(const float* __restrict__ u, const float* __
 }
 
 // v' = u* - forward_difference(q)   (pressure.py:194-196)
+// q_above: plane N0 of q (the next rank's first plane on a slab-decomposed grid; q itself on one GPU)
 __global__ void correct3d_kernel(const float* __restrict__ us, const float* __restrict__ vs,
                                  const float* __restrict__ ws, const float* __restrict__ q,
-                                 float* __restrict__ uo, float* __restrict__ vo,
+                                 const float* __restrict__ q_above, float* __restrict__ uo, float* __restrict__ vo,
                                  float* __restrict__ wo, int N0, int N1, int N2, float ihx,
                                  float ihy, float ihz) {
   const size_t b = blockIdx.y;
@@ -282,10 +302,10 @@ __global__ void correct3d_kernel(const float* __restrict__ us, const float* __re
   const int k = 4 * ((blockIdx.x % nchunk) * blockDim.x + threadIdx.x);
   if (k >= N2) return;
   const size_t plane = (size_t)N1 * N2, base = b * (size_t)N0 * plane;
-  const int xp = x == N0 - 1 ? 0 : x + 1, yp = y == N1 - 1 ? 0 : y + 1;
+  const int yp = y == N1 - 1 ? 0 : y + 1;
   const size_t off = base + x * plane + (size_t)y * N2 + k;
   const float4 q0 = ldg4(q + off);
-  const float4 qx = ldg4(q + base + xp * plane + (size_t)y * N2 + k);
+  const float4 qx = ldg4((x == N0 - 1 ? q_above + base : q + base + (x + 1) * plane) + (size_t)y * N2 + k);
   const float4 qy = ldg4(q + base + x * plane + (size_t)yp * N2 + k);
   const float qz = __ldg(q + base + x * plane + (size_t)y * N2 + (k + 4 == N2 ? 0 : k + 4));
   const float4 a = ldg4(us + off), bq = ldg4(vs + off), c = ldg4(ws + off);
@@ -351,24 +371,25 @@ int launch_lines_gather_t(cudaStream_t st, const float2* B, float2* A, int plane
 }
 
 template <int LM>
-int launch_xlines3_t(cudaStream_t st, float2* T, size_t nlines, int N1, int NZP, const float2* tw,
+int launch_xlines3_t(cudaStream_t st, const LinePeers& peers, int lnloc, size_t line_begin, size_t nlines, int N1,
+                     int NZP, const float2* tw,
                      const double* const* lam, const float* const* lamf, int fastd, double cutoff,
                      float norm, const float* dtab) {
   if (dtab) fastd = 0;
   constexpr int LINES = lines_for(LM);
   using P = FftPlan<LM>;
   constexpr size_t smem = (size_t)LINES * row_stride(P::M, 16) * sizeof(float2);
-  if (nlines % LINES) return set_error_msg("internal: 3-D line count not divisible");
+  if (nlines % LINES || line_begin % LINES) return set_error_msg("3-D line count not divisible by the lines per CTA");
   if (fastd) {
     auto k = xlines3_kernel<LM, LINES, true>;
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, N1, NZP, tw, lam[0], lam[1], lam[2],
-                                                            lamf[0], lamf[1], lamf[2], cutoff, norm, dtab);
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, N1, NZP, tw, lam[0], lam[1],
+                                                            lam[2], lamf[0], lamf[1], lamf[2], cutoff, norm, dtab);
   } else {
     auto k = xlines3_kernel<LM, LINES, false>;
     if (int e = set_smem(k, smem)) return e;
-    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(T, N1, NZP, tw, lam[0], lam[1], lam[2],
-                                                            lamf[0], lamf[1], lamf[2], cutoff, norm, dtab);
+    k<<<(unsigned)(nlines / LINES), LINES * P::G, smem, st>>>(peers, lnloc, line_begin, N1, NZP, tw, lam[0], lam[1],
+                                                            lam[2], lamf[0], lamf[1], lamf[2], cutoff, norm, dtab);
   }
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
@@ -397,12 +418,21 @@ int launch_lines_gather(cudaStream_t st, int lm, const float2* B, float2* A, int
   CFD_DISPATCH_LM(lm, 4, 14, return launch_lines_gather_t<LM_>(st, B, A, planes, NL, tw));
   return 0;
 }
+// lines [line_begin, line_begin + nlines) of the spectrum; element x of a line lives in peers.p[x >> lnloc]
+int launch_xlines3_peers(cudaStream_t st, int lm, const LinePeers& peers, int lnloc, size_t line_begin,
+                         size_t nlines, int N1, int NZP, const float2* tw, const double* const* lam,
+                         const float* const* lamf, int fastd, double cutoff, float norm, const float* dtab) {
+  CFD_DISPATCH_LM(lm, 4, 14,
+                  return launch_xlines3_t<LM_>(st, peers, lnloc, line_begin, nlines, N1, NZP, tw, lam, lamf, fastd,
+                                               cutoff, norm, dtab));
+  return 0;
+}
 int launch_xlines3(cudaStream_t st, int lm, float2* T, size_t nlines, int N1, int NZP,
                    const float2* tw, const double* const* lam, const float* const* lamf, int fastd,
                    double cutoff, float norm, const float* dtab) {
-  CFD_DISPATCH_LM(lm, 4, 14,
-                  return launch_xlines3_t<LM_>(st, T, nlines, N1, NZP, tw, lam, lamf, fastd, cutoff, norm, dtab));
-  return 0;
+  LinePeers peers;
+  for (int i = 0; i < CFD_MAX_PEERS; ++i) peers.p[i] = T;
+  return launch_xlines3_peers(st, lm, peers, lm, 0, nlines, N1, NZP, tw, lam, lamf, fastd, cutoff, norm, dtab);
 }
 int launch_divergence_generic(cudaStream_t st, const float* u, const float* v, const float* w, float* rhs,
                               int batch, int N0, int N1, int N2, float ih0, float ih1, float ih2);
@@ -410,12 +440,30 @@ int launch_correct_generic(cudaStream_t st, const float* us, const float* vs, co
                            float* uo, float* vo, float* wo, int batch, int N0, int N1, int N2, float ih0,
                            float ih1, float ih2);
 
+int launch_divergence_3d_slab(cudaStream_t st, const float* u, const float* u_below, const float* v,
+                              const float* w, float* rhs, int batch, int N0, int N1, int N2, float ihx,
+                              float ihy, float ihz) {
+  if (N2 % 4) return set_error_msg("internal: slab divergence needs N2 % 4 == 0");
+  const int threads = N2 / 4 < 128 ? N2 / 4 : 128;
+  dim3 grid(((N2 / 4 + threads - 1) / threads) * N0 * N1, batch);
+  divergence3d_kernel<<<grid, threads, 0, st>>>(u, u_below, v, w, rhs, N0, N1, N2, ihx, ihy, ihz);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 int launch_divergence_3d(cudaStream_t st, const float* u, const float* v, const float* w, float* rhs,
                          int batch, int N0, int N1, int N2, float ihx, float ihy, float ihz) {
   if (N2 % 4) return launch_divergence_generic(st, u, v, w, rhs, batch, N0, N1, N2, ihx, ihy, ihz);
+  return launch_divergence_3d_slab(st, u, u + (size_t)(N0 - 1) * N1 * N2, v, w, rhs, batch, N0, N1, N2, ihx,
+                                   ihy, ihz);
+}
+int launch_correct_3d_slab(cudaStream_t st, const float* us, const float* vs, const float* ws, const float* q,
+                           const float* q_above, float* uo, float* vo, float* wo, int batch, int N0, int N1,
+                           int N2, float ihx, float ihy, float ihz) {
+  if (N2 % 4) return set_error_msg("internal: slab correction needs N2 % 4 == 0");
   const int threads = N2 / 4 < 128 ? N2 / 4 : 128;
   dim3 grid(((N2 / 4 + threads - 1) / threads) * N0 * N1, batch);
-  divergence3d_kernel<<<grid, threads, 0, st>>>(u, v, w, rhs, N0, N1, N2, ihx, ihy, ihz);
+  correct3d_kernel<<<grid, threads, 0, st>>>(us, vs, ws, q, q_above, uo, vo, wo, N0, N1, N2, ihx, ihy, ihz);
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;
@@ -424,12 +472,7 @@ int launch_correct_3d(cudaStream_t st, const float* us, const float* vs, const f
                       const float* q, float* uo, float* vo, float* wo, int batch, int N0, int N1,
                       int N2, float ihx, float ihy, float ihz) {
   if (N2 % 4) return launch_correct_generic(st, us, vs, ws, q, uo, vo, wo, batch, N0, N1, N2, ihx, ihy, ihz);
-  const int threads = N2 / 4 < 128 ? N2 / 4 : 128;
-  dim3 grid(((N2 / 4 + threads - 1) / threads) * N0 * N1, batch);
-  correct3d_kernel<<<grid, threads, 0, st>>>(us, vs, ws, q, uo, vo, wo, N0, N1, N2, ihx, ihy, ihz);
-  count_launch();
-  CFD_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_correct_3d_slab(st, us, vs, ws, q, q, uo, vo, wo, batch, N0, N1, N2, ihx, ihy, ihz);
 }
 
 }  // namespace cfd

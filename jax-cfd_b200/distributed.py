@@ -37,10 +37,22 @@ def line_range(ny: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def check_decomposition(shape: Sequence[int], world: int) -> None:
-  """The constraints cfd_dist_plan_create enforces, checked on the host (same messages)."""
-  nx, ny = shape
+  """The constraints cfd_dist_plan_create[_nd] enforces, checked on the host (same messages)."""
   if world not in (1, 2, 4, 8):
     raise ValueError('world size must be 1, 2, 4 or 8')
+  if len(shape) == 3:
+    n0, n1, n2 = shape
+    nloc = n0 // world
+    if n0 % world or nloc < 16 or nloc & (nloc - 1):
+      raise ValueError('local slab must be a power of two >= 16 planes')
+    if n1 % 8 or n2 % 64:
+      raise ValueError('slab-decomposed 3-D grids need N1 % 8 == 0 and N2 % 64 == 0')
+    if n1 % (16 * world):
+      raise ValueError('axis 1 must be divisible by 16 x the number of ranks')
+    if n0 > (1 << 14):
+      raise NotImplementedError('global axis 0 longer than 16384 is not supported in 3-D')
+    return
+  nx, ny = shape
   nloc = nx // world
   if nx % world or nloc < 16 or nloc & (nloc - 1):
     raise ValueError('local slab must be a power of two >= 16 rows')
@@ -142,8 +154,8 @@ class SlabStepper:
   def __init__(self, grid: grids.Grid, dt: float, density: float, viscosity: Optional[float],
                forcing=None, *, rank: int, world: int, device: int,
                exchange: Optional[Callable[[bytes], List[bytes]]] = None):
-    if grid.ndim != 2:
-      raise NotImplementedError('slab decomposition is implemented for 2-D grids')
+    if grid.ndim not in (2, 3):
+      raise NotImplementedError('slab decomposition is implemented for 2-D and 3-D grids')
     check_decomposition(grid.shape, world)
     _lib.require_device()
     if exchange is None:
@@ -151,12 +163,13 @@ class SlabStepper:
     self._exchange = exchange
     self.grid, self.rank, self.world, self.device = grid, rank, world, device
     self.rows = slab_rows(grid.shape[0], rank, world)
-    self.local_shape = (self.rows[1] - self.rows[0], grid.shape[1])
+    self.local_shape = (self.rows[1] - self.rows[0],) + tuple(grid.shape[1:])
     check(lib().cfd_set_device(device))
-    shape = (ctypes.c_int64 * 2)(*grid.shape)
-    step = (ctypes.c_double * 2)(*grid.step)
+    nd = grid.ndim
+    shape = (ctypes.c_int64 * nd)(*grid.shape)
+    step = (ctypes.c_double * nd)(*grid.step)
     self.handle = ctypes.c_void_p()
-    check(lib().cfd_dist_plan_create(ctypes.byref(self.handle), shape, step, rank, world, device))
+    check(lib().cfd_dist_plan_create_nd(ctypes.byref(self.handle), nd, shape, step, rank, world, device))
     nb = lib().cfd_dist_handle_bytes()
     blob = ctypes.create_string_buffer(nb)
     check(lib().cfd_dist_export(self.handle, blob))
@@ -170,11 +183,12 @@ class SlabStepper:
 
   def _staging(self):
     if getattr(self, '_stage', None) is None:
-      self._stage = [_lib.DeviceArray(self.local_shape) for _ in range(2)]
+      self._stage = [_lib.DeviceArray(self.local_shape) for _ in range(self.grid.ndim)]
     return self._stage
 
   def load(self, v_local):
-    """v_local: the rank's rows of (u, v): numpy (ideally pinned) or device arrays of local_shape."""
+    """v_local: the rank's rows (planes in 3-D) of every velocity component: numpy (ideally pinned)
+    or device arrays of local_shape."""
     arrs = []
     for a, stage in zip(v_local, self._staging()):
       assert tuple(a.shape) == self.local_shape, (a.shape, self.local_shape)
@@ -196,7 +210,7 @@ class SlabStepper:
     if host_out is not None:
       outs = self._staging()
     else:
-      outs = [_lib.DeviceArray(self.local_shape) for _ in range(2)]
+      outs = [_lib.DeviceArray(self.local_shape) for _ in range(self.grid.ndim)]
     q = _lib.DeviceArray(self.local_shape) if want_q else None
     check(lib().cfd_dist_store(self.handle, self.stream.handle, _lib.ptr_array(outs),
                                None if q is None else q.ptr))
@@ -211,10 +225,10 @@ class SlabStepper:
 
   def profile(self, nsteps: int = 2):
     """Mean CUDA-event time per launch of every kernel of `nsteps` steps (all ranks must call)."""
-    names = (ctypes.c_char_p * 16)()
-    ms = (ctypes.c_float * 16)()
+    names = (ctypes.c_char_p * 24)()
+    ms = (ctypes.c_float * 24)()
     nk = ctypes.c_int(0)
-    check(lib().cfd_dist_profile(self.handle, self.stream.handle, nsteps, ctypes.byref(self.params), 16,
+    check(lib().cfd_dist_profile(self.handle, self.stream.handle, nsteps, ctypes.byref(self.params), 24,
                                  ms, names, ctypes.byref(nk)))
     return {names[i].decode(): float(ms[i]) for i in range(nk.value)}
 
