@@ -19,8 +19,10 @@
 #include "common.cuh"
 #include "fft_smem.cuh"
 #include "fft_rows.cuh"
+#include "xline_scale.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -96,89 +98,6 @@ rfft_rows_kernel(const float* __restrict__ rhs, float2* __restrict__ T, int Nx,
       const float2 WB = cmul(__ldg(rtw + k), B);               // (-i w^k) B
       *tptr(k, r) = make_float2(A.x + WB.x, A.y + WB.y);
       *tptr(M - k, r) = make_float2(A.x - WB.x, -(A.y - WB.y));
-    }
-  }
-}
-
-// Multiply the spectrum of one x line (held in registers, v[slot] <-> sub-index d = t + G*slot) by
-// the pseudo-inverse table D(kx, ky) = norm / (lam_x[kx] + lam_y[ky]),  kx = kmul * d + kadd.
-// (kmul, kadd) = (1, 0) for a whole line; (2, 0) / (2, 1) for the even / odd half-spectra of the
-// split 32768-point transform.  The packed line ky = 0 (ky = 0 in Re, ky = Ny/2 in Im) is split
-// into its two real sequences by symmetry: with C the line spectrum and C~ = conj C[N - kx],
-//   C'[kx] = D(kx,0)/2 (C + C~) + D(kx,Ny/2)/2 (C - C~);   N - kx stays in the same half-spectrum.
-template <class P, bool FASTD>
-__device__ __forceinline__ void scale_line(float2 (&v)[P::E], int t, float2* s, int ky, int My,
-                                           bool cta_has_packed, int kmul, int kadd,
-                                           const double* __restrict__ lamx,
-                                           const double* __restrict__ lamy,
-                                           const float* __restrict__ lamxf,
-                                           const float* __restrict__ lamyf, double cutoff,
-                                           float norm, const float* __restrict__ dtab) {
-  constexpr int M = P::M, G = P::G, E = P::E;
-  // dtab != nullptr (only with FASTD == false): the diagonal comes from a caller-supplied table in
-  // line layout, dtab[ky][kx] with My + 1 lines of kmul * M entries (cfd_transform: any real
-  // func(eigenvalues), fast_diagonalization.py:28-126) instead of the pseudo-inverse
-  const float* trow = dtab ? dtab + (size_t)ky * (size_t)(kmul * M) : nullptr;
-  if (!cta_has_packed || ky != 0) {
-    if (FASTD) {
-      // only the mean mode is below the cutoff (checked on the host in f64): float eigenvalues,
-      // |lam| >= min nonzero |lam_x|, |lam_y| > cutoff, so no per-element test is needed here
-      const float ly = __ldg(lamyf + ky);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float d = norm * fast_rcp(__ldg(lamxf + kmul * (t + G * e) + kadd) + ly);
-        v[e].x *= d;
-        v[e].y *= d;
-      }
-    } else {
-      if (trow) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const float d = norm * __ldg(trow + kmul * (t + G * e) + kadd);
-          v[e].x *= d;
-          v[e].y *= d;
-        }
-      } else {
-        const double ly = __ldg(lamy + ky);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const double lam = __ldg(lamx + kmul * (t + G * e) + kadd) + ly;
-          const float d = (fabs(lam) > cutoff) ? norm * fast_rcp((float)lam) : 0.f;
-          v[e].x *= d;
-          v[e].y *= d;
-        }
-      }
-    }
-  }
-  if (cta_has_packed) {
-    __syncthreads();
-    if (ky == 0) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) s[P::pad(t + G * e)] = v[e];
-    }
-    __syncthreads();
-    if (ky == 0) {
-      const double ly0 = __ldg(lamy + 0), lyM = __ldg(lamy + My);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int d = t + G * e;
-        const int dp = kadd ? (M - 1 - d) : ((M - d) & (M - 1));  // sub-index of N - kx
-        const float2 cp = s[P::pad(dp)];
-        float d0, dM;
-        if (dtab) {
-          d0 = 0.5f * norm * __ldg(dtab + kmul * d + kadd);
-          dM = 0.5f * norm * __ldg(dtab + (size_t)My * (size_t)(kmul * M) + kmul * d + kadd);
-        } else {
-          const double lx = __ldg(lamx + kmul * d + kadd);
-          const double l0 = lx + ly0, lM = lx + lyM;
-          d0 = (fabs(l0) > cutoff) ? 0.5f * norm * fast_rcp((float)l0) : 0.f;
-          dM = (fabs(lM) > cutoff) ? 0.5f * norm * fast_rcp((float)lM) : 0.f;
-        }
-        const float2 c = v[e];
-        const float2 sum = make_float2(c.x + cp.x, c.y - cp.y);
-        const float2 dif = make_float2(c.x - cp.x, c.y + cp.y);
-        v[e] = make_float2(d0 * sum.x + dM * dif.x, d0 * sum.y + dM * dif.y);
-      }
     }
   }
 }
@@ -665,6 +584,12 @@ int launch_rfft_rows(cudaStream_t st, int lm_row, const float* rhs, float2* T, i
   return launch_rfft_rows_block(st, lm_row, rhs, T, batch, Nx, tw, rtw, paired, 0, -1);
 }
 // lm_x = log2(Nx)
+int launch_xlines15_cluster(cudaStream_t st, const LinePeers& peers, const LinePeers& peers_w, int lnloc,
+                            size_t line_begin, size_t nlines, int My, const float2* tw, const double* lamx,
+                            const double* lamy, const float* lamxf, const float* lamyf, int fastd,
+                            double cutoff, float norm, const float2* wbig, int paired, const float* dtab);
+bool x15_cluster(int paired);
+
 // `scratch` / `wbig` are only needed for lm_x == 15 (32768-point lines): scratch holds
 // nlines * 32768 float2, wbig[m] = exp(-2 pi i m / 32768), m < 16384.  With side streams the split
 // path runs in chunks of lines on those streams, so that the NVLink reads of one chunk (split), the
@@ -676,6 +601,11 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         const float2* wbig, const SideStreams* side, int paired, const float* dtab,
                         const LinePeers* peers_out) {
   const LinePeers& peers_w = peers_out ? *peers_out : peers;  // results go back in place by default
+  if (lm_x == 15 && x15_cluster(paired)) {
+    if (!wbig) return set_error_msg("internal: 32768-point lines need the w table");
+    return launch_xlines15_cluster(st, peers, peers_w, lnloc, line_begin, nlines, My, tw, lamx, lamy, lamxf, lamyf,
+                                   fastd, cutoff, norm, wbig, paired, dtab);
+  }
   if (lm_x == 15) {
     if (!scratch || !wbig) return set_error_msg("internal: 32768-point lines need the split scratch");
     const int half = 1 << 14;

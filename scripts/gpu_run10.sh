@@ -1,0 +1,18 @@
+# cluster kernel for 32768-point lines: parity tests + timing vs the split path on one GPU
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "paired_spectrum or (matches_oracle and 32768) or slab_stepper_world1" 2>&1 | tail -5
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 600 python bench.py --workload K32768 --gpus 1 --steps 5 --warmup 3 > gpurun_out/r2i_$name.json 2> gpurun_out/r2i_$name.err
+  python - <<PY
+import json
+try:
+  d=json.loads([l for l in open('gpurun_out/r2i_$name.json') if l.startswith('{')][-1])
+  print('$name', 'ms/step', round(d['ms_per_step'],4), 'value', round(d['value'],1), {k:round(v,3) for k,v in d['kernel_ms_rank0'].items()})
+except Exception as e:
+  print('$name FAILED', e); print(open('gpurun_out/r2i_$name.err').read()[-1500:])
+PY
+}
+run plain_cluster CFD_SLAB_SHAPE=32768x8192
+run plain_split CFD_SLAB_SHAPE=32768x8192 CFD_X15=split
+run paired_cluster CFD_SLAB_SHAPE=32768x16384
+run paired_split CFD_SLAB_SHAPE=32768x16384 CFD_X15=split

@@ -157,6 +157,39 @@ def test_step_matches_oracle(cfd, shape, nsteps):
   assert np.abs(cfd_oracle.divergence(to_np(got), grid.step)).max() < max(2e-3, 3 * ref_div)
 
 
+@pytest.mark.parametrize('shape', [(8192, 64), (32768, 64)])
+def test_paired_spectrum_layout_is_bitwise_equal_to_plain(cfd, shape, monkeypatch):
+  """The pair-interleaved spectrum layout T[ky/2][x][ky&1] (chosen by the plan for rows of >= 16384
+  reals; forced here on a thin grid) changes where the numbers live, not the numbers: x lines of
+  8192 points (stride-2 line kernel) and of 32768 points (4-CTA cluster kernel with the DSMEM
+  radix-2 exchange, vs the 2-CTA cluster of the plain layout)."""
+  from jax_cfd_b200 import _engine
+  dom = ((0.0, 2 * np.pi), (0.0, 2 * np.pi))
+  grid = cfd.grids.Grid(shape, domain=dom)
+  v0 = cfd_oracle.filtered_velocity_field(5, shape, dom, 3.0, 4)
+  dt = 0.5 * min(grid.step) / 3.0
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+
+  def run():
+    with _engine._plans_lock:
+      _engine._plans.clear()
+    step = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-4, dt, grid, forcing=forcing)
+    got, q = step.advance(wrap(cfd, grid, v0), 3, return_q=True)
+    return to_np(got) + [np.asarray(q)]
+
+  try:
+    monkeypatch.setenv('CFD_T_PAIRED', '0')
+    plain = run()
+    monkeypatch.setenv('CFD_T_PAIRED', '1')
+    paired = run()
+  finally:
+    with _engine._plans_lock:
+      _engine._plans.clear()
+  for a, b in zip(plain, paired):
+    np.testing.assert_array_equal(a, b)
+
+
 def test_host_and_device_paths_agree_bitwise(cfd):
   rec = gu.load('k2d_64x32')
   grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
