@@ -17,6 +17,7 @@
 // and 31 are halo lanes (their results are not stored), so a warp produces 30*C columns.  x-face
 // fluxes are computed once and carried to the next row in registers; y-face fluxes are computed
 // once per lane (C+1 faces for C cells).  No shared memory, no block-level synchronisation.
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -367,6 +368,38 @@ int explicit_2d_tile_rows(int batch, int Nx, int Ny) {
   return warps64 >= 148L * 12 ? 64 : 16;
 }
 
+// Rows per warp of a launch that covers the WHOLE grid (the slab-decomposed step launches ranges of
+// explicit_2d_tile_rows tiles and keeps those).  All warps of the launch do the same work and 16 of
+// them fit an SM (128 registers), so the launch runs in waves of 148 x 16 warps and its last wave
+// is only as full as the warp count allows: at 8192^2, 64-row tiles are 8832 warps = 3.73 waves.
+// Pick the tile height in [48, 95] (the row profile table holds 96 rows) that fills its last wave
+// best, preferring taller tiles (5 warm-up rows each).  CFD_EXPLICIT_TX=n overrides.
+static int explicit_2d_tile_rows_full(int batch, int Nx, int Ny, int warp_cols) {
+  static const int forced = [] {
+    const char* e = getenv("CFD_EXPLICIT_TX");
+    return e ? atoi(e) : 0;
+  }();
+  const int base = explicit_2d_tile_rows(batch, Nx, Ny);
+  if (forced >= 8 && forced <= 95) return forced;
+  if (forced < 0 || base != 64) return base;
+  const long strips = (Ny + warp_cols - 1) / warp_cols;
+  const long cta_per_tile = (strips + kWarpsPerCta - 1) / kWarpsPerCta;
+  const double slots = 148.0 * (16 / kWarpsPerCta);  // CTAs resident at once
+  int best = base;
+  double best_cost = 1e30;
+  for (int tx = 48; tx <= 95; ++tx) {
+    const long tiles = (Nx + tx - 1) / tx;
+    const double waves = (double)(tiles * cta_per_tile * batch) / slots;
+    // time ~ full waves (rounded up) x rows marched per warp, warm-up rows included
+    const double cost = ceil(waves - 1e-9) * (tx + 5);
+    if (cost < best_cost - 1e-9 || (fabs(cost - best_cost) <= 1e-9 && tx > best)) {
+      best_cost = cost;
+      best = tx;
+    }
+  }
+  return best;
+}
+
 // tile_begin / tile_count: the range of row tiles (explicit_2d_tile_rows rows each) this launch
 // covers; tile_count < 0 = all of them.  The slab-decomposed step launches the stencil block by
 // block so that the row FFT and the NVLink transfer of a block overlap the stencil of the next.
@@ -376,13 +409,6 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
                             int tile_count) {
   const float* qprev = sq.own;
   if (Nx < 3) return set_error_msg("a slab needs at least 3 rows");
-  const int TX = explicit_2d_tile_rows(batch, Nx, Ny);
-  const int tiles_all = (Nx + TX - 1) / TX;
-  if (tile_count < 0) {
-    tile_begin = 0;
-    tile_count = tiles_all;
-  }
-  if (tile_begin < 0 || tile_begin + tile_count > tiles_all) return set_error_msg("internal: bad stencil tile range");
   static const int forced_cols = [] {  // tuning knob: CFD_EXPLICIT_COLS=2|4 columns per lane
     const char* e = getenv("CFD_EXPLICIT_COLS");
     return (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
@@ -391,6 +417,14 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
   const int work4 = ((Ny + 119) / 120) * 128, work2 = ((Ny + 55) / 56) * 64;
   const int cols = forced_cols ? forced_cols : (work2 < work4 ? 2 : 4);
   const int warp_cols = cols == 4 ? 120 : 56;
+  const int TX = tile_count < 0 ? explicit_2d_tile_rows_full(batch, Nx, Ny, warp_cols)
+                                : explicit_2d_tile_rows(batch, Nx, Ny);
+  const int tiles_all = (Nx + TX - 1) / TX;
+  if (tile_count < 0) {
+    tile_begin = 0;
+    tile_count = tiles_all;
+  }
+  if (tile_begin < 0 || tile_begin + tile_count > tiles_all) return set_error_msg("internal: bad stencil tile range");
   const int strips = (Ny + warp_cols - 1) / warp_cols;
   dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, tile_count, batch);
   int pattern = 0, nt = 0;

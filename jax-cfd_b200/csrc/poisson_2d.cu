@@ -588,7 +588,7 @@ int launch_xlines15_cluster(cudaStream_t st, const LinePeers& peers, const LineP
                             size_t line_begin, size_t nlines, int My, const float2* tw, const double* lamx,
                             const double* lamy, const float* lamxf, const float* lamyf, int fastd,
                             double cutoff, float norm, const float2* wbig, int paired, const float* dtab);
-bool x15_cluster(int paired);
+bool x15_cluster(int paired, int several_gpus);
 
 // `scratch` / `wbig` are only needed for lm_x == 15 (32768-point lines): scratch holds
 // nlines * 32768 float2, wbig[m] = exp(-2 pi i m / 32768), m < 16384.  With side streams the split
@@ -601,7 +601,7 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         const float2* wbig, const SideStreams* side, int paired, const float* dtab,
                         const LinePeers* peers_out) {
   const LinePeers& peers_w = peers_out ? *peers_out : peers;  // results go back in place by default
-  if (lm_x == 15 && x15_cluster(paired)) {
+  if (lm_x == 15 && x15_cluster(paired, lnloc != lm_x)) {
     if (!wbig) return set_error_msg("internal: 32768-point lines need the w table");
     return launch_xlines15_cluster(st, peers, peers_w, lnloc, line_begin, nlines, My, tw, lamx, lamy, lamxf, lamyf,
                                    fastd, cutoff, norm, wbig, paired, dtab);

@@ -16,22 +16,27 @@ namespace cfd {
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// 32768-point x lines on a thread-block CLUSTER (the default; CFD_X15=split selects the scratch
-// path above).  The radix-2 step that makes a line fit is done on chip: CTA h of a cluster holds
-// the half x[h N/2 ..] of the line in registers, the two halves meet through distributed shared
-// memory (each CTA publishes its registers in its own shared memory, cluster barrier, the partner
-// reads them with ld.shared::cluster), and CTA h then owns the half-length line y_h whose
-// transform is the even (h = 0) / odd (h = 1) frequencies -- the same arithmetic, operation for
-// operation, as split_lines_kernel -> xlines_kernel<14, SPLIT> -> merge_lines_kernel, without the
-// scratch: the spectrum is read once and written once and nothing else touches HBM (8 B/cell
-// instead of 24).
+// 32768-point x lines on a thread-block CLUSTER (CFD_X15=split selects the scratch path of
+// poisson_2d.cu instead).  A line does not fit one CTA (16384 points = 1024 threads x 16 registers
+// is the most), so one radix-2 decimation-in-frequency step splits it over the CTAs of a cluster:
+//   in:   CTA h forms y_h[m] = (x[m] +- x[m + N/2]) w^(h m) for all m < N/2 straight from the
+//         spectrum -- both CTAs of a line load both halves; the second copy of every sector comes
+//         out of L2, which measured faster than handing the halves over through DSMEM;
+//   mid:  y_0 / y_1 are ordinary 16384-point lines whose transforms are the even / odd frequencies:
+//         forward passes, pseudo-inverse scaling (kx = 2 d + h), inverse passes, as in xlines_kernel;
+//   out:  x'[m] = y_0' + y_1' conj(w^m), x'[m + N/2] = y_0' - y_1' conj(w^m): every CTA publishes its
+//         half-length result in its own shared memory, cluster barrier, and reads the partner's
+//         through distributed shared memory (ld.shared::cluster).
+// Operation for operation this is split_lines_kernel -> xlines_kernel<14, SPLIT> ->
+// merge_lines_kernel (bit-identical results) without the scratch: the spectrum is read once from
+// HBM and written once, 8 B/cell instead of 24.
 //   plain layout:   cluster of 2 CTAs = one line.
 //   PAIRED layout:  cluster of 4 CTAs = the two interleaved lines of a pair, CTA rank = 2 l + h.
 //                   Loads are the stride-2 accesses of the layout (the partner line's CTAs use the
 //                   other half of every sector at the same time); for the STORES -- posted NVLink
 //                   writes to the slab owners on several GPUs, where half-filled sectors would
-//                   double the link traffic -- the four CTAs exchange once more so that every
-//                   thread writes whole float4 = both lines of the pair.
+//                   double the link traffic -- each CTA gathers both lines from all four CTAs so
+//                   that every thread writes whole float4 = both lines of the pair.
 // Cluster barrier halves: work that does not depend on the partners (register-only passes, global
 // stores) runs between the arrive and the wait.
 __device__ __forceinline__ void cluster_arrive_release() {
@@ -73,51 +78,23 @@ xlines15_cluster_kernel(LinePeers peers, LinePeers peers_w, int lnloc, size_t li
   __syncthreads();
   auto elem = [&](int x) -> float2* { return s_peer[x >> lnloc] + loff + XS * (x & nloc_mask); };
   auto elem_w = [&](int x) -> float2* { return s_peer_w[x >> lnloc] + loff + XS * (x & nloc_mask); };
-  float2* const other_half = cluster.map_shared_rank(smem, crank ^ 1u);
 
   float2 v[E];
-  if constexpr (!PAIRED) {
-    // ---- radix-2 decimation in frequency: both CTAs read BOTH halves of the line straight from
-    // the spectrum (the partner's copy of every sector comes out of L2) -- no exchange on the way in
+  // ---- radix-2 decimation in frequency: both CTAs of a line read BOTH halves of it straight from
+  // the spectrum (every sector is requested by the 2 / 4 CTAs of the cluster at about the same time:
+  // one HBM read, the other copies come out of L2) -- no exchange on the way in
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int m = t + G * e;
-      const float2 a = *elem(m), b = *elem(M + m);
-      if (h == 0) {
-        v[e] = make_float2(a.x + b.x, a.y + b.y);  // y0[m] = x[m] + x[m + N/2]
-      } else {
-        const float2 d = make_float2(a.x - b.x, a.y - b.y);
-        v[e] = cmul(d, __ldg(wbig + m));           // y1[m] = (x[m] - x[m + N/2]) w^m
-      }
+  for (int e = 0; e < E; ++e) {
+    const int m = t + G * e;
+    const float2 a = *elem(m), b = *elem(M + m);
+    if (h == 0) {
+      v[e] = make_float2(a.x + b.x, a.y + b.y);  // y0[m] = x[m] + x[m + N/2]
+    } else {
+      const float2 d = make_float2(a.x - b.x, a.y - b.y);
+      v[e] = cmul(d, __ldg(wbig + m));           // y1[m] = (x[m] - x[m + N/2]) w^m
     }
-    fft_pass_compute<P, P::lr_fwd(0), P::lns_fwd(0), -1>(v, t, tw + P::tw_off_fwd(0));
-  } else {
-#pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = *elem(h * M + t + G * e);
-    // ---- radix-2 decimation in frequency across the two CTAs of the line
-#pragma unroll
-    for (int e = 0; e < E; ++e) smem[P::pad(t + G * e)] = v[e];
-    cluster_arrive_release();
-    cluster_wait();
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int m = t + G * e;
-      const float2 o = other_half[P::pad(m)];
-      if (h == 0) {
-        v[e] = make_float2(v[e].x + o.x, v[e].y + o.y);  // y0[m] = x[m] + x[m + N/2]
-      } else {
-        const float2 d = make_float2(o.x - v[e].x, o.y - v[e].y);
-        v[e] = cmul(d, __ldg(wbig + m));                 // y1[m] = (x[m] - x[m + N/2]) w^m
-      }
-    }
-    // "I have read your half": shared memory is rewritten by the first exchange of the transform,
-    // which FftRun starts with a CTA barrier -- the cluster wait sits right before it (pass 0 works
-    // on registers only and overlaps the barrier latency).  Release: the partner's reads above must
-    // be performed before it arrives.
-    cluster_arrive_release();
-    fft_pass_compute<P, P::lr_fwd(0), P::lns_fwd(0), -1>(v, t, tw + P::tw_off_fwd(0));
-    cluster_wait();
   }
+  fft_pass_compute<P, P::lr_fwd(0), P::lns_fwd(0), -1>(v, t, tw + P::tw_off_fwd(0));
   FftRun<P, -1, SyncCta, false, 0, false>::template exchange<0>(v, t, smem, 0, 0);
   FftRun<P, -1, SyncCta, false, 0, false>::template passes<1>(v, t, smem, tw, 0, 0);
   scale_line<P, FASTD>(v, t, smem, ky, My, ky == 0, 2, h, lamx, lamy, lamxf, lamyf, cutoff, norm,
@@ -182,12 +159,13 @@ xlines15_cluster_kernel(LinePeers peers, LinePeers peers_w, int lnloc, size_t li
 }  // namespace
 
 // CFD_X15=split selects the scratch path (split -> 16384-point lines -> merge) for 32768-point lines
-// Which implementation runs 32768-point lines: CFD_X15=cluster|split forces one; by default the
-// cluster kernel takes the plain layout (measured on one B200, 32768 x 8192: x pass 2.38 ms vs
-// 2.51 ms through the scratch) and the scratch path keeps the pair-interleaved layout (32768 x
-// 16384: 4.0 ms vs 4.7 ms on the 4-CTA cluster, whose output exchange moves 3/4 of its data
-// through DSMEM at ~20 B/clk per SM).
-bool x15_cluster(int paired) {
+// Which implementation runs 32768-point lines: CFD_X15=cluster|split forces one.  Default: the
+// cluster kernel, except for the pair-interleaved layout on ONE GPU.  Measured x pass (B200):
+//   plain,  1 GPU, 32768 x 8192:              cluster 1.66 ms, scratch path 2.46 ms
+//   paired, 1 GPU, 32768 x 16384:             cluster 4.48 ms, scratch path 4.00 ms (the 4-CTA output
+//                                             exchange moves 3/4 of its data through DSMEM)
+//   paired, 8 GPUs, 32768 x 16384 / 32768^2:  cluster 0.64 / 1.24 ms, scratch path 0.74 / 1.45 ms
+bool x15_cluster(int paired, int several_gpus) {
   static const int forced = [] {
     const char* e = getenv("CFD_X15");
     if (e && strcmp(e, "split") == 0) return 0;
@@ -195,7 +173,7 @@ bool x15_cluster(int paired) {
     return -1;
   }();
   if (forced >= 0) return forced == 1;
-  return !paired;
+  return !paired || several_gpus;
 }
 
 int launch_xlines15_cluster(cudaStream_t st, const LinePeers& peers, const LinePeers& peers_w, int lnloc,
