@@ -380,9 +380,17 @@ static int explicit_2d_tile_rows_full(int batch, int Nx, int Ny, int warp_cols) 
     return e ? atoi(e) : 0;
   }();
   const int base = explicit_2d_tile_rows(batch, Nx, Ny);
-  if (forced >= 8 && forced <= 95) return forced;
-  if (forced < 0 || base != 64) return base;
+  if (forced >= 2 && forced <= 95) return forced;
+  if (forced < 0) return base;
   const long strips = (Ny + warp_cols - 1) / warp_cols;
+  if (base != 64) {
+    // small grids are latency bound (256^2 with 16-row tiles: 80 warps on 148 SMs, each marching
+    // 21 rows): shorter tiles until there are a few warps per SM -- 256^2: 4 rows, stencil 16.4 ->
+    // 9.1 us; 2048^2 keeps 16 rows
+    int tx = base;
+    while (tx > 4 && strips * ((Nx + tx - 1) / tx) * batch < 148L * 4) tx /= 2;
+    return tx;
+  }
   const long cta_per_tile = (strips + kWarpsPerCta - 1) / kWarpsPerCta;
   const double slots = 148.0 * (16 / kWarpsPerCta);  // CTAs resident at once
   int best = base;
@@ -413,9 +421,14 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
     const char* e = getenv("CFD_EXPLICIT_COLS");
     return (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
   }();
-  // columns per lane: the choice that wastes fewer lanes on this row length (ties -> 4)
+  // columns per lane: the choice that wastes fewer lanes on this row length (ties -> 4).  When the
+  // launch fills the GPU anyway, 4 columns per lane win unless they waste a quarter more lanes (2
+  // columns cost 1.5 instead of 1.25 y-face fluxes per cell): 1024 x 256^2, 384 vs 320 lane-columns
+  // per row, measured 0.551 ms (4) vs 0.574 ms (2).
   const int work4 = ((Ny + 119) / 120) * 128, work2 = ((Ny + 55) / 56) * 64;
-  const int cols = forced_cols ? forced_cols : (work2 < work4 ? 2 : 4);
+  const bool fills_gpu = (long)((Ny + 119) / 120) * ((Nx + 63) / 64) * batch >= 148L * 16;
+  const int cols = forced_cols ? forced_cols
+                               : (fills_gpu ? (4 * work2 < 3 * work4 ? 2 : 4) : (work2 < work4 ? 2 : 4));
   const int warp_cols = cols == 4 ? 120 : 56;
   const int TX = tile_count < 0 ? explicit_2d_tile_rows_full(batch, Nx, Ny, warp_cols)
                                 : explicit_2d_tile_rows(batch, Nx, Ny);

@@ -473,11 +473,11 @@ int step_push(cfd_plan* p, cudaStream_t st, const SharedLayout& L, const StepCon
     if (int e = wait_flags(p, st, L, kSlotNbr, 1, 2, p->dist_nbr_epoch, "wait_nbr")) return e;
   }
   // ---- stencil + row FFT block by block; each finished block is pushed to the line owners.
-  // The stencil is split like the row FFT (measured on 2 x 8192^2: one stencil launch 0.42 ms, four
-  // 0.50 ms, but with a single launch the first push starts 0.4 ms later and the step is 0.2 ms
-  // longer); CFD_DIST_STENCIL_PARTS overrides the number of stencil launches.
+  // The stencil runs in TWO launches (CFD_DIST_STENCIL_PARTS overrides): a single launch delays the
+  // first push by the whole stencil, one launch per row block costs a ramp and a tail each.  Measured
+  // on 4 x 8192^2 (32768 x 8192, four row blocks): 1 / 2 / 4 launches = 1.570 / 1.488 / 1.540 ms.
   static const int wish_parts = [] { const char* e = getenv("CFD_DIST_STENCIL_PARTS"); return e ? atoi(e) : 0; }();
-  int nst = wish_parts > 0 ? (wish_parts > NB ? NB : wish_parts) : NB;
+  int nst = wish_parts > 0 ? (wish_parts > NB ? NB : wish_parts) : (NB >= 2 ? 2 : 1);
   while (NB % nst) --nst;
   const int bpst = NB / nst;  // row blocks per stencil launch
   for (int b = 0; b < NB; ++b) {

@@ -601,7 +601,9 @@ int launch_xlines_peers(cudaStream_t st, int lm_x, const LinePeers& peers, int l
                         const float2* wbig, const SideStreams* side, int paired, const float* dtab,
                         const LinePeers* peers_out) {
   const LinePeers& peers_w = peers_out ? *peers_out : peers;  // results go back in place by default
-  if (lm_x == 15 && x15_cluster(paired, lnloc != lm_x)) {
+  // (pull mode -- the line is READ from the peers -- keeps the scratch path: the cluster kernel
+  // loads every element twice, which would double the NVLink reads)
+  if (lm_x == 15 && !(lnloc != lm_x && peers_out == nullptr) && x15_cluster(paired, lnloc != lm_x)) {
     if (!wbig) return set_error_msg("internal: 32768-point lines need the w table");
     return launch_xlines15_cluster(st, peers, peers_w, lnloc, line_begin, nlines, My, tw, lamx, lamy, lamxf, lamyf,
                                    fastd, cutoff, norm, wbig, paired, dtab);

@@ -202,3 +202,40 @@ def test_forward_euler_with_a_different_time_step_keeps_the_convection_dt():
   assert step.dt == 0.005 and step.convect_dt == 0.01
   same = cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, grid)
   assert same.dt == 0.01 and same.convect_dt is None
+
+
+def test_jax_ffi_attributes_describe_the_equation_without_pointers():
+  """The attribute dictionary of the XLA custom call (jax_ffi.step_attrs) carries exactly what struct
+  cfd_params carries, as typed scalars / small arrays (csrc/xla_ffi_shim.cc, CFD_STEP_ATTRS) --
+  serialisable, no host pointers -- and the forcing tables travel as operands."""
+  import jax_cfd_b200 as cfd
+  from jax_cfd_b200 import jax_ffi, _lib
+  grid = cfd.grids.Grid((64, 32), domain=((0.0, 2 * np.pi), (0.0, 2 * np.pi)))
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=2.0, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  a = jax_ffi.step_attrs(grid, 0.01, 1.5, None, forcing, nsteps=7)
+  expected = {'step', 'nsteps', 'implementation', 'dt', 'convect_dt', 'density', 'viscosity', 'linear_coef',
+              'smagorinsky_cs', 'terms', 'sep_scale', 'sep_mask', 'sep_has', 'field_mask'}
+  assert set(a) == expected
+  assert all(isinstance(v, (np.generic, np.ndarray)) for v in a.values())
+  assert a['viscosity'] < 0 and a['nsteps'] == 7 and a['density'] == 1.5
+  assert list(a['terms']) == [_lib.FORCE_SEPARABLE, _lib.FORCE_LINEAR]
+  assert a['linear_coef'] == -0.1 and a['sep_scale'][0] == 2.0
+  assert a['sep_has'] == 1          # only u is forced (forcings.py:88-99)
+  sep, fld = jax_ffi.forcing_operands(grid, forcing)
+  assert sep.shape == (bin(int(a['sep_mask'])).count('1'), 64) and sep.dtype == np.float32
+  assert fld.shape == (0, 64, 32)
+  # the profile rows are the term's own tables, in (component, axis) order of the set bits
+  term = forcing.terms[0]
+  rows = [np.asarray(term.profiles[c][j], np.float32) for c in range(2) for j in range(2)
+          if term.profiles[c][j] is not None]
+  for r, want in zip(sep, rows):
+    np.testing.assert_array_equal(r[:want.size], want)
+  # 3-D with the Smagorinsky closure: one term, one scalar
+  g3 = cfd.grids.Grid((32, 32, 64), domain=((0.0, 2 * np.pi),) * 3)
+  f3 = cfd._engine.ForcingFn([cfd._engine.SmagorinskyTerm(0.2)])
+  a3 = jax_ffi.step_attrs(g3, 0.01, 1.0, 1e-3, f3)
+  assert list(a3['terms']) == [_lib.FORCE_SMAGORINSKY] and a3['smagorinsky_cs'] == 0.2
+  assert a3['step'].shape == (3,) and a3['viscosity'] == 1e-3
+  assert set(jax_ffi.TARGETS.values()) == {'B200CfdStep2D', 'B200CfdStep3D', 'B200CfdProject2D',
+                                           'B200CfdProject3D'}
