@@ -45,6 +45,15 @@ __device__ __forceinline__ FC<2> ldrow<2>(const float* p) {
   const float2 v = __ldg(reinterpret_cast<const float2*>(p));
   return FC<2>{{v.x, v.y}};
 }
+template <>
+__device__ __forceinline__ FC<8> ldrow<8>(const float* p) {
+  const float4 a = ldg4(p), b = ldg4(p + 4);
+  return FC<8>{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ void strow(float* p, const FC<8>& f) {
+  stg4(p, make_float4(f.a[0], f.a[1], f.a[2], f.a[3]));
+  stg4(p + 4, make_float4(f.a[4], f.a[5], f.a[6], f.a[7]));
+}
 __device__ __forceinline__ void strow(float* p, const FC<4>& f) {
   stg4(p, make_float4(f.a[0], f.a[1], f.a[2], f.a[3]));
 }
@@ -65,7 +74,13 @@ __device__ __forceinline__ void strow(float* p, const FC<2>& f) {
 // straight from the neighbouring ranks' buffers over NVLink (SlabSrc::prev / next, peer-mapped
 // with CUDA IPC) -- the halo exchange is fused into the stencil loads.  On one GPU prev = next =
 // own, which is the periodic wrap.
-template <int PATTERN, int C, bool LAZY>
+//
+// WRAP: the row is exactly 32 * C columns long, so ONE warp owns whole rows and the periodic column
+// halo is the wrap-around of the lane index -- no halo lanes, no redundant columns, every y-face
+// flux evaluated by a lane is used.  With C = 8 this is the 256-column row of the ensemble members
+// (BASELINE config #3), where halo lanes waste a third of the machine (3 x 128 lane-columns for 256
+// columns).  The four warps of a CTA then take four consecutive row tiles.
+template <int PATTERN, int C, bool LAZY, bool WRAP = false>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
                   float* __restrict__ vs, float* __restrict__ rhs, int Nx, int Ny, int row0,
@@ -75,20 +90,30 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
   // own stencil reaches 2 further columns: 4 columns = 1 lane (C = 4) or 2 lanes (C = 2) on the
   // left, 1 lane on the right.
   // (LAZY adds one column on the right: projecting v[j] needs q[j+1]; C = 2 then needs 2 lanes.)
-  constexpr int kHaloL = 4 / C;
-  constexpr int kHaloR = (C == 2) ? 2 : 1;
-  constexpr int kWarpCols = (32 - kHaloL - kHaloR) * C;  // stored columns per warp: 120 or 56
+  static_assert(WRAP || C <= 4, "more than 4 columns per lane only in WRAP mode");
+  constexpr int kHaloL = WRAP ? 0 : 4 / C;
+  constexpr int kHaloR = WRAP ? 0 : ((C == 2) ? 2 : 1);
+  constexpr int kWarpCols = (32 - kHaloL - kHaloR) * C;  // stored columns per warp: 120 or 56 (WRAP: all)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int strip = blockIdx.x * kWarpsPerCta + warp;
+  const int strip = WRAP ? 0 : blockIdx.x * kWarpsPerCta + warp;
   if (strip * kWarpCols >= Ny) return;
   const int jbase = strip * kWarpCols - kHaloL * C + C * lane;
   int jg = jbase % Ny;
   if (jg < 0) jg += Ny;
-  const bool store_ok = (lane >= kHaloL) && (lane < 32 - kHaloR) && (jbase < Ny);
+  const bool store_ok = WRAP || ((lane >= kHaloL) && (lane < 32 - kHaloR) && (jbase < Ny));
   const size_t boff = (size_t)blockIdx.z * (size_t)Nx * (size_t)Ny;
-  const int i0 = (blockIdx.y + tile_begin) * TX;  // row tiles [tile_begin, tile_begin + gridDim.y)
+  // row tiles [tile_begin, tile_begin + tiles of this launch); WRAP: one tile per warp
+  const int i0 = ((WRAP ? blockIdx.y * kWarpsPerCta + warp : blockIdx.y) + tile_begin) * TX;
+  if (WRAP && i0 >= Nx) return;
   const int iend = min(i0 + TX, Nx);  // exclusive
+  // value of the previous / next lane; WRAP: around the row
+  auto from_left = [&](float x) {
+    return WRAP ? __shfl_sync(FULLMASK, x, (lane + 31) & 31) : __shfl_up_sync(FULLMASK, x, 1);
+  };
+  auto from_right = [&](float x) {
+    return WRAP ? __shfl_sync(FULLMASK, x, (lane + 1) & 31) : __shfl_down_sync(FULLMASK, x, 1);
+  };
 
   // row i in [-Nx, 2 Nx) of a slab-decomposed field
   auto rowptr = [&](const SlabSrc& f, int i) -> const float* {
@@ -119,7 +144,7 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
   // lazily projected input: row r of (u, v) = (u*, v*)[r] - grad q, needs q rows r and r+1 and
   // the column to the right (from lane+1; lane 31's last column is never used by lane 30)
   auto project_row = [&](Row& ur, Row& vr, const Row& q0, const Row& q1) {
-    const float qR = __shfl_down_sync(FULLMASK, q0.a[0], 1);
+    const float qR = from_right(q0.a[0]);
 #pragma unroll
     for (int k = 0; k < C; ++k) {
       const float qright = (k == C - 1) ? qR : q0.a[(k + 1) % C];
@@ -141,7 +166,7 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
   // x-face fluxes at face (i0-2 | i0-1), needed by row i0-1:  stencil rows i0-3 .. i0
   Row f0u_prev, f0v_prev;
   {
-    const float uR1 = __shfl_down_sync(FULLMASK, ua[1].a[0], 1);
+    const float uR1 = from_right(ua[1].a[0]);
 #pragma unroll
     for (int k = 0; k < C; ++k) {
       const float Uu = ua[1].a[k] + ua[2].a[k];
@@ -154,7 +179,7 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
   Row us_prev;
 #pragma unroll
   for (int k = 0; k < C; ++k) us_prev.a[k] = 0.f;
-  float vL1_cur = __shfl_up_sync(FULLMASK, va[2].a[C - 1], 1);  // v[i][-1] for i = i0-1
+  float vL1_cur = from_left(va[2].a[C - 1]);  // v[i][-1] for i = i0-1
 
 
   // forcing tables: the column profiles of the separable term are fixed per thread
@@ -217,15 +242,15 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
   for (int i = i0 - 1; i < iend; ++i) {
     // ---- column halos of row i (and v[i+1][-1]) from neighbouring lanes
     float ue[C + 4], ve[C + 4];
-    ue[0] = __shfl_up_sync(FULLMASK, ua[2].a[C - 2], 1);
-    ue[1] = __shfl_up_sync(FULLMASK, ua[2].a[C - 1], 1);
-    ue[C + 2] = __shfl_down_sync(FULLMASK, ua[2].a[0], 1);
-    ue[C + 3] = __shfl_down_sync(FULLMASK, ua[2].a[1], 1);
-    ve[0] = __shfl_up_sync(FULLMASK, va[2].a[C - 2], 1);
+    ue[0] = from_left(ua[2].a[C - 2]);
+    ue[1] = from_left(ua[2].a[C - 1]);
+    ue[C + 2] = from_right(ua[2].a[0]);
+    ue[C + 3] = from_right(ua[2].a[1]);
+    ve[0] = from_left(va[2].a[C - 2]);
     ve[1] = vL1_cur;
-    ve[C + 2] = __shfl_down_sync(FULLMASK, va[2].a[0], 1);
-    ve[C + 3] = __shfl_down_sync(FULLMASK, va[2].a[1], 1);
-    const float vnL1 = __shfl_up_sync(FULLMASK, va[3].a[C - 1], 1);  // v[i+1][-1]
+    ve[C + 2] = from_right(va[2].a[0]);
+    ve[C + 3] = from_right(va[2].a[1]);
+    const float vnL1 = from_left(va[3].a[C - 1]);  // v[i+1][-1]
 #pragma unroll
     for (int k = 0; k < C; ++k) {
       ue[2 + k] = ua[2].a[k];
@@ -317,7 +342,7 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
       vs_cur.a[k] = dvdt_mode ? dv : v0 + c.dt * dv;
     }
 
-    const float vsL = __shfl_up_sync(FULLMASK, vs_cur.a[C - 1], 1);  // v*[i][-1]
+    const float vsL = from_left(vs_cur.a[C - 1]);  // v*[i][-1]
     if (i >= i0 && store_ok) {
       const size_t off = boff + (size_t)iw * Ny + jg;
       strow(us + off, us_cur);
@@ -430,8 +455,9 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
   const int cols = forced_cols ? forced_cols
                                : (fills_gpu ? (4 * work2 < 3 * work4 ? 2 : 4) : (work2 < work4 ? 2 : 4));
   const int warp_cols = cols == 4 ? 120 : 56;
-  const int TX = tile_count < 0 ? explicit_2d_tile_rows_full(batch, Nx, Ny, warp_cols)
-                                : explicit_2d_tile_rows(batch, Nx, Ny);
+  const bool full_launch = tile_count < 0;
+  const int TX = full_launch ? explicit_2d_tile_rows_full(batch, Nx, Ny, warp_cols)
+                             : explicit_2d_tile_rows(batch, Nx, Ny);
   const int tiles_all = (Nx + TX - 1) / TX;
   if (tile_count < 0) {
     tile_begin = 0;
@@ -440,6 +466,10 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
   if (tile_begin < 0 || tile_begin + tile_count > tiles_all) return set_error_msg("internal: bad stencil tile range");
   const int strips = (Ny + warp_cols - 1) / warp_cols;
   dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, tile_count, batch);
+  // whole-row warps (WRAP, 8 columns per lane) for GPU-filling batches of 256-column rows
+  static const int wrap_ok = [] { const char* e = getenv("CFD_EXPLICIT_WRAP"); return e ? atoi(e) : 1; }();
+  const bool wrap8 = wrap_ok && !forced_cols && Ny == 256 && fills_gpu && full_launch;
+  if (wrap8) grid = dim3(1, (tile_count + kWarpsPerCta - 1) / kWarpsPerCta, batch);
   int pattern = 0, nt = 0;
   for (int t = 0; t < c.n_terms; ++t) {
     const int kind = c.term_kind[t];
@@ -450,18 +480,21 @@ int launch_explicit_2d_slab(cudaStream_t stream, SlabSrc su, SlabSrc sv, SlabSrc
       if (((pattern >> (2 * q)) & 3) == code) return set_error_msg("each forcing kind may appear once");
     pattern |= code << (2 * nt++);
   }
-#define CFD_EXPL_LAUNCH(P, CC, LZ)                                                          \
-  explicit2d_kernel<P, CC, LZ><<<grid, 32 * kWarpsPerCta, 0, stream>>>(                        \
+#define CFD_EXPL_LAUNCH(P, CC, LZ, WR)                                                      \
+  explicit2d_kernel<P, CC, LZ, WR><<<grid, 32 * kWarpsPerCta, 0, stream>>>(                    \
       su, sv, sq, us, vs, rhs, Nx, Ny, row0, nx_global, c, dvdt_mode, TX, tile_begin)
-#define CFD_EXPL_CASE(P)                    \
-  case P:                                   \
-    if (cols == 2) {                        \
-      if (qprev) CFD_EXPL_LAUNCH(P, 2, true);  \
-      else CFD_EXPL_LAUNCH(P, 2, false);    \
-    } else {                                \
-      if (qprev) CFD_EXPL_LAUNCH(P, 4, true);  \
-      else CFD_EXPL_LAUNCH(P, 4, false);    \
-    }                                       \
+#define CFD_EXPL_CASE(P)                           \
+  case P:                                          \
+    if (wrap8) {                                   \
+      if (qprev) CFD_EXPL_LAUNCH(P, 8, true, true);   \
+      else CFD_EXPL_LAUNCH(P, 8, false, true);     \
+    } else if (cols == 2) {                        \
+      if (qprev) CFD_EXPL_LAUNCH(P, 2, true, false);  \
+      else CFD_EXPL_LAUNCH(P, 2, false, false);    \
+    } else {                                       \
+      if (qprev) CFD_EXPL_LAUNCH(P, 4, true, false);  \
+      else CFD_EXPL_LAUNCH(P, 4, false, false);    \
+    }                                              \
     break;
   switch (pattern) {
     CFD_EXPL_CASE(0)
