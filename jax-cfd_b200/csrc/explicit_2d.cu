@@ -237,7 +237,10 @@ explicit2d_kernel(SlabSrc su, SlabSrc sv, SlabSrc sq, float* __restrict__ us,
 
   // two rows per trip in the lazy kernel: half of the window-rotation moves disappear (423 -> 407 us
   // at 8192^2; the plain kernel gets slower with it, 407 -> 421 us, and keeps one row per trip)
-  constexpr int kRowUnroll = LAZY ? 2 : 1;
+#ifndef CFD_WRAP_UNROLL
+#define CFD_WRAP_UNROLL 1
+#endif
+  constexpr int kRowUnroll = LAZY ? (C > 4 ? CFD_WRAP_UNROLL : 2) : 1;
 #pragma unroll kRowUnroll
   for (int i = i0 - 1; i < iend; ++i) {
     // ---- column halos of row i (and v[i+1][-1]) from neighbouring lanes
