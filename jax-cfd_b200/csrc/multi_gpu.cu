@@ -11,18 +11,18 @@
 //     between the phases.  No NCCL on the data path; the host side only exchanges 64-byte IPC
 //     handles once (any transport: torch.distributed in jax_cfd_b200.distributed).
 //
-// Default since round 2 ("push" mode, CFD_DIST_MODE=pull selects the scheme above): the two
-// transposes are PUSHED by copy kernels on a second, high-priority stream while the compute kernels
-// keep running on local memory only:
-//   * the stencil and the row FFT run block by block over the slab's rows; as soon as a block of
-//     rows is transformed its part of every ky line is stored into the line owners' line buffers
-//     (posted NVLink writes of >= 2 KB pieces), overlapping the stencil / row FFT of the next block;
-//   * the x-direction kernel then works on a purely local line buffer (no peer table, same speed
-//     as on one GPU), chunk of lines by chunk of lines; finished chunks are pushed back to the slab
-//     owners while the next chunk is transformed;
-//   * per-(rank, block) flags written after each push replace two of the three global barriers:
-//     a rank waits only for the data it is about to read; the barrier before the stencil becomes
-//     a neighbour-only flag.  Line buffers are double buffered across steps.
+// Default since round 2 ("push" mode, CFD_DIST_MODE=pull selects the scheme above):
+//   * the stencil (two launches) and the row FFT run block by block over the slab's rows; as soon
+//     as a block of rows is transformed, a TMA bulk-copy kernel on a second, high-priority stream
+//     (slab_push_tma_kernel: cp.async.bulk global -> shared -> peer global, SASS UBLKCP) stores its
+//     part of every ky line into the line owners' receive buffers, overlapping the stencil / row
+//     FFT of the next block; a per-(rank, block) flag follows every copy;
+//   * the x-direction kernel then READS only local memory (its own spectrum + the receive buffers
+//     through the peer table) and WRITES its results straight into the slab owners' spectra --
+//     posted NVLink stores, so the backward transpose needs neither a copy nor a buffer; one flag
+//     per rank says "my lines are back";
+//   * flags replace two of the three global barriers: a rank waits only for the data it is about
+//     to read; the barrier before the stencil becomes a neighbour-only flag.
 // Results stay bit-identical to the single-GPU path (same kernels, same arithmetic).
 #include <stdlib.h>
 #include <string.h>
@@ -126,41 +126,6 @@ __global__ void slab_wait_kernel(unsigned long long* flags, int base, int nsrc, 
   const int i = threadIdx.x;
   if (i < nsrc * nper) spin_until(flags + base + (i / nper) * kMaxBlocks + i % nper, value, flags + kSlotErr, budget);
   __threadfence_system();
-}
-
-// Block copy between a slab-local spectrum T[ky][x_loc] and the line buffers L[line][x_global] (same
-// layout: plain, or pair-interleaved with a pair of lines as one row): for every destination rank
-// (blockIdx.y) `nlines` rows of `len` points, one float4 per thread and trip.
-//   FWD  = true:  src = own T, lines [r * nlines, (r + 1) * nlines), points [x0, x0 + len)
-//                 dst = rank r's line buffer, line l, points [dst_x0, dst_x0 + len)
-//   FWD  = false: src = own line buffer, lines [l0, l0 + nlines), points [r * len, (r + 1) * len)
-//                 dst = rank r's T, lines [dst_l0, dst_l0 + nlines), all `len` = Nloc points
-struct PushDst {
-  float2* p[CFD_MAX_PEERS];
-};
-template <bool FWD, bool PAIRED>
-__global__ void __launch_bounds__(256)
-slab_push_kernel(const float2* __restrict__ src, PushDst dst, int nlines, int len, int nloc, size_t nxg,
-                 int x0, int dst_x0, int l0, int dst_l0) {
-  static_assert(!PAIRED, "both buffers share the layout: a pair of lines is one row of twice the length");
-  const int r = blockIdx.y;
-  float2* __restrict__ d = dst.p[r];
-  const int nvec = len / 2;  // float4 = two consecutive points
-  for (int l = blockIdx.x; l < nlines; l += gridDim.x) {
-    const float2* s;
-    float2* o;
-    if (FWD) {
-      s = src + ((size_t)r * nlines + l) * nloc + x0;
-      o = d + (size_t)l * nxg + dst_x0;
-    } else {
-      s = src + (size_t)(l0 + l) * nxg + (size_t)r * len;
-      o = d + (size_t)(dst_l0 + l) * nloc;
-    }
-    const float4* s4 = reinterpret_cast<const float4*>(s);
-    float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < nvec; i += 256) o4[i] = __ldcs(s4 + i);
-  }
 }
 
 // layout of the shared (IPC-exported) allocation, identical on every rank; units = floats
@@ -294,8 +259,8 @@ int xpass_staged(cfd_plan* p, cudaStream_t st, const SharedLayout& L, int lnloc)
 // One thread per CTA drives a ring of shared-memory stages: cp.async.bulk global -> shared (completion
 // on an mbarrier), then cp.async.bulk shared -> global (local HBM or the peer's memory over NVLink).
 // Megabytes stay in flight per CTA-sized footprint of 32 threads, so a few dozen CTAs saturate
-// NVLink while the SMs keep computing -- the LSU-driven slab_push_kernel above needed the whole GPU
-// for that (scripts/ubench/p2p.cu: 650 GB/s with >= 148 CTAs, 200 GB/s with 48).
+// NVLink while the SMs keep computing -- LSU-driven copy kernels (the first push implementation)
+// need the whole GPU for that (scripts/ubench/p2p.cu: 650 GB/s with >= 148 CTAs, 200 GB/s with 48).
 // A "row" is a line (plain layout) or a pair of lines (pair-interleaved layout): both buffers use
 // the same layout in push mode, so every piece is one contiguous run of bytes.
 struct TmaPush {
@@ -369,15 +334,6 @@ __global__ void __launch_bounds__(32) slab_push_tma_kernel(TmaPush a) {
     }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes performed before the kernel ends
-}
-
-// CFD_DIST_COPY=lsu selects slab_push_kernel instead
-bool tma_copies() {
-  static const bool v = [] {
-    const char* e = getenv("CFD_DIST_COPY");
-    return !(e && strcmp(e, "lsu") == 0);
-  }();
-  return v;
 }
 
 int launch_push_tma(cudaStream_t st, const TmaPush& a, int ctas, int world) {
@@ -460,7 +416,10 @@ int step_push(cfd_plan* p, cudaStream_t st, const SharedLayout& L, const StepCon
   int all[CFD_MAX_PEERS];
   for (int r = 0; r < W; ++r) all[r] = r;
   static const int wish_ctas = [] { const char* e = getenv("CFD_DIST_COPY_CTAS"); return e ? atoi(e) : 0; }();
-  const int tma_ctas = wish_ctas > 0 ? wish_ctas : (W <= 2 ? 8 : (W <= 4 ? 6 : 4));  // per destination rank
+  // CTAs of the copy kernel per destination rank: enough bytes in flight to fill NVLink, few enough
+  // to leave the SMs to the row FFT.  Measured: 2 GPUs (one destination) 8 / 32 CTAs = 1.343 / 1.264
+  // ms per step; 4 GPUs 6 / 12 / 24 = 1.495 / 1.537 / 1.539 ms.
+  const int tma_ctas = wish_ctas > 0 ? wish_ctas : (W <= 2 ? 32 : (W <= 4 ? 6 : 4));
   auto recv = [&](int owner, int source) {  // R_owner[source]
     return reinterpret_cast<float2*>(fptr(p->peer_shared[owner], L.off_L[0])) + (size_t)source * blk;
   };
