@@ -254,10 +254,14 @@ def _device_count():
     return 0
 
 
-@pytest.mark.parametrize('world,shape,nsteps', [(2, (256, 512), 6), (2, (2048, 1024), 4),
-                                                (4, (1024, 512), 4), (8, (2048, 1024), 4),
-                                                (2, (64, 32, 64), 3), (8, (128, 128, 64), 2)])
-def test_slab_decomposition_is_bitwise_equal_to_one_gpu(world, shape, nsteps):
+@pytest.mark.parametrize('world,shape,nsteps,env', [
+    (2, (256, 512), 6, {}), (2, (2048, 1024), 4, {}), (4, (1024, 512), 4, {}), (8, (2048, 1024), 4, {}),
+    # 32768-point x lines: the cluster / DSMEM kernel writing to the peers, plain and pair-interleaved layout
+    (2, (32768, 64), 3, {}), (2, (32768, 64), 3, {'CFD_T_PAIRED': '1'}), (8, (32768, 256), 2, {'CFD_T_PAIRED': '1'}),
+    (2, (2048, 1024), 4, {'CFD_DIST_MODE': 'pull'}),
+    # 3-D with the Smagorinsky closure (config #5)
+    (2, (64, 32, 64), 3, {}), (8, (128, 128, 64), 2, {})])
+def test_slab_decomposition_is_bitwise_equal_to_one_gpu(world, shape, nsteps, env):
   """Row (e): the slab-decomposed step on `world` GPUs reproduces the single-GPU result bit for
   bit (tests/mgpu_worker.py under torchrun, one rank per GPU).  Skipped on boxes with fewer GPUs."""
   if _device_count() < world:
@@ -266,7 +270,7 @@ def test_slab_decomposition_is_bitwise_equal_to_one_gpu(world, shape, nsteps):
   cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
          '--master-addr', '127.0.0.1', '--master-port', str(port),
          os.path.join(ROOT, 'tests', 'mgpu_worker.py'), *[str(n) for n in shape], str(nsteps)]
-  out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+  out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, **env})
   assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
   assert 'MGPU PASS' in out.stdout
   assert out.stdout.count('bitwise=True') == len(shape) + 1, out.stdout
