@@ -262,14 +262,96 @@ constexpr int kHZ = kBZ + 8;  // row: [pad pad h h | 64 interior (16-byte aligne
 constexpr int kZ0 = 4;        // column of the first interior cell
 constexpr int kPlane = kHY * kHZ;  // floats per component per slot
 
+// Readers of the shared-memory plane rings (velocity, nu_t) and the strain / eddy-viscosity samples
+// of subgrid_models.py:40-134 expressed through them (used by the Smagorinsky kernels below and by
+// the fused stencil).
+template <int AX, class R>
+__device__ __forceinline__ float fwd_r(const R& rd, int comp, int p0, int p1, int p2, float inv_h) {
+  int d[3] = {p0, p1, p2};
+  const float a = rd(comp, d[0], d[1], d[2]);
+  d[AX] += 1;
+  return (rd(comp, d[0], d[1], d[2]) - a) * inv_h;
+}
+template <int I, int J, class R>
+__device__ __forceinline__ float strain_r(const R& rd, int p0, int p1, int p2, const float* inv_h) {
+  return 0.5f * (fwd_r<J>(rd, I, p0, p1, p2, inv_h[J]) + fwd_r<I>(rd, J, p0, p1, p2, inv_h[I]));
+}
+template <int I, int J, class R>
+__device__ __forceinline__ float strain_center_r(const R& rd, const float* inv_h) {
+  if (I == J) {
+    int d[3] = {0, 0, 0};
+    d[I] = -1;
+    return strain_r<I, I>(rd, d[0], d[1], d[2], inv_h);
+  }
+  constexpr int A = I < J ? I : J, B = I < J ? J : I;
+  float r[2];
+#pragma unroll
+  for (int sb = 0; sb < 2; ++sb) {
+    int d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+    d0[B] = d1[B] = sb - 1;
+    d0[A] = -1;
+    const float lo = strain_r<I, J>(rd, d0[0], d0[1], d0[2], inv_h);
+    const float hi = strain_r<I, J>(rd, d1[0], d1[1], d1[2], inv_h);
+    r[sb] = 0.5f * lo + 0.5f * hi;
+  }
+  return 0.5f * r[0] + 0.5f * r[1];
+}
+template <int I, int J, class NR>
+__device__ __forceinline__ float nu_at_r(const NR& nr, int p0, int p1, int p2) {
+  if (I == J) {
+    int d[3] = {p0, p1, p2};
+    d[I] += 1;
+    return nr(d[0], d[1], d[2]);
+  }
+  constexpr int A = I < J ? I : J, B = I < J ? J : I;
+  float r[2];
+#pragma unroll
+  for (int sb = 0; sb < 2; ++sb) {
+    int d0[3] = {p0, p1, p2}, d1[3] = {p0, p1, p2};
+    d0[B] += sb;
+    d1[B] += sb;
+    d1[A] += 1;
+    r[sb] = 0.5f * nr(d0[0], d0[1], d0[2]) + 0.5f * nr(d1[0], d1[1], d1[2]);
+  }
+  return 0.5f * r[0] + 0.5f * r[1];
+}
+
+// Readers over three consecutive planes (x-1, x, x+1) of a shared-memory ring
+struct VelPlanes {
+  const float* pl[3];
+  int own;
+  __device__ __forceinline__ float operator()(int comp, int d0, int d1, int d2) const {
+    return pl[d0 + 1][comp * kPlane + own + d1 * kHZ + d2];
+  }
+};
+struct NutPlanes {
+  const float* pl[3];
+  int own;
+  __device__ __forceinline__ float operator()(int d0, int d1, int d2) const {
+    return pl[d0 + 1][own + d1 * kHZ + d2];
+  }
+};
+
 // HAS_FORCE = false: no forcing term other than Smagorinsky (which the smag kernels add) -- the
 // runtime walk over the term list, 6 times per plane, is compiled out.
-template <bool HAS_FORCE>
-__global__ void __launch_bounds__(256, 4)
-explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ us,
+//
+// SMAG = true: the Smagorinsky acceleration -div tau (subgrid_models.py:101-134, the LAST forcing term,
+// subgrid_models.py:188-213) is added in the same kernel from a second ring of nu_t planes: the
+// separate smag_acc_march_kernel re-loads the three velocity planes and read-modify-writes u*
+// (-36 B/cell) and is latency bound on exactly those loads.  Same arithmetic, same operation order
+// (u* = (c0 + dt dv) + scale (-d)): bit-identical to the two-kernel path (CFD_SMAG_FUSED=0).
+// Two CTAs per SM (117 registers, no spills): measured at 512^3, stencil + closure 3.51 ms as two
+// kernels, 4.00 / 3.91 / 2.71 ms fused with 3 / 4 / 2 CTAs per SM (85 / 64 / 128-register caps).
+#ifndef CFD_SMAG_MINB
+#define CFD_SMAG_MINB 2
+#endif
+template <bool HAS_FORCE, bool SMAG = false>
+__global__ void __launch_bounds__(256, SMAG ? CFD_SMAG_MINB : 4)
+explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, SlabSrc snut, float* __restrict__ us,
                         float* __restrict__ vs, float* __restrict__ ws, int N0, int N1, int N2,
                         StepConsts c, int dvdt_mode, int TX, int row0) {
-  extern __shared__ __align__(16) float sm3[];  // [slot][comp][kHY][kHZ]
+  extern __shared__ __align__(16) float sm3[];  // [slot][comp][kHY][kHZ] (+ SMAG: [slot][kHY][kHZ] of nu_t)
+  float* const smn = sm3 + kSlots * 3 * kPlane;
   const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
   const int tilesz = N2 / kBZ, tilesy = N1 / kBY;
   const int tz = blockIdx.x % tilesz, tyb = (blockIdx.x / tilesz) % tilesy;
@@ -306,6 +388,7 @@ explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ 
     ld_dst = r * kHZ + (hc < 2 ? kZ0 - 2 + hc : kZ0 + kBZ + (hc - 2));
   }
   auto slot_base = [&](int plane) { return sm3 + ((plane + kSlots) & (kSlots - 1)) * (3 * kPlane); };
+  auto nslot_base = [&](int plane) { return smn + ((plane + kSlots) & (kSlots - 1)) * kPlane; };
   auto load_plane = [&](int i) {
     float* dst = slot_base(i);
     if (tid < 192) {
@@ -313,10 +396,13 @@ explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ 
       for (int comp = 0; comp < 3; ++comp)
         *reinterpret_cast<float4*>(dst + comp * kPlane + ld_dst) =
             ldg4(slab_plane(f[comp], i, N0, planeN) + boff + ld_src);
+      if (SMAG)
+        *reinterpret_cast<float4*>(nslot_base(i) + ld_dst) = ldg4(slab_plane(snut, i, N0, planeN) + boff + ld_src);
     } else if (tid < 240) {
 #pragma unroll
       for (int comp = 0; comp < 3; ++comp)
         dst[comp * kPlane + ld_dst] = __ldg(slab_plane(f[comp], i, N0, planeN) + boff + ld_src);
+      if (SMAG) nslot_base(i)[ld_dst] = __ldg(slab_plane(snut, i, N0, planeN) + boff + ld_src);
     }
   };
   // value of component `comp` at plane (pa: i, pb: i+1, pm: i-1), row j + dy, column k + dz
@@ -367,9 +453,13 @@ explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ 
       Fxp[A][col] = face_flux(X[A][1][col], X[A][2][col], X[A][3][col], X[A][4][col], U, dthh[0]);
     }
 
+  const float smag_scale = (dvdt_mode ? 1.f : c.dt) * c.inv_rho;
   for (int i = i0; i < iend; ++i) {
     pa = slot_base(i);
     pb = slot_base(i + 1);
+    // SMAG reads plane i-1 as well, whose slot the load of plane i+3 reuses: nobody may start the
+    // next plane's load before everyone has finished this plane
+    if (SMAG && i > i0) __syncthreads();
     load_plane(i + 2);
     // shift the register window: offsets -2..+1 <- old -1..+2
 #pragma unroll
@@ -389,6 +479,35 @@ explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ 
 
     const int jg = j0 + ty, kg = k0 + 2 * lane;
     const size_t cell0 = (size_t)i * planeN + (size_t)jg * N2 + kg;
+    float sd[3][2];  // SMAG: div tau per component and column
+    if (SMAG) {
+#pragma unroll
+      for (int col = 0; col < 2; ++col) {
+        const VelPlanes rd = {{slot_base(i - 1), pa, pb}, own + col};
+        const NutPlanes nr = {{nslot_base(i - 1), nslot_base(i), nslot_base(i + 1)}, own + col};
+#define TAU(I, J, p0, p1, p2) (-2.f * nu_at_r<I, J>(nr, p0, p1, p2) * strain_r<I, J>(rd, p0, p1, p2, c.inv_h))
+        // every distinct tau sample once (tau_ij == tau_ji), same order as smag_acc_march_kernel
+        const float t00 = TAU(0, 0, 0, 0, 0), t00m = TAU(0, 0, -1, 0, 0);
+        const float t11 = TAU(1, 1, 0, 0, 0), t11m = TAU(1, 1, 0, -1, 0);
+        const float t22 = TAU(2, 2, 0, 0, 0), t22m = TAU(2, 2, 0, 0, -1);
+        const float t01 = TAU(0, 1, 0, 0, 0), t01x = TAU(0, 1, -1, 0, 0), t01y = TAU(0, 1, 0, -1, 0);
+        const float t02 = TAU(0, 2, 0, 0, 0), t02x = TAU(0, 2, -1, 0, 0), t02z = TAU(0, 2, 0, 0, -1);
+        const float t12 = TAU(1, 2, 0, 0, 0), t12y = TAU(1, 2, 0, -1, 0), t12z = TAU(1, 2, 0, 0, -1);
+#undef TAU
+        float d0 = (t00 - t00m) * c.inv_h[0];
+        d0 += (t01 - t01y) * c.inv_h[1];
+        d0 += (t02 - t02z) * c.inv_h[2];
+        float d1 = (t01 - t01x) * c.inv_h[0];
+        d1 += (t11 - t11m) * c.inv_h[1];
+        d1 += (t12 - t12z) * c.inv_h[2];
+        float d2 = (t02 - t02x) * c.inv_h[0];
+        d2 += (t12 - t12y) * c.inv_h[1];
+        d2 += (t22 - t22m) * c.inv_h[2];
+        sd[0][col] = d0;
+        sd[1][col] = d1;
+        sd[2][col] = d2;
+      }
+    }
 #pragma unroll
     for (int A = 0; A < 3; ++A) {
       // unit vector of A for the face-velocity interpolation (interpolation.py:57-62)
@@ -446,6 +565,7 @@ explicit3d_march_kernel(SlabSrc su, SlabSrc sv, SlabSrc sw, float* __restrict__ 
           dv = fmaf(fsum, c.inv_rho, dv);
         }
         out[col] = dvdt_mode ? dv : c0 + c.dt * dv;
+        if (SMAG) out[col] += smag_scale * (-sd[A][col]);
       }
       *reinterpret_cast<float2*>(o[A] + cell0) = make_float2(out[0], out[1]);
     }
@@ -592,73 +712,6 @@ __global__ void smag_acc_fields_kernel(Sf S, const float* __restrict__ nut, floa
 //   smag_acc_march_kernel:  u* += scale * (-div tau)        (subgrid_models.py:101-134, 188-213)
 // The arithmetic (operation order included) is that of strain<> / strain_center<> / nu_at<> above,
 // read through shared-memory planes instead of global memory.
-template <int AX, class R>
-__device__ __forceinline__ float fwd_r(const R& rd, int comp, int p0, int p1, int p2, float inv_h) {
-  int d[3] = {p0, p1, p2};
-  const float a = rd(comp, d[0], d[1], d[2]);
-  d[AX] += 1;
-  return (rd(comp, d[0], d[1], d[2]) - a) * inv_h;
-}
-template <int I, int J, class R>
-__device__ __forceinline__ float strain_r(const R& rd, int p0, int p1, int p2, const float* inv_h) {
-  return 0.5f * (fwd_r<J>(rd, I, p0, p1, p2, inv_h[J]) + fwd_r<I>(rd, J, p0, p1, p2, inv_h[I]));
-}
-template <int I, int J, class R>
-__device__ __forceinline__ float strain_center_r(const R& rd, const float* inv_h) {
-  if (I == J) {
-    int d[3] = {0, 0, 0};
-    d[I] = -1;
-    return strain_r<I, I>(rd, d[0], d[1], d[2], inv_h);
-  }
-  constexpr int A = I < J ? I : J, B = I < J ? J : I;
-  float r[2];
-#pragma unroll
-  for (int sb = 0; sb < 2; ++sb) {
-    int d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
-    d0[B] = d1[B] = sb - 1;
-    d0[A] = -1;
-    const float lo = strain_r<I, J>(rd, d0[0], d0[1], d0[2], inv_h);
-    const float hi = strain_r<I, J>(rd, d1[0], d1[1], d1[2], inv_h);
-    r[sb] = 0.5f * lo + 0.5f * hi;
-  }
-  return 0.5f * r[0] + 0.5f * r[1];
-}
-template <int I, int J, class NR>
-__device__ __forceinline__ float nu_at_r(const NR& nr, int p0, int p1, int p2) {
-  if (I == J) {
-    int d[3] = {p0, p1, p2};
-    d[I] += 1;
-    return nr(d[0], d[1], d[2]);
-  }
-  constexpr int A = I < J ? I : J, B = I < J ? J : I;
-  float r[2];
-#pragma unroll
-  for (int sb = 0; sb < 2; ++sb) {
-    int d0[3] = {p0, p1, p2}, d1[3] = {p0, p1, p2};
-    d0[B] += sb;
-    d1[B] += sb;
-    d1[A] += 1;
-    r[sb] = 0.5f * nr(d0[0], d0[1], d0[2]) + 0.5f * nr(d1[0], d1[1], d1[2]);
-  }
-  return 0.5f * r[0] + 0.5f * r[1];
-}
-
-// Readers over three consecutive planes (x-1, x, x+1) of a shared-memory ring
-struct VelPlanes {
-  const float* pl[3];
-  int own;
-  __device__ __forceinline__ float operator()(int comp, int d0, int d1, int d2) const {
-    return pl[d0 + 1][comp * kPlane + own + d1 * kHZ + d2];
-  }
-};
-struct NutPlanes {
-  const float* pl[3];
-  int own;
-  __device__ __forceinline__ float operator()(int d0, int d1, int d2) const {
-    return pl[d0 + 1][own + d1 * kHZ + d2];
-  }
-};
-
 // Per-thread source / destination offsets of the plane loader (see explicit3d_march_kernel)
 __device__ __forceinline__ void plane_loader_offsets(int tid, int j0, int k0, int N1, int N2,
                                                      int* ld_src, int* ld_dst) {
@@ -878,6 +931,8 @@ bool explicit_3d_uses_march(int N0, int N1, int N2);
 // x rows per CTA of the marching kernels: long enough to amortise the 3-plane prologue, short
 // enough to fill the GPU
 static int march_tx(int batch, int N0, int N1, int N2) {
+  static const int forced = [] { const char* e = getenv("CFD_MARCH_TX"); return e ? atoi(e) : 0; }();
+  if (forced >= 4) return forced;
   int TX = 32;
   while (TX > 8 && (long)(N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX) * batch < 148L * 4) TX /= 2;
   return TX;
@@ -948,27 +1003,54 @@ bool explicit_3d_uses_march(int N0, int N1, int N2) {
   return use_march && N1 % kBY == 0 && N2 % kBZ == 0 && N0 >= 4;
 }
 
-// the marching stencil on a slab (row0 = first GLOBAL plane of the slab, for the forcing profiles)
+// CFD_SMAG_FUSED=0: -div tau by the separate smag_acc_march_kernel instead of inside the stencil
+bool smag_fused() {
+  static const int v = [] {
+    const char* e = getenv("CFD_SMAG_FUSED");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
+// the marching stencil on a slab (row0 = first GLOBAL plane of the slab, for the forcing profiles);
+// snut != nullptr: the Smagorinsky acceleration is added in the same kernel from these nu_t planes
 int launch_explicit_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw, float* us, float* vs, float* ws,
-                            int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode, int row0) {
+                            int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode, int row0,
+                            const SlabSrc* snut) {
   if (!explicit_3d_uses_march(N0, N1, N2)) return set_error_msg("slab needs N1 % 8 == 0, N2 % 64 == 0, >= 4 planes");
   const int TX = march_tx(batch, N0, N1, N2);
   constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
+  constexpr size_t smem_smag = (size_t)kSlots * 4 * kPlane * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true>,
+    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false>,
+    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_smag));
+    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_smag));
     attr_set = true;
   }
   dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
   bool has_force = false;  // a non-zero forcing sum (an all-Smagorinsky list adds +0 here)
   for (int t = 0; t < c.n_terms; ++t) has_force = has_force || c.term_kind[t] != CFD_FORCE_SMAGORINSKY;
-  if (has_force)
-    explicit3d_march_kernel<true><<<grid, 256, smem, st>>>(su, sv, sw, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX, row0);
-  else
-    explicit3d_march_kernel<false><<<grid, 256, smem, st>>>(su, sv, sw, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX, row0);
+  const SlabSrc none = {nullptr, nullptr, nullptr};
+  if (snut) {
+    if (has_force)
+      explicit3d_march_kernel<true, true><<<grid, 256, smem_smag, st>>>(su, sv, sw, *snut, us, vs, ws, N0, N1, N2, c,
+                                                                        dvdt_mode, TX, row0);
+    else
+      explicit3d_march_kernel<false, true><<<grid, 256, smem_smag, st>>>(su, sv, sw, *snut, us, vs, ws, N0, N1, N2, c,
+                                                                         dvdt_mode, TX, row0);
+  } else if (has_force) {
+    explicit3d_march_kernel<true, false><<<grid, 256, smem, st>>>(su, sv, sw, none, us, vs, ws, N0, N1, N2, c,
+                                                                  dvdt_mode, TX, row0);
+  } else {
+    explicit3d_march_kernel<false, false><<<grid, 256, smem, st>>>(su, sv, sw, none, us, vs, ws, N0, N1, N2, c,
+                                                                   dvdt_mode, TX, row0);
+  }
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1000,9 +1082,15 @@ int launch_explicit_3d(cudaStream_t st, const float* u, const float* v, const fl
   const size_t cells = (size_t)N0 * N1 * N2;
   if (explicit_3d_uses_march(N0, N1, N2)) {
     const SlabSrc su = {u, u, u}, sv = {v, v, v}, sw = {w, w, w};
-    if (int e = launch_explicit_3d_slab(st, su, sv, sw, us, vs, ws, batch, N0, N1, N2, c, dvdt_mode, 0)) return e;
-    if (nut && !sfield && smag_uses_tiles(N0, N1, N2)) {
-      const SlabSrc sn = {nut, nut, nut};
+    const SlabSrc sn = {nut, nut, nut};
+    const bool tiled_smag = nut && !sfield && smag_uses_tiles(N0, N1, N2);
+    const bool fused = tiled_smag && smag_fused();
+    if (int e = launch_explicit_3d_slab(st, su, sv, sw, us, vs, ws, batch, N0, N1, N2, c, dvdt_mode, 0,
+                                        fused ? &sn : nullptr))
+      return e;
+    if (fused) {
+      // -div tau was added inside the stencil
+    } else if (tiled_smag) {
       if (int e = launch_smag_acc_3d_slab(st, su, sv, sw, sn, us, vs, ws, batch, N0, N1, N2, c, dvdt_mode)) return e;
     } else if (nut && sfield) {
       dim3 g2((unsigned)((cells + 127) / 128), batch);

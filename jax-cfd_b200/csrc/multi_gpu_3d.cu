@@ -24,7 +24,9 @@ namespace cfd {
 int launch_smag_nut_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw, float* nut, int batch, int N0,
                             int N1, int N2, const StepConsts& c);
 int launch_explicit_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw, float* us, float* vs, float* ws,
-                            int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode, int row0);
+                            int batch, int N0, int N1, int N2, const StepConsts& c, int dvdt_mode, int row0,
+                            const SlabSrc* snut);
+bool smag_fused();
 int launch_smag_acc_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw, SlabSrc snut, float* us,
                             float* vs, float* ws, int batch, int N0, int N1, int N2, const StepConsts& c,
                             int dvdt_mode);
@@ -178,14 +180,18 @@ int dist3_advance(cfd_plan* p, cudaStream_t st, int nsteps, const StepConsts& c)
       if (int e = launch_smag_nut_3d_slab(st, su, sv, sw, nut, 1, nloc, N1, N2, c)) return e;
       prof_mark(p, st, "smag_nut");
     }
-    if (int e = launch_explicit_3d_slab(st, su, sv, sw, us[0], us[1], us[2], 1, nloc, N1, N2, c, 0, rank * nloc))
+    const SlabSrc snut = src3(L.off_nut);
+    const bool fused = smag && smag_fused();
+    if (fused) {
+      if (int e = slab_barrier(p, st)) return e;  // the neighbours' nu_t planes are complete
+    }
+    if (int e = launch_explicit_3d_slab(st, su, sv, sw, us[0], us[1], us[2], 1, nloc, N1, N2, c, 0, rank * nloc,
+                                        fused ? &snut : nullptr))
       return e;
     prof_mark(p, st, "explicit_3d");
-    if (smag) {
+    if (smag && !fused) {
       if (int e = slab_barrier(p, st)) return e;  // the neighbours' nu_t planes are complete
-      if (int e = launch_smag_acc_3d_slab(st, su, sv, sw, src3(L.off_nut), us[0], us[1], us[2], 1, nloc, N1, N2,
-                                          c, 0))
-        return e;
+      if (int e = launch_smag_acc_3d_slab(st, su, sv, sw, snut, us[0], us[1], us[2], 1, nloc, N1, N2, c, 0)) return e;
       prof_mark(p, st, "smag_acc");
     }
     if (int e = slab_barrier(p, st)) return e;  // the previous rank's last u* plane is complete

@@ -1,0 +1,18 @@
+python scripts/state_hash.py 2>&1 | tail -2
+CFD_SMAG_FUSED=0 python scripts/state_hash.py 2>&1 | tail -1
+python -m pytest tests -m gpu -q -x -k "3d or tgv or smagorinsky or slab_stepper" 2>&1 | tail -3
+run() { # name, workload, steps, warmup, env...
+  name=$1; wl=$2; st=$3; wu=$4; shift; shift; shift; shift
+  env "$@" timeout 600 python bench.py --workload $wl --gpus 1 --steps $st --warmup $wu --no-cpu-baseline > gpurun_out/r2z_$name.json 2> gpurun_out/r2z_$name.err
+  python - <<PY
+import json
+try:
+  d=json.loads([l for l in open('gpurun_out/r2z_$name.json') if l.startswith('{')][-1])
+  k = d.get('kernel_ms_rank0') or d.get('roofline_step',{}).get('kernel_ms')
+  print('$name', 'ms/step', round(d['ms_per_step'],5), 'value', round(d['value'],2), {a:round(b,4) for a,b in k.items()})
+except Exception as e:
+  print('$name FAILED', e); print(open('gpurun_out/r2z_$name.err').read()[-1500:])
+PY
+}
+run tgv512_fused TGV512 10 3 A=1
+run tgv512_unfused TGV512 10 3 CFD_SMAG_FUSED=0
