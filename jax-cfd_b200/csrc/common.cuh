@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/cfd_b200.h"
 
 namespace cfd {
@@ -110,5 +113,24 @@ __device__ __forceinline__ float face_flux(float cL, float c0, float cR, float c
 int set_error(const char* what, cudaError_t e, const char* file, int line);
 int set_error_msg(const char* msg);
 void count_launch(int n = 1);
+
+// Opt-in to `bytes` of dynamic shared memory for `kernel` on the CURRENT device, once per (kernel,
+// device): the attribute is per device, a process may drive several, and the call is kept off the
+// launch path (CUDA-graph captures then record plain launches).
+template <typename K>
+int opt_in_smem(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> done[64];  // per device, keyed by kernel
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[dev & 63][reinterpret_cast<const void*>(kernel)];
+  if (bytes > have) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem)", e, __FILE__, __LINE__);
+    have = bytes;
+  }
+  return 0;
+}
 
 }  // namespace cfd

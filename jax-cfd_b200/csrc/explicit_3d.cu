@@ -953,12 +953,7 @@ int launch_smag_nut_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw,
   if (!explicit_3d_uses_march(N0, N1, N2)) return set_error_msg("slab needs N1 % 8 == 0, N2 % 64 == 0, >= 4 planes");
   const int TX = march_tx(batch, N0, N1, N2);
   constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFD_CUDA_OK(cudaFuncSetAttribute(smag_nut_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    attr_set = true;
-  }
+  if (int e = opt_in_smem(smag_nut_march_kernel, smem)) return e;
   dim3 g((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
   smag_nut_march_kernel<<<g, 256, smem, st>>>(su, sv, sw, nut, N0, N1, N2, c, TX);
   count_launch();
@@ -1021,22 +1016,16 @@ int launch_explicit_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw,
   const int TX = march_tx(batch, N0, N1, N2);
   constexpr size_t smem = (size_t)kSlots * 3 * kPlane * sizeof(float);
   constexpr size_t smem_smag = (size_t)kSlots * 4 * kPlane * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true, false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false, false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<true, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_smag));
-    CFD_CUDA_OK(cudaFuncSetAttribute(explicit3d_march_kernel<false, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_smag));
-    attr_set = true;
-  }
   dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
   bool has_force = false;  // a non-zero forcing sum (an all-Smagorinsky list adds +0 here)
   for (int t = 0; t < c.n_terms; ++t) has_force = has_force || c.term_kind[t] != CFD_FORCE_SMAGORINSKY;
   const SlabSrc none = {nullptr, nullptr, nullptr};
+  auto ready = [&](auto k, size_t bytes) { return opt_in_smem(k, bytes); };
+  if (int e = snut ? (has_force ? ready(explicit3d_march_kernel<true, true>, smem_smag)
+                               : ready(explicit3d_march_kernel<false, true>, smem_smag))
+                   : (has_force ? ready(explicit3d_march_kernel<true, false>, smem)
+                               : ready(explicit3d_march_kernel<false, false>, smem)))
+    return e;
   if (snut) {
     if (has_force)
       explicit3d_march_kernel<true, true><<<grid, 256, smem_smag, st>>>(su, sv, sw, *snut, us, vs, ws, N0, N1, N2, c,
@@ -1063,12 +1052,7 @@ int launch_smag_acc_3d_slab(cudaStream_t st, SlabSrc su, SlabSrc sv, SlabSrc sw,
   if (!explicit_3d_uses_march(N0, N1, N2)) return set_error_msg("slab needs N1 % 8 == 0, N2 % 64 == 0, >= 4 planes");
   const int TX = march_tx(batch, N0, N1, N2);
   constexpr size_t smem2 = (size_t)kSlots * 4 * kPlane * sizeof(float);
-  static bool attr2_set = false;
-  if (!attr2_set) {
-    CFD_CUDA_OK(cudaFuncSetAttribute(smag_acc_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem2));
-    attr2_set = true;
-  }
+  if (int e = opt_in_smem(smag_acc_march_kernel, smem2)) return e;
   dim3 grid((unsigned)((N1 / kBY) * (N2 / kBZ) * ((N0 + TX - 1) / TX)), batch);
   smag_acc_march_kernel<<<grid, 256, smem2, st>>>(su, sv, sw, snut, us, vs, ws, N0, N1, N2, c, dvdt_mode, TX);
   count_launch();

@@ -337,12 +337,8 @@ __global__ void __launch_bounds__(32) slab_push_tma_kernel(TmaPush a) {
 }
 
 int launch_push_tma(cudaStream_t st, const TmaPush& a, int ctas, int world) {
-  static bool attr = false;
   constexpr int smem = kTmaStages * (int)kTmaChunk;
-  if (!attr) {
-    CFD_CUDA_OK(cudaFuncSetAttribute(slab_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  if (int e = opt_in_smem(slab_push_tma_kernel, smem)) return e;
   slab_push_tma_kernel<<<dim3(ctas, world), 32, smem, st>>>(a);
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());

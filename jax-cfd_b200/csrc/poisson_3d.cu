@@ -10,6 +10,8 @@
 // The half spectrum is stored UNPACKED here (N2/2 + 1 planes): the point-reflection partner needed
 // to split a packed plane lives in a different line, and one extra plane in N2/2 is negligible.
 // Scaling: Z stores 2X and Zi consumes 2Z, all passes unnormalised -> D carries 1/(2 N0 N1 N2).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fft_rows.cuh"
 #include "fft_smem.cuh"
@@ -327,6 +329,18 @@ __global__ void correct3d_kernel(const float* __restrict__ us, const float* __re
   stg4(wo + off, ow);
 }
 
+// Rows per CTA of the 3-D row / line kernels are capped at CFD_FFT3_ROWS = 8 | 16 | 32.  Default 16:
+// with rows_for's maximum of 32 a CTA of 512-point lines is 1024 threads and 139 KB, one per SM;
+// 16 rows (512 threads, 70 KB) let three independent CTAs share an SM and overlap each other's
+// load / exchange / store phases -- measured at 512^3: the four sweeps 1.12 -> 0.95 ms.
+static int rows3_cap() {
+  static const int v = [] {
+    const char* e = getenv("CFD_FFT3_ROWS");
+    return e ? atoi(e) : 16;
+  }();
+  return v;
+}
+
 // generic launcher: KERNEL<LM, ROWS> over (count / ROWS, planes) CTAs, ROWS from rows_for(LM)
 #define CFD_ROWS_LAUNCH(KERNEL, count, planes, ...)                                              \
   do {                                                                                           \
@@ -342,7 +356,10 @@ __global__ void correct3d_kernel(const float* __restrict__ us, const float* __re
       CFD_CUDA_OK(cudaGetLastError());                                                           \
       return 0;                                                                                  \
     };                                                                                           \
-    if ((count) % ROWS_MAX == 0) return go(std::integral_constant<int, ROWS_MAX>{});             \
+    if ((count) % ROWS_MAX == 0 && rows3_cap() >= ROWS_MAX) return go(std::integral_constant<int, ROWS_MAX>{}); \
+    if constexpr (ROWS_MAX > 8) {                                                                \
+      if ((count) % 8 == 0 && rows3_cap() <= 8) return go(std::integral_constant<int, 8>{});     \
+    }                                                                                            \
     if constexpr (ROWS_MAX > 16) {                                                               \
       if ((count) % 16 == 0) return go(std::integral_constant<int, 16>{});                       \
     }                                                                                            \
