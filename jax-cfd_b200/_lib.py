@@ -249,6 +249,22 @@ class DeviceArray:
     a = self.numpy()
     return a if dtype is None else a.astype(dtype)
 
+  def __len__(self):
+    return self.shape[0]
+
+  def __getitem__(self, k):
+    """Leading-axis integer index -> a view (no copy) that keeps this array alive, e.g. one frame
+    of a stacked trajectory."""
+    if not isinstance(k, (int, np.integer)) or not self.shape:
+      raise TypeError('DeviceArray supports integer indexing of the leading axis only')
+    n = self.shape[0]
+    k = int(k) + n if k < 0 else int(k)
+    if not 0 <= k < n:
+      raise IndexError('index out of range')
+    sub = self.shape[1:]
+    step = int(np.prod(sub, dtype=np.int64)) * self.dtype.itemsize
+    return DeviceArray(sub, self.dtype, ptr=self.ptr + k * step, owner=self, device=self.device)
+
   @property
   def __cuda_array_interface__(self):
     return {'shape': self.shape, 'typestr': self.dtype.str, 'data': (self.ptr, False), 'version': 3}

@@ -30,16 +30,26 @@ def _stack(frames):
     return grids.GridVariable(_stack([fr.array for fr in frames]), first.bc)
   if isinstance(first, grids.GridArray):
     return grids.GridArray(_stack([fr.data for fr in frames]), first.offset, first.grid)
+  if isinstance(first, _lib.DeviceArray):
+    # frames stay on the device: one (steps, *shape) array filled by device-to-device copies that
+    # are ordered on the stream the steps run on -- no host round trip, no synchronisation per frame
+    # (the reference's scan stacks its outputs on the device the same way, funcutils.py:65-79)
+    out = _lib.DeviceArray((len(frames),) + first.shape, first.dtype, device=first.device)
+    for k, fr in enumerate(frames):
+      _lib.check(_lib.lib().cfd_memcpy_d2d(out.ptr + k * first.nbytes, fr.ptr, first.nbytes, None))
+    return out
   if _lib.is_device_array(first):
-    return np.stack([np.asarray(fr.numpy() if hasattr(fr, 'numpy') and isinstance(fr, _lib.DeviceArray)
-                                else fr.cpu().numpy()) for fr in frames])
+    if hasattr(first, 'new_empty'):  # torch CUDA tensors: stacked by their own library, on the device
+      import torch
+      return torch.stack(list(frames))
+    return np.stack([np.asarray(fr.cpu().numpy()) for fr in frames])
   return np.stack([np.asarray(fr) for fr in frames])
 
 
 def trajectory(step_fn: Callable, steps: int, post_process: Callable = lambda x: x, *,
                start_with_input: bool = False) -> Callable:
-  """funcutils.py:95-126: returns (final_state, stacked post-processed frames).  Frames are
-  gathered on the host (the reference's `jax.device_get` of the stacked scan outputs)."""
+  """funcutils.py:95-126: returns (final_state, stacked post-processed frames).  Device-resident
+  frames are stacked on the device (no host copy inside the loop); host frames with NumPy."""
   def multistep(values):
     frames = []
     x = values
