@@ -156,6 +156,19 @@ int cfd_transform_matmul(cfd_plan* plan, cfd_stream stream, const float* in, flo
 int cfd_scale(cfd_plan* plan, cfd_stream stream, const float* const* x, double numer, double denom,
               float* const* out);
 
+/* Post-processing either side of the path (`trajectory(post_process=...)`, funcutils.py:118-121), plan-free:
+ * resize.downsample_staggered_velocity_component (resize.py:38-74) -- of the fine faces normal to
+ * `direction` keep those on a coarse face and average the factor^(ndim-1) that tile it (a
+ * divergence-free field stays divergence free); in: (batch, *shape), out: (batch, *shape / factor).
+ * `factor` must divide every axis other than `direction` (array_utils.block_reduce,
+ * array_utils.py:155-160); along `direction` a remainder is dropped like the reference's slice. */
+int cfd_downsample_component(cfd_stream stream, const float* in, float* out, int ndim,
+                             const int64_t* shape, int batch, int direction, int factor);
+/* vorticity_2d at offset (1, 1): (S(v,+1,x) - v) / dx - (S(u,+1,y) - u) / dy, periodic
+ * (data/xarray_utils.py:155-163). */
+int cfd_vorticity_2d(cfd_stream stream, const float* u, const float* v, float* out,
+                     const int64_t* shape, int batch, double dx, double dy);
+
 /* out = x + sum_k coef[k] * y[k]  per component (the stage combinations of navier_stokes_rk,
  * time_stepping.py:96-101).  y is an array of nterms pointers-to-component-arrays. */
 int cfd_axpy(cfd_plan* plan, cfd_stream stream, const float* const* x, int nterms,

@@ -98,6 +98,12 @@ _SIGS = {
                                             ctypes.c_void_p]),
     'cfd_scale': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                  ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p)]),
+    'cfd_downsample_component': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int]),
+    'cfd_vorticity_2d': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_double,
+                                        ctypes.c_double]),
     'cfd_axpy': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                 ctypes.c_int, ctypes.POINTER(ctypes.POINTER(ctypes.c_void_p)),
                                 ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_void_p)]),

@@ -109,6 +109,48 @@ __global__ void diag2d_kernel(const float* __restrict__ u, const float* __restri
   }
 }
 
+// resize.downsample_staggered_velocity_component (resize.py:38-74): of the fine faces normal to
+// `direction` keep those that lie on a coarse face (index (I + 1) f - 1 along `direction`) and
+// average the f^(d-1) of them that tile the coarse face.  One thread per coarse value; shapes are
+// the FINE grid's (N2 = 1 in 2-D), row-major with a leading batch axis.  The sum runs over the
+// block in row-major order in float32 and is divided by the count (jnp.mean).
+__global__ void downsample_component_kernel(const float* __restrict__ in, float* __restrict__ out, int N0,
+                                            int N1, int N2, int f, int direction, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int M0 = N0 / f, M1 = N1 / f, M2 = N2 > 1 ? N2 / f : 1;
+  const int K = (int)(idx % M2), J = (int)((idx / M2) % M1), I = (int)((idx / ((size_t)M2 * M1)) % M0);
+  const size_t b = idx / ((size_t)M2 * M1 * M0);
+  const float* src = in + b * (size_t)N0 * N1 * N2;
+  const int f2 = N2 > 1 ? f : 1;
+  const int lo[3] = {I * f, J * f, K * f2};
+  int cnt[3] = {f, f, f2};
+  int beg[3] = {lo[0], lo[1], lo[2]};
+  beg[direction] = lo[direction] + (direction == 2 ? f2 : f) - 1;
+  cnt[direction] = 1;
+  float sum = 0.f;
+  for (int a = 0; a < cnt[0]; ++a)
+    for (int c = 0; c < cnt[1]; ++c)
+      for (int d = 0; d < cnt[2]; ++d)
+        sum += __ldg(src + ((size_t)(beg[0] + a) * N1 + (beg[1] + c)) * N2 + (beg[2] + d));
+  out[idx] = __fdiv_rn(sum, (float)(cnt[0] * cnt[1] * cnt[2]));
+}
+
+// vorticity at offset (1, 1): (v[i+1][j] - v[i][j]) / dx - (u[i][j+1] - u[i][j]) / dy, periodic
+// (data/xarray_utils.py:155-163)
+__global__ void vorticity2d_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                   float* __restrict__ out, int N0, int N1, float dx, float dy, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % N1), i = (int)((idx / N1) % N0);
+  const size_t base = idx - (size_t)i * N1 - j;
+  const int ip = i + 1 == N0 ? 0 : i + 1, jp = j + 1 == N1 ? 0 : j + 1;
+  const float dv_dx = __fdiv_rn(__ldg(v + base + (size_t)ip * N1 + j) - __ldg(v + idx), dx);
+  const float du_dy = __fdiv_rn(__ldg(u + base + (size_t)i * N1 + jp) - __ldg(u + idx), dy);
+  out[idx] = dv_dx - du_dy;
+}
+
+
 }  // namespace
 
 int launch_axpy(cudaStream_t st, const float* x, int nterms, const float* const* y,
@@ -145,6 +187,26 @@ int launch_diag_2d(cudaStream_t st, const float* u, const float* v, int batch, i
   size_t blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 8) blocks = 148 * 8;
   diag2d_kernel<<<(int)blocks, threads, 0, st>>>(u, v, Nx, Ny, total, inv_hx, inv_hy, out4);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_downsample_component(cudaStream_t st, const float* in, float* out, int batch, int N0, int N1, int N2,
+                                int factor, int direction) {
+  const size_t total = (size_t)batch * (N0 / factor) * (N1 / factor) * (N2 > 1 ? N2 / factor : 1);
+  if (total == 0) return 0;
+  downsample_component_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, N0, N1, N2, factor,
+                                                                               direction, total);
+  count_launch();
+  CFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_vorticity_2d(cudaStream_t st, const float* u, const float* v, float* out, int batch, int N0, int N1,
+                        float dx, float dy) {
+  const size_t total = (size_t)batch * N0 * N1;
+  vorticity2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(u, v, out, N0, N1, dx, dy, total);
   count_launch();
   CFD_CUDA_OK(cudaGetLastError());
   return 0;

@@ -37,6 +37,10 @@ int launch_axpy(cudaStream_t, const float* x, int nterms, const float* const* y,
 int launch_diag_2d(cudaStream_t, const float* u, const float* v, int batch, int Nx, int Ny,
                    float inv_hx, float inv_hy, double* out4);
 int launch_scale(cudaStream_t, const float* x, float numer, float denom, float* out, size_t n);
+int launch_downsample_component(cudaStream_t st, const float* in, float* out, int batch, int N0, int N1, int N2,
+                                int factor, int direction);
+int launch_vorticity_2d(cudaStream_t st, const float* u, const float* v, float* out, int batch, int N0, int N1,
+                        float dx, float dy);
 int launch_explicit_2d_generic(cudaStream_t, const float* u, const float* v, float* us, float* vs, int batch,
                                int N0, int N1, const StepConsts& c, int dvdt_mode);
 void periodic_laplacian_eigenbasis(int N, double h, std::vector<double>* V, std::vector<double>* lam);
@@ -972,6 +976,35 @@ int cfd_transform_matmul(cfd_plan* p, cfd_stream stream, const float* in, float*
   if (p->impl != 1) return set_error_msg("cfd_transform_matmul needs a plan of the matmul implementation");
   return matmul_transform((cudaStream_t)stream, p->ndim, p->shape, p->batch, in, out, eigvecs, eigvecs_t, diag,
                           p->mm_w1, p->mm_w2);
+}
+
+int cfd_downsample_component(cfd_stream stream, const float* in, float* out, int ndim, const int64_t* shape,
+                             int batch, int direction, int factor) {
+  if (!in || !out || !shape) return set_error_msg("null argument");
+  if (ndim != 2 && ndim != 3) return set_error_msg("cfd_downsample_component: ndim must be 2 or 3");
+  if (direction < 0 || direction >= ndim) return set_error_msg("cfd_downsample_component: bad direction");
+  if (factor < 1 || batch < 1) return set_error_msg("cfd_downsample_component: factor and batch must be >= 1");
+  for (int j = 0; j < ndim; ++j)  // along `direction` the strided slice drops a remainder (resize.py:72)
+    if (shape[j] < 1 || (j != direction && shape[j] % factor))
+      return set_error_msg("`block_size` must divide `array.shape`");  // array_utils.py:159-160
+  DeviceGuard guard_;
+  int dev = 0;
+  if (int e = cfd_pointer_device(in, &dev)) return e;  // no CUDA device / host pointer: no CPU fallback
+  CFD_CUDA_OK(cudaSetDevice(dev));
+  return launch_downsample_component((cudaStream_t)stream, in, out, batch, (int)shape[0], (int)shape[1],
+                                     ndim == 3 ? (int)shape[2] : 1, factor, direction);
+}
+
+int cfd_vorticity_2d(cfd_stream stream, const float* u, const float* v, float* out, const int64_t* shape,
+                     int batch, double dx, double dy) {
+  if (!u || !v || !out || !shape) return set_error_msg("null argument");
+  if (shape[0] < 1 || shape[1] < 1 || batch < 1) return set_error_msg("cfd_vorticity_2d: bad shape");
+  DeviceGuard guard_;
+  int dev = 0;
+  if (int e = cfd_pointer_device(u, &dev)) return e;
+  CFD_CUDA_OK(cudaSetDevice(dev));
+  return launch_vorticity_2d((cudaStream_t)stream, u, v, out, batch, (int)shape[0], (int)shape[1], (float)dx,
+                             (float)dy);
 }
 
 int cfd_scale(cfd_plan* p, cfd_stream stream, const float* const* x, double numer, double denom,

@@ -19,6 +19,7 @@ from . import equations  # noqa: E402,F401
 from . import subgrid_models  # noqa: E402,F401
 from . import funcutils  # noqa: E402,F401
 from . import initial_conditions  # noqa: E402,F401
+from . import resize  # noqa: E402,F401
 from . import distributed  # noqa: E402,F401
 from ._engine import diagnostics, get_plan, clear_plans  # noqa: E402,F401
 from ._lib import DeviceArray, CfdError  # noqa: E402,F401

@@ -349,6 +349,31 @@ def rk_step(v, dt, h, tableau_a, tableau_b, density=1.0, viscosity=None, forcing
 
 
 # --------------------------------------------------------------------------- diagnostics
+def downsample_staggered_velocity_component(u, direction, factor):
+  """resize.py:72-74: slice_along_axis(u, direction, slice(factor - 1, None, factor)) then
+  block_reduce(w, block_size, mean) with block 1 along `direction` and `factor` elsewhere
+  (array_utils.py:136-166)."""
+  u = np.asarray(u)
+  sl = [slice(None)] * u.ndim
+  sl[direction] = slice(factor - 1, None, factor)
+  w = u[tuple(sl)]
+  new_shape, axes = [], []
+  for j, s_ in enumerate(w.shape):
+    b = 1 if j == direction else factor
+    if s_ % b:
+      raise ValueError('`block_size` must divide `array.shape`')
+    new_shape += [s_ // b, b]
+    axes.append(2 * j + 1)
+  return w.reshape(new_shape).mean(axis=tuple(axes), dtype=w.dtype if w.dtype.kind == 'f' else None)
+
+
+def vorticity_2d(u, v, dx, dy):
+  """data/xarray_utils.py:155-163: (roll(v, -1, x) - v) / dx - (roll(u, -1, y) - u) / dy."""
+  dv_dx = (np.roll(v, -1, axis=-2) - v) / v.dtype.type(dx)
+  du_dy = (np.roll(u, -1, axis=-1) - u) / u.dtype.type(dy)
+  return dv_dx - du_dy
+
+
 def diagnostics(v, h):
   """Mean kinetic energy, mean enstrophy (2-D), max |div|, max speed^2.
 

@@ -162,6 +162,29 @@ def run_implicit_case(name, shape, domain, seed, density, viscosity, dt, forcing
   print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
 
 
+def run_post_case(name, shape, seed, factors):
+  """resize.downsample_staggered_velocity (resize.py:187-222) of a random staggered field, every
+  component along its own direction, for each coarse-graining factor."""
+  from jax_cfd.base import resize
+  nd = len(shape)
+  domain = tuple((0.0, 2 * np.pi) for _ in shape)
+  grid = cfd.grids.Grid(shape, domain=domain)
+  rs = np.random.RandomState(seed)
+  v0 = [rs.standard_normal(shape).astype(np.float32) for _ in range(nd)]
+  rec = {'shape': np.asarray(shape), 'domain': np.asarray(domain), 'factors': np.asarray(factors)}
+  for i, a in enumerate(v0):
+    rec[f'v0_{i}'] = a
+  for f in factors:
+    dst = cfd.grids.Grid(tuple(n // f for n in shape), domain=domain)
+    out = resize.downsample_staggered_velocity(grid, dst, wrap(grid, v0))
+    for i, u in enumerate(out):
+      assert u.offset == grid.cell_faces[i] and u.grid == dst
+      rec[f'down{f}_{i}'] = np.asarray(u.data, np.float32)
+  path = os.path.join(OUT, name + '.npz')
+  np.savez_compressed(path, **rec)
+  print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
+
+
 def cases():
   """name -> thunk.  New fixtures are appended at the end; running without arguments rewrites every
   fixture (bit-identical on re-generation), `gen_golden.py NAME...` only the named ones."""
@@ -221,6 +244,9 @@ def cases():
   c['imp2d_48x36'] = lambda: run_implicit_case('imp2d_48x36', (48, 36), d2, 32, 1.0, 1e-2, 0.02, None, [1, 3])
   c['imp3d_16x16x32'] = lambda: run_implicit_case('imp3d_16x16x32', (16, 16, 32), d3, 33, 1.0, 2e-2, 0.03,
                                                   [('linear', -0.1)], [1, 2])
+  # flux-preserving coarse-graining of trajectories (resize.py:38-74, 187-222; "next" row f4)
+  c['post2d_32x48'] = lambda: run_post_case('post2d_32x48', (32, 48), 41, [2, 4])
+  c['post3d_8x12x16'] = lambda: run_post_case('post3d_8x12x16', (8, 12, 16), 42, [2, 4])
   return c
 
 

@@ -32,7 +32,7 @@ def load(name):
 
 def step_cases():
   return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                if not os.path.basename(p).startswith(('proj', 'imp')))
+                if not os.path.basename(p).startswith(('proj', 'imp', 'post')))
 
 
 def implicit_cases():

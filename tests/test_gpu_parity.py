@@ -669,3 +669,53 @@ def test_unsupported_shapes_and_implementations_raise_at_build_time(cfd):
     cfd.pressure.solve_fast_diag((), implementation='cg')
   with pytest.raises(NotImplementedError):
     cfd.equations.semi_implicit_navier_stokes(1.0, 1e-3, 0.01, grid, pressure_solve=lambda v: v)
+
+
+@pytest.mark.parametrize('name', ['post2d_32x48', 'post3d_8x12x16'])
+def test_downsample_matches_reference_golden(cfd, name):
+  """resize.downsample_staggered_velocity on the device ("next" row f4) vs the reference's own output;
+  offsets and the coarse grid as in resize.py:204-216."""
+  rec = gu.load(name)
+  nd = rec['ndim']
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(nd)])
+  for f in rec['factors']:
+    f = int(f)
+    dst = cfd.grids.Grid(tuple(n // f for n in rec['shape']), domain=rec['domain'])
+    out = cfd.resize.downsample_staggered_velocity(grid, dst, v)
+    for i, u in enumerate(out):
+      assert u.grid == dst and u.offset == grid.cell_faces[i]
+      np.testing.assert_allclose(np.asarray(u.data), rec[f'down{f}_{i}'], rtol=0, atol=1e-6)
+  # raw arrays with a leading batch axis, host in -> host out
+  batch = np.stack([rec['v0_0'], 2 * rec['v0_0']])
+  got = cfd.resize.downsample_staggered_velocity_component(batch, 0, 2, ndim=nd)
+  assert isinstance(got, np.ndarray) and got.shape == (2,) + tuple(n // 2 for n in rec['shape'])
+  np.testing.assert_allclose(got[1], 2 * rec['down2_0'], rtol=0, atol=2e-6)
+  with pytest.raises(ValueError):
+    cfd.resize.downsample_staggered_velocity_component(rec['v0_0'], 0, 5)  # 48 (or 12, 16) % 5 != 0
+
+
+def test_trajectory_post_process_runs_on_the_device(cfd):
+  """funcutils.trajectory(post_process=...) (funcutils.py:118-121) with the coarse-graining and the
+  vorticity evaluated on the device: frames are stacked in device memory and agree with the oracle
+  applied to the states of the same trajectory."""
+  rec = gu.load('k2d_64x32')
+  grid = cfd.grids.Grid(rec['shape'], domain=rec['domain'])
+  dst = cfd.grids.Grid((16, 8), domain=rec['domain'])
+  step = build_step(cfd, rec, grid)
+  v = wrap(cfd, grid, [rec[f'v0_{i}'] for i in range(2)])
+
+  def post(state):
+    coarse = cfd.resize.downsample_staggered_velocity(grid, dst, state)
+    return coarse + (cfd.resize.vorticity_2d(state),)
+
+  final, frames = cfd.funcutils.trajectory(cfd.funcutils.repeated(step, 2), 3, post_process=post)(v)
+  assert isinstance(frames[0].data, cfd.DeviceArray) and frames[0].data.shape == (3, 16, 8)
+  assert frames[2].data.shape == (3, 64, 32) and frames[2].offset == (1.0, 1.0)
+  # last frame vs the oracle on the final state
+  fin = to_np(final)
+  for i in range(2):
+    want = cfd_oracle.downsample_staggered_velocity_component(fin[i], i, 4)
+    np.testing.assert_allclose(np.asarray(frames[i].data[-1]), want, rtol=0, atol=1e-6)
+  wz = cfd_oracle.vorticity_2d(fin[0], fin[1], grid.step[0], grid.step[1])
+  np.testing.assert_allclose(np.asarray(frames[2].data[-1]), wz, rtol=0, atol=1e-5 * np.abs(wz).max())

@@ -120,3 +120,40 @@ def test_implicit_diffusion_step_matches_reference(name, prec):
     for i in range(rec['ndim']):
       assert v[i].dtype == dtype
       assert gu.rel_l2(v[i], rec[f'{prec}_v{n}_{i}']) < tol * max(1, n), (name, n, i)
+
+
+@pytest.mark.parametrize('name', ['post2d_32x48', 'post3d_8x12x16'])
+def test_downsample_matches_reference(name):
+  """resize.downsample_staggered_velocity (resize.py:187-222) run by the reference itself vs the
+  oracle's restatement (mean over the block in a possibly different order: 1e-6)."""
+  rec = gu.load(name)
+  for f in rec['factors']:
+    for i in range(rec['ndim']):
+      got = cfd_oracle.downsample_staggered_velocity_component(rec[f'v0_{i}'], i, int(f))
+      want = rec[f'down{int(f)}_{i}']
+      assert got.shape == want.shape and got.dtype == np.float32
+      np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+
+
+def test_downsample_kat_of_the_reference_test():
+  """resize_test.py:41-56: the reference's own known-answer vectors."""
+  u = np.arange(16.0).reshape(4, 4)
+  np.testing.assert_array_equal(cfd_oracle.downsample_staggered_velocity_component(u, 0, 2),
+                                [[4.5, 6.5], [12.5, 14.5]])
+  np.testing.assert_array_equal(cfd_oracle.downsample_staggered_velocity_component(u, 1, 2),
+                                [[3.0, 5.0], [11.0, 13.0]])
+  with pytest.raises(ValueError):  # array_utils.py:157-160
+    cfd_oracle.downsample_staggered_velocity_component(np.zeros((4, 6)), 0, 4)
+  # along `direction` itself the strided slice simply drops the remainder (resize.py:72)
+  assert cfd_oracle.downsample_staggered_velocity_component(np.zeros((6, 4)), 0, 4).shape == (1, 1)
+
+
+def test_downsampling_keeps_a_divergence_free_field_divergence_free():
+  """The property the procedure exists for (resize.py:49-51)."""
+  rec = gu.load('proj2d_64x32')
+  v = [rec['f32_proj_0'].astype(np.float64), rec['f32_proj_1'].astype(np.float64)]
+  h = rec['h']
+  assert np.abs(cfd_oracle.divergence(v, h)).max() < 1e-4
+  f = 4
+  vc = [cfd_oracle.downsample_staggered_velocity_component(a, i, f) for i, a in enumerate(v)]
+  assert np.abs(cfd_oracle.divergence(vc, tuple(f * x for x in h))).max() < 1e-4
