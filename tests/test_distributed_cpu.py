@@ -25,6 +25,17 @@ def test_partition_arithmetic():
     D.check_decomposition((8192, 64), 4)     # 8 lines per rank
   with pytest.raises(NotImplementedError):
     D.check_decomposition((65536, 32768), 8)
+  # 3-D slabs (config #5): the constraints of cfd_dist_plan_create_nd, same messages
+  D.check_decomposition((512, 512, 512), 8)
+  D.check_decomposition((64, 32, 64), 2)
+  with pytest.raises(ValueError, match='power of two >= 16 planes'):
+    D.check_decomposition((64, 128, 64), 8)        # 8 planes per rank
+  with pytest.raises(ValueError, match='N2 % 64'):
+    D.check_decomposition((128, 128, 32), 2)       # the marching stencil's tile is 8 x 64
+  with pytest.raises(ValueError, match='16 x the number of ranks'):
+    D.check_decomposition((256, 64, 64), 8)        # (kz, ky) lines must split evenly over the ranks
+  with pytest.raises(ValueError):
+    D.check_decomposition((512, 512, 512), 3)
 
 
 def _worker(rank, world, port, q):
