@@ -188,6 +188,8 @@ cfft_lines_gather_kernel(const float2* __restrict__ B, float2* __restrict__ A, i
 }
 
 // ---- X: lines B[line][0..M) with line = (b * (Mz + 1) + kz) * N1 + ky : fwd * D * inv in place ---------
+// (no minimum-blocks hint: measured at 512^3 with 512-point lines, 0.307 ms as is -- 127 registers,
+// two CTAs per SM -- against 0.332 / 0.396 ms capped at 80 / 64 registers, which spill)
 template <int LM, int LINES, bool FASTD>
 __global__ void __launch_bounds__(LINES * FftPlan<LM>::G)
 xlines3_kernel(LinePeers peers, int lnloc, size_t line_begin, int N1, int NZP, const float2* __restrict__ tw,
@@ -332,17 +334,19 @@ __global__ void correct3d_kernel(const float* __restrict__ us, const float* __re
 // Rows per CTA of the 3-D row / line kernels are capped at CFD_FFT3_ROWS = 8 | 16 | 32.  Default 16:
 // with rows_for's maximum of 32 a CTA of 512-point lines is 1024 threads and 139 KB, one per SM;
 // 16 rows (512 threads, 70 KB) let three independent CTAs share an SM and overlap each other's
-// load / exchange / store phases -- measured at 512^3: the four sweeps 1.12 -> 0.95 ms.
-static int rows3_cap() {
+// load / exchange / store phases -- measured at 512^3: the four sweeps 1.12 -> 0.95 ms (inverse y
+// sweep alone: 0.326 / 0.287 / 0.249 ms with 32 / 16 / 8 rows).
+static int rows3_cap(int gather) {
   static const int v = [] {
     const char* e = getenv("CFD_FFT3_ROWS");
-    return e ? atoi(e) : 16;
+    return e ? atoi(e) : 0;
   }();
-  return v;
+  if (v > 0) return v;
+  return gather ? 8 : 16;  // the transposed gather of the inverse y sweep likes even smaller CTAs
 }
 
 // generic launcher: KERNEL<LM, ROWS> over (count / ROWS, planes) CTAs, ROWS from rows_for(LM)
-#define CFD_ROWS_LAUNCH(KERNEL, count, planes, ...)                                              \
+#define CFD_ROWS_LAUNCH(KERNEL, CAP, count, planes, ...)                                              \
   do {                                                                                           \
     constexpr int ROWS_MAX = rows_for(LM);                                                       \
     using P = FftPlan<LM>;                                                                       \
@@ -356,9 +360,9 @@ static int rows3_cap() {
       CFD_CUDA_OK(cudaGetLastError());                                                           \
       return 0;                                                                                  \
     };                                                                                           \
-    if ((count) % ROWS_MAX == 0 && rows3_cap() >= ROWS_MAX) return go(std::integral_constant<int, ROWS_MAX>{}); \
+    if ((count) % ROWS_MAX == 0 && (CAP) >= ROWS_MAX) return go(std::integral_constant<int, ROWS_MAX>{}); \
     if constexpr (ROWS_MAX > 8) {                                                                \
-      if ((count) % 8 == 0 && rows3_cap() <= 8) return go(std::integral_constant<int, 8>{});     \
+      if ((count) % 8 == 0 && (CAP) <= 8) return go(std::integral_constant<int, 8>{});     \
     }                                                                                            \
     if constexpr (ROWS_MAX > 16) {                                                               \
       if ((count) % 16 == 0) return go(std::integral_constant<int, 16>{});                       \
@@ -369,22 +373,22 @@ static int rows3_cap() {
 template <int LM>
 int launch_rfft_rows3_t(cudaStream_t st, const float* rhs, float2* T, int batch, int NR,
                         const float2* tw, const float2* rtw) {
-  CFD_ROWS_LAUNCH(rfft_rows3_kernel, NR, batch, rhs, T, NR, tw, rtw);
+  CFD_ROWS_LAUNCH(rfft_rows3_kernel, rows3_cap(0), NR, batch, rhs, T, NR, tw, rtw);
 }
 template <int LM>
 int launch_irfft_rows3_t(cudaStream_t st, const float2* T, float* q, int batch, int NR,
                          const float2* tw, const float2* rtw) {
-  CFD_ROWS_LAUNCH(irfft_rows3_kernel, NR, batch, T, q, NR, tw, rtw);
+  CFD_ROWS_LAUNCH(irfft_rows3_kernel, rows3_cap(0), NR, batch, T, q, NR, tw, rtw);
 }
 template <int LM>
 int launch_lines_scatter_t(cudaStream_t st, const float2* A, float2* B, int planes, int NL,
                            const float2* tw) {
-  CFD_ROWS_LAUNCH(cfft_lines_scatter_kernel, NL, planes, A, B, NL, tw);
+  CFD_ROWS_LAUNCH(cfft_lines_scatter_kernel, rows3_cap(0), NL, planes, A, B, NL, tw);
 }
 template <int LM>
 int launch_lines_gather_t(cudaStream_t st, const float2* B, float2* A, int planes, int NL,
                           const float2* tw) {
-  CFD_ROWS_LAUNCH(cfft_lines_gather_kernel, NL, planes, B, A, NL, tw);
+  CFD_ROWS_LAUNCH(cfft_lines_gather_kernel, rows3_cap(1), NL, planes, B, A, NL, tw);
 }
 
 template <int LM>
