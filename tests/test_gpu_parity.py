@@ -719,3 +719,25 @@ def test_trajectory_post_process_runs_on_the_device(cfd):
     np.testing.assert_allclose(np.asarray(frames[i].data[-1]), want, rtol=0, atol=1e-6)
   wz = cfd_oracle.vorticity_2d(fin[0], fin[1], grid.step[0], grid.step[1])
   np.testing.assert_allclose(np.asarray(frames[2].data[-1]), wz, rtol=0, atol=1e-5 * np.abs(wz).max())
+
+
+def test_readme_example_flow(cfd):
+  """The user-facing flow of README.md at a small size: device initial condition, repeated steps in
+  one call, a trajectory with a device post-process, diagnostics."""
+  grid = cfd.grids.Grid((512, 512), domain=((0, 2 * np.pi), (0, 2 * np.pi)))
+  v0 = cfd.initial_conditions.filtered_velocity_field(0, grid, maximum_velocity=7.0, peak_wavenumber=4)
+  dt = cfd.equations.stable_time_step(7.0, 0.5, 1e-3, grid)
+  forcing = cfd.forcings.sum_forcings(cfd.forcings.kolmogorov_forcing(grid, scale=1.0, k=4),
+                                      cfd.forcings.linear_forcing(grid, -0.1))
+  step_fn = cfd.equations.semi_implicit_navier_stokes(density=1.0, viscosity=1e-3, dt=dt, grid=grid,
+                                                      forcing=forcing)
+  v = cfd.funcutils.repeated(step_fn, 20)(v0)
+  dst = cfd.grids.Grid((64, 64), domain=grid.domain)
+  coarse = lambda s: cfd.resize.downsample_staggered_velocity(grid, dst, s)
+  v, frames = cfd.funcutils.trajectory(cfd.funcutils.repeated(step_fn, 5), 4, post_process=coarse)(v)
+  assert frames[0].data.shape == (4, 64, 64) and frames[0].grid == dst
+  d = cfd.diagnostics(v)
+  assert np.isfinite(d['kinetic_energy']) and d['max_abs_div'] < 2e-3
+  # the coarse frames of a divergence-free state are divergence free on the coarse grid
+  last = [np.asarray(f.data[-1]) for f in frames]
+  assert np.abs(cfd_oracle.divergence(last, dst.step)).max() < 2e-3
